@@ -1,0 +1,606 @@
+// Host orchestration + extern "C" shim of the B200 LDL^T backend (see include/b200ldlt.h).
+// One translation unit: the kernels are included so nvcc sees launch sites and definitions together.
+#include "../../include/b200ldlt.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "factor_kernels.cu"
+#include "solve_kernels.cu"
+#include "symbolic.hpp"
+
+namespace b200 {
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, count * sizeof(T));
+  }
+  template <class U>
+  cudaError_t upload(const std::vector<U>& v, cudaStream_t st) {
+    std::vector<T> tmp(v.begin(), v.end());
+    cudaError_t e = alloc(tmp.size());
+    if (e != cudaSuccess || tmp.empty()) return e;
+    e = cudaMemcpyAsync(p, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);  // tmp dies here
+  }
+};
+
+struct LevelPlan {
+  // big fronts of the level: [big_off, big_off+big_cnt) in front_list
+  int big_off = 0, big_cnt = 0, big_kmax = 0, big_fmax = 0, big_rmax = 0, big_chmax = 0;
+  long long big_entmax = 0, big_zero_max = 0;
+  struct Bucket { int off, cnt, fmax, kmax, threads; size_t smem; };
+  std::vector<Bucket> small;
+  int all_off = 0, all_cnt = 0, fmax = 0;  // whole level (solve)
+};
+
+struct Solver {
+  b200ldlt_options opt;
+  std::string err;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  int n = 0, nnz = 0;
+  std::vector<int> irn, jcn;
+  double* h_vals = nullptr;      // pinned
+  double* h_rhs = nullptr;       // pinned staging (n * rhs_cap)
+  int rhs_cap = 0;
+  int* h_counters = nullptr;     // pinned
+  bool analysed = false, factored = false, have_dev_vals = false;
+  Symbolic S;
+  std::vector<LevelPlan> plan;
+  b200ldlt_info info;
+  int num_neg = 0;
+  double pivtol = 1e-8;
+
+  // device
+  DevBuf<int> d_sn_start, d_sn_parent, d_rows, d_rel, d_child_ptr, d_child_idx, d_front_list, d_perm;
+  DevBuf<int> d_useg_src, d_u_row, d_u_col, d_irn, d_jcn;
+  DevBuf<long long> d_rows_ptr, d_uent_ptr, d_u_dst64, d_L_off, d_cb_off, d_useg_ptr;
+  DevBuf<unsigned> d_u_dst;
+  DevBuf<double> d_vals, d_uval, d_L, d_W, d_CB, d_dinv, d_doff, d_scale, d_x, d_cbv, d_rhs, d_res;
+  DevBuf<int> d_ptype, d_lperm, d_bperm, d_counters;
+  DevBuf<unsigned long long> d_rmax;
+  DevSym DS;
+  DevNum DN;
+  int launches = 0;
+
+  ~Solver() {
+    if (h_vals) cudaFreeHost(h_vals);
+    if (h_rhs) cudaFreeHost(h_rhs);
+    if (h_counters) cudaFreeHost(h_counters);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+};
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      sv->err = std::string(#call) + ": " + cudaGetErrorString(e__);                     \
+      if (sv->opt.verbose) fprintf(stderr, "[b200ldlt] CUDA error: %s\n", sv->err.c_str()); \
+      return B200LDLT_FATAL_ERROR;                                                       \
+    }                                                                                    \
+  } while (0)
+
+static int run_analysis(Solver* sv, const double* vals) {
+  AnalyseOptions ao;
+  ao.ordering = sv->opt.ordering;
+  ao.pair_saddle = sv->opt.pair_saddle;
+  ao.leaf_k = sv->opt.leaf_k;
+  ao.relax_frac = sv->opt.relax_frac;
+  std::string e;
+  int rc = analyse(sv->n, sv->nnz, sv->irn.data(), sv->jcn.data(), vals, ao, sv->S, e);
+  if (rc != 0) { sv->err = e; return B200LDLT_FATAL_ERROR; }
+  Symbolic& S = sv->S;
+  cudaStream_t st = sv->stream;
+  CU(sv->d_sn_start.upload(S.sn_start, st));
+  CU(sv->d_sn_parent.upload(S.sn_parent, st));
+  CU(sv->d_rows_ptr.upload(S.rows_ptr, st));
+  CU(sv->d_rows.upload(S.rows, st));
+  CU(sv->d_rel.upload(S.rel, st));
+  CU(sv->d_child_ptr.upload(S.child_ptr, st));
+  CU(sv->d_child_idx.upload(S.child_idx, st));
+  CU(sv->d_uent_ptr.upload(S.uent_ptr, st));
+  CU(sv->d_u_dst.upload(S.u_dst, st));
+  CU(sv->d_u_dst64.upload(S.u_dst64, st));
+  CU(sv->d_L_off.upload(S.L_off, st));
+  CU(sv->d_cb_off.upload(S.cb_off, st));
+  CU(sv->d_useg_ptr.upload(S.useg_ptr, st));
+  CU(sv->d_useg_src.upload(S.useg_src, st));
+  CU(sv->d_u_row.upload(S.u_row, st));
+  CU(sv->d_u_col.upload(S.u_col, st));
+  CU(sv->d_perm.upload(S.perm, st));
+  CU(sv->d_irn.upload(sv->irn, st));
+  CU(sv->d_jcn.upload(sv->jcn, st));
+  const int n = S.n;
+  CU(sv->d_vals.alloc(sv->nnz));
+  CU(sv->d_uval.alloc(S.nnz_u));
+  CU(sv->d_L.alloc(S.L_off[S.nsn]));
+  CU(sv->d_W.alloc(S.L_off[S.nsn]));
+  CU(sv->d_CB.alloc(std::max<int64_t>(S.cb_off[S.nsn], 1)));
+  CU(sv->d_dinv.alloc(n)); CU(sv->d_doff.alloc(n)); CU(sv->d_scale.alloc(n));
+  CU(sv->d_x.alloc(n)); CU(sv->d_rhs.alloc(n)); CU(sv->d_res.alloc(n));
+  CU(sv->d_cbv.alloc(std::max<size_t>(S.rows.size(), 1)));
+  CU(sv->d_ptype.alloc(n)); CU(sv->d_lperm.alloc(n)); CU(sv->d_bperm.alloc(n));
+  CU(sv->d_counters.alloc(CNT_N));
+  CU(sv->d_rmax.alloc(n));
+  CU(cudaMemsetAsync(sv->d_rmax.p, 0, n * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(sv->d_L.p, 0, sv->d_L.n * sizeof(double), st));
+
+  DevSym& D = sv->DS;
+  D.n = n; D.nsn = S.nsn;
+  D.sn_start = sv->d_sn_start.p; D.sn_parent = sv->d_sn_parent.p;
+  D.rows_ptr = sv->d_rows_ptr.p; D.rows = sv->d_rows.p; D.rel = sv->d_rel.p;
+  D.child_ptr = sv->d_child_ptr.p; D.child_idx = sv->d_child_idx.p;
+  D.uent_ptr = sv->d_uent_ptr.p; D.u_dst = sv->d_u_dst.p; D.u_dst64 = sv->d_u_dst64.p;
+  D.L_off = sv->d_L_off.p; D.cb_off = sv->d_cb_off.p;
+  DevNum& N = sv->DN;
+  N.L = sv->d_L.p; N.W = sv->d_W.p; N.CB = sv->d_CB.p; N.uval = sv->d_uval.p;
+  N.dinv = sv->d_dinv.p; N.doff = sv->d_doff.p; N.ptype = sv->d_ptype.p;
+  N.lperm = sv->d_lperm.p; N.bperm = sv->d_bperm.p; N.counters = sv->d_counters.p;
+
+  // ---- launch plan: per level, big fronts first then small ones by descending order --------
+  const int smax = sv->opt.smem_front_max;
+  std::vector<int> fl;
+  fl.reserve(S.nsn);
+  sv->plan.assign(S.nlevels, LevelPlan());
+  for (int l = 0; l < S.nlevels; ++l) {
+    LevelPlan& P = sv->plan[l];
+    P.all_off = (int)fl.size();
+    P.big_off = (int)fl.size();
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      int s = S.level_sn[q];
+      P.fmax = std::max(P.fmax, S.f(s));
+      if (S.f(s) > smax) {
+        fl.push_back(s);
+        P.big_cnt++;
+        P.big_kmax = std::max(P.big_kmax, S.k(s));
+        P.big_fmax = std::max(P.big_fmax, S.f(s));
+        P.big_rmax = std::max(P.big_rmax, S.r(s));
+        P.big_chmax = std::max(P.big_chmax, S.child_ptr[s + 1] - S.child_ptr[s]);
+        P.big_entmax = std::max<long long>(P.big_entmax, S.uent_ptr[s + 1] - S.uent_ptr[s]);
+        P.big_zero_max = std::max<long long>(P.big_zero_max, (long long)S.f(s) * S.k(s) + (long long)S.r(s) * S.r(s));
+      }
+    }
+    // small fronts (level_sn is sorted by f descending inside a level)
+    const int lim[3] = {64, 32, 0};
+    const int thr[3] = {256, 128, 64};
+    int b = 0;
+    LevelPlan::Bucket cur{(int)fl.size(), 0, 0, 0, thr[0], 0};
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      int s = S.level_sn[q];
+      int f = S.f(s);
+      if (f > smax) continue;
+      while (b < 2 && f <= lim[b]) {
+        if (cur.cnt) P.small.push_back(cur);
+        ++b;
+        cur = LevelPlan::Bucket{(int)fl.size(), 0, 0, 0, thr[b], 0};
+      }
+      fl.push_back(s);
+      cur.cnt++;
+      cur.fmax = std::max(cur.fmax, f);
+      cur.kmax = std::max(cur.kmax, S.k(s));
+    }
+    if (cur.cnt) P.small.push_back(cur);
+    for (auto& bk : P.small) {
+      size_t ld = (size_t)(bk.fmax | 1);
+      bk.smem = (ld * bk.fmax + 2 * (size_t)bk.fmax) * sizeof(double) + (2 * (size_t)bk.kmax + 8) * sizeof(int);
+      // k can exceed kmax of another front with smaller f only inside the bucket; kmax covers the bucket
+    }
+    P.all_cnt = (int)fl.size() - P.all_off;
+  }
+  CU(sv->d_front_list.upload(fl, st));
+  CU(cudaFuncSetAttribute(k_front_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute(k_bwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaStreamSynchronize(st));
+
+  b200ldlt_info& I = sv->info;
+  I.n = n; I.nnz_in = S.nnz_in; I.nnz_unique = S.nnz_u;
+  I.nsupernodes = S.nsn; I.nlevels = S.nlevels; I.max_front = S.max_front; I.max_pivots = S.max_k;
+  I.n_saddle = S.n_saddle; I.n_pairs = S.n_pairs;
+  I.nnz_L = S.nnzL; I.nnz_L_true = S.nnzL_true;
+  I.L_bytes = (int64_t)sv->d_L.n * 8; I.cb_bytes = (int64_t)sv->d_CB.n * 8;
+  I.flops_panel = S.flops_panel; I.flops_schur = S.flops_schur;
+  I.t_order_s = S.t_order; I.t_symbolic_s = S.t_symbolic;
+  if (sv->opt.verbose)
+    fprintf(stderr,
+            "[b200ldlt] analyse: n=%d nnz=%lld uniq=%lld saddle=%d pairs=%d nsn=%d levels=%d maxfront=%d maxk=%d "
+            "nnzL=%lld (true %lld) flops panel=%.3g schur=%.3g cb=%.1f MB  order %.2fs symbolic %.2fs\n",
+            n, (long long)S.nnz_in, (long long)S.nnz_u, S.n_saddle, S.n_pairs, S.nsn, S.nlevels, S.max_front,
+            S.max_k, (long long)S.nnzL, (long long)S.nnzL_true, S.flops_panel, S.flops_schur,
+            S.cb_total * 8.0 / 1e6, S.t_order, S.t_symbolic);
+  sv->analysed = true;
+  return B200LDLT_SUCCESS;
+}
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// enqueue the whole numeric factorisation of the values in d_vals
+static int enqueue_factor(Solver* sv) {
+  Symbolic& S = sv->S;
+  cudaStream_t st = sv->stream;
+  DevSym& D = sv->DS;
+  DevNum& N = sv->DN;
+  N.u = sv->pivtol;
+  N.tiny = sv->opt.tiny;
+  const int n = S.n;
+  const long long nu = S.nnz_u;
+  const int* fl = sv->d_front_list.p;
+  int& L = sv->launches;
+  L = 0;
+  CU(cudaMemsetAsync(sv->d_counters.p, 0, CNT_N * sizeof(int), st));
+  k_sum_dups<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_useg_ptr.p, sv->d_useg_src.p, sv->d_vals.p, sv->d_uval.p); ++L;
+  k_fill<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_scale.p, 1.0); ++L;
+  for (int sw = 0; sw < sv->opt.scaling; ++sw) {
+    k_rowmax<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_u_row.p, sv->d_u_col.p, sv->d_uval.p, sv->d_scale.p, sv->d_rmax.p); ++L;
+    k_scale_update<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_scale.p, sv->d_rmax.p); ++L;
+  }
+  if (sv->opt.scaling > 0) {
+    k_apply_scale<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_u_row.p, sv->d_u_col.p, sv->d_scale.p, sv->d_uval.p); ++L;
+  }
+  for (int l = 0; l < S.nlevels; ++l) {
+    const LevelPlan& P = sv->plan[l];
+    if (P.big_cnt) {
+      const int* bl = fl + P.big_off;
+      k_big_zero<<<dim3(std::min<unsigned>(cdiv(P.big_zero_max, 1024), 592), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
+      k_big_assemble<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_entmax, 256), 64)), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
+      for (int q = 0; q < P.big_chmax; ++q) {
+        k_big_extend_add<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_fmax, 8), 128)), P.big_cnt), 256, 0, st>>>(D, N, bl, q); ++L;
+      }
+    }
+    for (const auto& bk : P.small) {
+      k_front_smem<<<bk.cnt, bk.threads, bk.smem, st>>>(D, N, fl + bk.off); ++L;
+    }
+    if (P.big_cnt) {
+      const int* bl = fl + P.big_off;
+      for (int jb = 0; jb < P.big_kmax; jb += NB) {
+        k_big_diag<<<P.big_cnt, 128, 0, st>>>(D, N, bl, jb); ++L;
+        int rows_below = P.big_fmax - jb;  // upper bound
+        k_big_trsm<<<dim3(std::max(1u, cdiv(rows_below, 128)), P.big_cnt), 128, 0, st>>>(D, N, bl, jb); ++L;
+        int rem_k = P.big_kmax - jb - NB;
+        if (rem_k > 0) {
+          k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, st>>>(D, N, bl, jb); ++L;
+        }
+      }
+      if (P.big_rmax > 0) {
+        k_big_schur<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
+      }
+    }
+  }
+  CU(cudaGetLastError());
+  return B200LDLT_SUCCESS;
+}
+
+static int finish_factor(Solver* sv, int check_inertia, int expected_neg, int* num_neg) {
+  cudaStream_t st = sv->stream;
+  CU(cudaEventRecord(sv->ev1, st));
+  CU(cudaMemcpyAsync(sv->h_counters, sv->d_counters.p, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, sv->ev0, sv->ev1);
+  b200ldlt_info& I = sv->info;
+  I.ms_factor_gpu = ms;
+  I.launches_factor = sv->launches;
+  I.num_neg = sv->h_counters[CNT_NEG];
+  I.num_forced = sv->h_counters[CNT_FORCED];
+  I.num_tiny = sv->h_counters[CNT_TINY];
+  I.num_growth = sv->h_counters[CNT_GROWTH];
+  I.num_2x2 = sv->h_counters[CNT_2X2];
+  sv->num_neg = I.num_neg;
+  if (num_neg) *num_neg = I.num_neg;
+  sv->factored = true;
+  if (sv->opt.verbose > 1)
+    fprintf(stderr, "[b200ldlt] factor: %.3f ms, %d launches, neg=%d 2x2=%d forced=%d tiny=%d growth=%d (u=%g)\n", ms,
+            sv->launches, I.num_neg, I.num_2x2, I.num_forced, I.num_tiny, I.num_growth, sv->pivtol);
+  if (I.num_tiny > 0) return B200LDLT_SINGULAR;
+  if (check_inertia && I.num_neg != expected_neg) return B200LDLT_WRONG_INERTIA;
+  return B200LDLT_SUCCESS;
+}
+
+static int do_factor(Solver* sv, const double* d_vals_ext, bool from_host, int check_inertia, int expected_neg,
+                     int* num_neg) {
+  if (num_neg) *num_neg = -1;
+  if (sv->n <= 0) { sv->err = "factor before analyse"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  if (!sv->analysed) {
+    std::vector<double> hv;
+    const double* vals = sv->h_vals;
+    if (!from_host && d_vals_ext) {
+      hv.resize(sv->nnz);
+      CU(cudaMemcpy(hv.data(), d_vals_ext, sv->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+      vals = hv.data();
+    }
+    int rc = run_analysis(sv, vals);
+    if (rc != B200LDLT_SUCCESS) return rc;
+  }
+  cudaStream_t st = sv->stream;
+  CU(cudaEventRecord(sv->ev0, st));
+  if (from_host)
+    CU(cudaMemcpyAsync(sv->d_vals.p, sv->h_vals, sv->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+  else if (d_vals_ext && d_vals_ext != sv->d_vals.p)
+    CU(cudaMemcpyAsync(sv->d_vals.p, d_vals_ext, sv->nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  sv->have_dev_vals = true;
+  if (!from_host) CU(cudaEventRecord(sv->ev0, st));  // device-resident timing excludes the staging copy
+  int rc = enqueue_factor(sv);
+  if (rc != B200LDLT_SUCCESS) return rc;
+  return finish_factor(sv, check_inertia, expected_neg, num_neg);
+}
+
+static int enqueue_solve(Solver* sv, const double* d_b, double* d_out) {
+  Symbolic& S = sv->S;
+  cudaStream_t st = sv->stream;
+  const int n = S.n;
+  const int* fl = sv->d_front_list.p;
+  int& L = sv->launches;
+  k_rhs_in<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, d_b, sv->d_x.p); ++L;
+  for (int l = 0; l < S.nlevels; ++l) {
+    const LevelPlan& P = sv->plan[l];
+    int threads = P.fmax <= 64 ? 64 : (P.fmax <= 256 ? 128 : 512);
+    k_fwd_front<<<P.all_cnt, threads, 2 * (size_t)P.fmax * sizeof(double), st>>>(sv->DS, sv->DN, fl + P.all_off, sv->d_x.p, sv->d_cbv.p); ++L;
+  }
+  for (int l = S.nlevels - 1; l >= 0; --l) {
+    const LevelPlan& P = sv->plan[l];
+    int threads = P.fmax <= 64 ? 64 : (P.fmax <= 256 ? 128 : 512);
+    k_bwd_front<<<P.all_cnt, threads, (size_t)P.fmax * sizeof(double), st>>>(sv->DS, sv->DN, fl + P.all_off, sv->d_x.p); ++L;
+  }
+  k_sol_out<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, sv->d_x.p, d_out); ++L;
+  CU(cudaGetLastError());
+  return B200LDLT_SUCCESS;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+void b200ldlt_default_options(b200ldlt_options* o) {
+  memset(o, 0, sizeof(*o));
+  o->device = -1;
+  o->stream = nullptr;
+  o->ordering = 0;
+  o->pair_saddle = 1;
+  o->leaf_k = 32;
+  o->relax_frac = 0.15;
+  o->scaling = 2;
+  o->pivtol = 1e-8;
+  o->pivtolmax = 1e-4;
+  o->tiny = 1e-20;
+  o->smem_front_max = 128;
+  o->use_graph = 0;
+  o->verbose = 0;
+}
+
+b200ldlt_handle b200ldlt_create(const b200ldlt_options* opt) {
+  Solver* sv = new Solver();
+  if (opt) sv->opt = *opt; else b200ldlt_default_options(&sv->opt);
+  if (sv->opt.smem_front_max > 160) sv->opt.smem_front_max = 160;
+  if (sv->opt.smem_front_max < 8) sv->opt.smem_front_max = 8;
+  sv->pivtol = sv->opt.pivtol;
+  memset(&sv->info, 0, sizeof(sv->info));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "[b200ldlt] FATAL: no usable CUDA device (%s); this backend has no CPU fallback\n",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    delete sv;
+    return nullptr;
+  }
+  if (sv->opt.device >= 0) sv->dev = sv->opt.device; else cudaGetDevice(&sv->dev);
+  if (cudaSetDevice(sv->dev) != cudaSuccess) {
+    fprintf(stderr, "[b200ldlt] FATAL: cannot select CUDA device %d\n", sv->dev);
+    delete sv;
+    return nullptr;
+  }
+  if (sv->opt.stream) sv->stream = (cudaStream_t)sv->opt.stream;
+  else { cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking); sv->own_stream = true; }
+  cudaEventCreate(&sv->ev0);
+  cudaEventCreate(&sv->ev1);
+  cudaHostAlloc((void**)&sv->h_counters, CNT_N * sizeof(int), cudaHostAllocDefault);
+  return (b200ldlt_handle)sv;
+}
+
+void b200ldlt_destroy(b200ldlt_handle h) {
+  Solver* sv = (Solver*)h;
+  if (!sv) return;
+  cudaSetDevice(sv->dev);
+  if (sv->stream) cudaStreamSynchronize(sv->stream);
+  delete sv;
+}
+
+const char* b200ldlt_last_error(b200ldlt_handle h) { return h ? ((Solver*)h)->err.c_str() : "null handle"; }
+
+int b200ldlt_analyse(b200ldlt_handle h, int dim, int nonzeros, const int* irn, const int* jcn) {
+  Solver* sv = (Solver*)h;
+  if (!sv) return B200LDLT_FATAL_ERROR;
+  if (dim <= 0 || nonzeros < 0 || (nonzeros > 0 && (!irn || !jcn))) { sv->err = "analyse: bad arguments"; return B200LDLT_FATAL_ERROR; }
+  for (int e = 0; e < nonzeros; ++e)
+    if (irn[e] < 1 || irn[e] > dim || jcn[e] < 1 || jcn[e] > dim) { sv->err = "analyse: index out of range"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  sv->n = dim; sv->nnz = nonzeros;
+  sv->irn.assign(irn, irn + nonzeros);
+  sv->jcn.assign(jcn, jcn + nonzeros);
+  if (sv->h_vals) { cudaFreeHost(sv->h_vals); sv->h_vals = nullptr; }
+  CU(cudaHostAlloc((void**)&sv->h_vals, std::max<size_t>(nonzeros, 1) * sizeof(double), cudaHostAllocDefault));
+  memset(sv->h_vals, 0, std::max<size_t>(nonzeros, 1) * sizeof(double));
+  sv->analysed = false; sv->factored = false; sv->have_dev_vals = false;
+  return B200LDLT_SUCCESS;
+}
+
+double* b200ldlt_values_ptr(b200ldlt_handle h) { return h ? ((Solver*)h)->h_vals : nullptr; }
+
+int b200ldlt_analyse_now(b200ldlt_handle h, const double* vals) {
+  Solver* sv = (Solver*)h;
+  if (!sv || sv->n <= 0) return B200LDLT_FATAL_ERROR;
+  CU(cudaSetDevice(sv->dev));
+  return run_analysis(sv, vals);
+}
+
+int b200ldlt_factor(b200ldlt_handle h, int check_inertia, int expected_neg, int* num_neg) {
+  Solver* sv = (Solver*)h;
+  if (!sv) return B200LDLT_FATAL_ERROR;
+  return do_factor(sv, nullptr, true, check_inertia, expected_neg, num_neg);
+}
+
+int b200ldlt_factor_device(b200ldlt_handle h, const double* d_vals, int check_inertia, int expected_neg, int* num_neg) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !d_vals) return B200LDLT_FATAL_ERROR;
+  return do_factor(sv, d_vals, false, check_inertia, expected_neg, num_neg);
+}
+
+int b200ldlt_refactor(b200ldlt_handle h, int check_inertia, int expected_neg, int* num_neg) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->analysed || !sv->have_dev_vals) { if (sv) sv->err = "refactor: no matrix on the device"; return B200LDLT_FATAL_ERROR; }
+  return do_factor(sv, sv->d_vals.p, false, check_inertia, expected_neg, num_neg);
+}
+
+int b200ldlt_solve_device(b200ldlt_handle h, int nrhs, double* d_rhs) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->factored) { if (sv) sv->err = "solve before factor"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  cudaStream_t st = sv->stream;
+  sv->launches = 0;
+  CU(cudaEventRecord(sv->ev0, st));
+  for (int c = 0; c < nrhs; ++c) {
+    double* col = d_rhs + (size_t)c * sv->n;
+    int rc = enqueue_solve(sv, col, col);
+    if (rc != B200LDLT_SUCCESS) return rc;
+  }
+  CU(cudaEventRecord(sv->ev1, st));
+  CU(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&sv->info.ms_solve_gpu, sv->ev0, sv->ev1);
+  sv->info.launches_solve = sv->launches;
+  return B200LDLT_SUCCESS;
+}
+
+int b200ldlt_solve(b200ldlt_handle h, int nrhs, double* rhs) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->factored) { if (sv) sv->err = "solve before factor"; return B200LDLT_FATAL_ERROR; }
+  if (nrhs <= 0) return B200LDLT_SUCCESS;
+  CU(cudaSetDevice(sv->dev));
+  cudaStream_t st = sv->stream;
+  const size_t n = sv->n;
+  if (nrhs > sv->rhs_cap) {
+    if (sv->h_rhs) cudaFreeHost(sv->h_rhs);
+    sv->h_rhs = nullptr;
+    CU(cudaHostAlloc((void**)&sv->h_rhs, n * nrhs * sizeof(double), cudaHostAllocDefault));
+    CU(sv->d_rhs.alloc(n * nrhs));
+    sv->rhs_cap = nrhs;
+  }
+  memcpy(sv->h_rhs, rhs, n * nrhs * sizeof(double));
+  sv->launches = 0;
+  CU(cudaEventRecord(sv->ev0, st));
+  CU(cudaMemcpyAsync(sv->d_rhs.p, sv->h_rhs, n * nrhs * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (int c = 0; c < nrhs; ++c) {
+    double* col = sv->d_rhs.p + (size_t)c * n;
+    int rc = enqueue_solve(sv, col, col);
+    if (rc != B200LDLT_SUCCESS) return rc;
+  }
+  CU(cudaMemcpyAsync(sv->h_rhs, sv->d_rhs.p, n * nrhs * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(sv->ev1, st));
+  CU(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&sv->info.ms_solve_gpu, sv->ev0, sv->ev1);
+  sv->info.launches_solve = sv->launches;
+  memcpy(rhs, sv->h_rhs, n * nrhs * sizeof(double));
+  return B200LDLT_SUCCESS;
+}
+
+int b200ldlt_num_neg(b200ldlt_handle h) { return h ? ((Solver*)h)->num_neg : -1; }
+
+int b200ldlt_increase_quality(b200ldlt_handle h) {
+  Solver* sv = (Solver*)h;
+  if (!sv) return 0;
+  if (sv->pivtol >= sv->opt.pivtolmax) return 0;
+  sv->pivtol = std::min(sv->opt.pivtolmax, std::pow(sv->pivtol, 0.75));
+  return 1;
+}
+
+int b200ldlt_get_info(b200ldlt_handle h, b200ldlt_info* info) {
+  if (!h || !info) return B200LDLT_FATAL_ERROR;
+  *info = ((Solver*)h)->info;
+  return B200LDLT_SUCCESS;
+}
+
+int64_t b200ldlt_symbolic_array(b200ldlt_handle h, const char* name, int64_t* out, int64_t cap) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !name) return -1;
+  if (!sv->analysed) {
+    if (sv->n <= 0) return -1;
+    if (run_analysis(sv, nullptr) != B200LDLT_SUCCESS) return -1;
+  }
+  const Symbolic& S = sv->S;
+  std::string nm(name);
+#define RET(vec)                                                        \
+  do {                                                                  \
+    int64_t len = (int64_t)(vec).size();                                \
+    if (out) for (int64_t i = 0; i < len && i < cap; ++i) out[i] = (int64_t)(vec)[i]; \
+    return len;                                                         \
+  } while (0)
+  if (nm == "perm") RET(S.perm);
+  if (nm == "sn_start") RET(S.sn_start);
+  if (nm == "sn_parent") RET(S.sn_parent);
+  if (nm == "rows_ptr") RET(S.rows_ptr);
+  if (nm == "rows") RET(S.rows);
+  if (nm == "rel") RET(S.rel);
+  if (nm == "L_off") RET(S.L_off);
+  if (nm == "cb_off") RET(S.cb_off);
+  if (nm == "u_dst64") RET(S.u_dst64);
+  if (nm == "uent_ptr") RET(S.uent_ptr);
+  if (nm == "t2u") RET(S.t2u);
+  if (nm == "sn_level") RET(S.sn_level);
+  if (nm == "level_ptr") RET(S.level_ptr);
+  if (nm == "level_sn") RET(S.level_sn);
+#undef RET
+  return -1;
+}
+
+int b200ldlt_residual(b200ldlt_handle h, const double* x, const double* b, double* r_inf, double* x_inf, double* b_inf) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->have_dev_vals) { if (sv) sv->err = "residual: no matrix on the device"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  cudaStream_t st = sv->stream;
+  const int n = sv->n;
+  DevBuf<double> dx, db;
+  DevBuf<unsigned long long> dm;
+  CU(dx.alloc(n)); CU(db.alloc(n)); CU(dm.alloc(3));
+  CU(cudaMemcpyAsync(dx.p, x, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(db.p, b, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(dm.p, 0, 3 * sizeof(unsigned long long), st));
+  k_residual_init<<<cdiv(n, 256), 256, 0, st>>>(n, db.p, sv->d_res.p);
+  k_residual_acc<<<cdiv(sv->nnz, 256), 256, 0, st>>>(sv->nnz, sv->d_irn.p, sv->d_jcn.p, sv->d_vals.p, dx.p, sv->d_res.p);
+  k_absmax<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_res.p, dm.p);
+  k_absmax<<<cdiv(n, 256), 256, 0, st>>>(n, dx.p, dm.p + 1);
+  k_absmax<<<cdiv(n, 256), 256, 0, st>>>(n, db.p, dm.p + 2);
+  unsigned long long hm[3];
+  CU(cudaMemcpyAsync(hm, dm.p, sizeof(hm), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  double v[3];
+  memcpy(v, hm, sizeof(v));
+  if (r_inf) *r_inf = v[0];
+  if (x_inf) *x_inf = v[1];
+  if (b_inf) *b_inf = v[2];
+  return B200LDLT_SUCCESS;
+}
+
+}  // extern "C"
