@@ -386,7 +386,7 @@ void b200ldlt_default_options(b200ldlt_options* o) {
   o->scaling = 2;
   o->pivtol = 1e-8;
   o->pivtolmax = 1e-4;
-  o->tiny = 1e-20;
+  o->tiny = 1e-15;
   o->smem_front_max = 128;
   o->use_graph = 0;
   o->verbose = 0;

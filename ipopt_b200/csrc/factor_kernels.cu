@@ -120,6 +120,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   for (int t = tid; t < k; t += nt) lp[t] = t;
+  if (tid == 0) sh[2] = 0;
   int c_neg = 0, c_forced = 0, c_tiny = 0, c_2x2 = 0;  // only meaningful on thread 0
   int j = 0, kend = k, progress = 0;
   bool forced = false;
@@ -132,8 +133,15 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
     // ---------------- pivot decision by warp 0 ----------------
     if (warp == 0) {
       int type = 0, r = -1;
-      if (forced) { type = 1; r = j; }
-      else {
+      if (forced) {
+        // every remaining candidate failed the threshold test: force 1x1 pivots.  If the whole remaining
+        // column is rounding noise (scaled matrix, entries O(1)) the matrix is numerically singular.
+        double cm = 0.0;
+        for (int i = j + lane; i < f; i += 32) cm = fmax(cm, fabs(F[i + j * ld]));
+        cm = warp_max(cm);
+        type = 1; r = j;
+        if (lane == 0) sh[2] = !(cm > 1e-12);
+      } else {
         double lam = 0.0, gam = 0.0;
         int ridx = -1;
         for (int i = j + 1 + lane; i < f; i += 32) {
@@ -172,7 +180,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       if (lane == 0) { sh[0] = type; sh[1] = r; }
     }
     __syncthreads();
-    const int type = sh[0], r = sh[1];
+    const int type = sh[0], r = sh[1], noise = sh[2];
     __syncthreads();  // everyone has read sh before it is rewritten
     if (type == 0) {  // reject for now: park column j at the end of the candidate range
       if (j != kend - 1) {
@@ -194,7 +202,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       // ---------------- 1x1 pivot at j ----------------
       double d = F[j + j * ld];
       if (forced) {
-        if (!(fabs(d) > tiny)) {  // zero (or NaN) pivot: static perturbation, reported as SINGULAR
+        if (noise || !(fabs(d) > tiny)) {  // zero (or NaN) pivot: static perturbation, reported as SINGULAR
           d = (d < 0.0) ? -1.5e-8 : 1.5e-8;
           if (tid == 0) ++c_tiny;
         } else if (tid == 0) ++c_forced;

@@ -138,6 +138,43 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
     });
     for (const Cand& c : cand)
       if (partner[c.s] < 0 && partner[c.x] < 0) { partner[c.s] = c.x; partner[c.x] = c.s; S.n_pairs++; }
+    // maximum-cardinality completion: augmenting paths (saddle -> primal -> its saddle partner -> ...)
+    // for the saddle rows the greedy weighted pass left unmatched.
+    std::vector<int> visit(n, -1), from_s(n, -1);
+    std::vector<int> stack;
+    std::vector<int64_t> cursor(n);
+    for (int s0 = 0; s0 < n; ++s0) {
+      if (!saddle[s0] || partner[s0] >= 0) continue;
+      stack.clear();
+      stack.push_back(s0);
+      cursor[s0] = xadj[s0];
+      int found_x = -1;
+      while (!stack.empty() && found_x < 0) {
+        int s = stack.back();
+        if (cursor[s] >= xadj[s + 1]) { stack.pop_back(); continue; }
+        int64_t p = cursor[s]++;
+        int x = adj[p];
+        if (saddle[x] || !(adjw[p] > 0.0) || visit[x] == s0) continue;
+        visit[x] = s0;
+        from_s[x] = s;
+        if (partner[x] < 0) { found_x = x; break; }
+        int s2 = partner[x];
+        stack.push_back(s2);
+        cursor[s2] = xadj[s2];
+      }
+      if (found_x >= 0) {
+        // flip the alternating path back to s0
+        int x = found_x;
+        while (true) {
+          int s = from_s[x];
+          int prev_x = partner[s];
+          partner[s] = x; partner[x] = s;
+          if (s == s0) break;
+          x = prev_x;
+        }
+        S.n_pairs++;
+      }
+    }
   }
 
   // ---- 4. compressed graph --------------------------------------------------------------------
