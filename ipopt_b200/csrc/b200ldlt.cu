@@ -210,7 +210,8 @@ static int run_analysis(Solver* sv, const double* vals) {
     P.all_cnt = (int)fl.size() - P.all_off;
   }
   CU(sv->d_front_list.upload(fl, st));
-  CU(cudaFuncSetAttribute(k_front_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CU(cudaFuncSetAttribute(k_front_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CU(cudaFuncSetAttribute(k_front_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute(k_bwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaStreamSynchronize(st));
@@ -270,14 +271,20 @@ static int enqueue_factor(Solver* sv) {
       }
     }
     for (const auto& bk : P.small) {
-      k_front_smem<<<bk.cnt, bk.threads, bk.smem, st>>>(D, N, fl + bk.off); ++L;
+      if (bk.fmax <= 32) {  // one warp per front, 4 fronts per CTA
+        int per = (int)((bk.smem + 15) / 16 * 16);
+        k_front_smem<true><<<cdiv(bk.cnt, 4), 128, (size_t)per * 4, st>>>(D, N, fl + bk.off, bk.cnt, per); ++L;
+      } else {
+        k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, st>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
+      }
     }
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
       for (int jb = 0; jb < P.big_kmax; jb += NB) {
-        k_big_diag<<<P.big_cnt, 128, 0, st>>>(D, N, bl, jb); ++L;
+        k_big_diag<<<P.big_cnt, 32, 0, st>>>(D, N, bl, jb); ++L;
         int rows_below = P.big_fmax - jb;  // upper bound
-        k_big_trsm<<<dim3(std::max(1u, cdiv(rows_below, 128)), P.big_cnt), 128, 0, st>>>(D, N, bl, jb); ++L;
+        int nrowblk = std::max(1u, cdiv(rows_below, 128));
+        k_big_trsm<<<dim3(nrowblk + cdiv(jb, 128), P.big_cnt), 128, 0, st>>>(D, N, bl, jb, nrowblk); ++L;
         int rem_k = P.big_kmax - jb - NB;
         if (rem_k > 0) {
           k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, st>>>(D, N, bl, jb); ++L;
@@ -356,12 +363,12 @@ static int enqueue_solve(Solver* sv, const double* d_b, double* d_out) {
   k_rhs_in<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, d_b, sv->d_x.p); ++L;
   for (int l = 0; l < S.nlevels; ++l) {
     const LevelPlan& P = sv->plan[l];
-    int threads = P.fmax <= 64 ? 64 : (P.fmax <= 256 ? 128 : 512);
+    int threads = P.fmax <= 64 ? 64 : (P.fmax <= 256 ? 256 : 1024);
     k_fwd_front<<<P.all_cnt, threads, 2 * (size_t)P.fmax * sizeof(double), st>>>(sv->DS, sv->DN, fl + P.all_off, sv->d_x.p, sv->d_cbv.p); ++L;
   }
   for (int l = S.nlevels - 1; l >= 0; --l) {
     const LevelPlan& P = sv->plan[l];
-    int threads = P.fmax <= 64 ? 64 : (P.fmax <= 256 ? 128 : 512);
+    int threads = P.fmax <= 64 ? 64 : (P.fmax <= 256 ? 256 : 1024);
     k_bwd_front<<<P.all_cnt, threads, (size_t)P.fmax * sizeof(double), st>>>(sv->DS, sv->DN, fl + P.all_off, sv->d_x.p); ++L;
   }
   k_sol_out<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, sv->d_x.p, d_out); ++L;

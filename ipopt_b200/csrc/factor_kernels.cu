@@ -99,32 +99,39 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// The pivoted front factorisation runs either on a whole CTA (WARP=false, __syncthreads) or on a single
+// warp (WARP=true, __syncwarp; several fronts per CTA).
+template <bool WARP>
+__device__ __forceinline__ void gsync() { if (WARP) __syncwarp(); else __syncthreads(); }
+
+template <bool WARP>
 __device__ void swap_sym(double* F, int ld, int f, int p, int q) {
   // symmetric interchange of rows/cols p and q of the full square; caller syncs before.
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nt = WARP ? 32 : blockDim.x;
   for (int t = tid; t < f; t += nt) {
     double a = F[p + t * ld], b = F[q + t * ld];
     F[p + t * ld] = b; F[q + t * ld] = a;
   }
-  __syncthreads();
+  gsync<WARP>();
   for (int t = tid; t < f; t += nt) {
     double a = F[t + p * ld], b = F[t + q * ld];
     F[t + p * ld] = b; F[t + q * ld] = a;
   }
-  __syncthreads();
+  gsync<WARP>();
 }
 
+template <bool WARP>
 __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int* pt, double* cv1,
                                   double* cv2, volatile int* sh, double u, double tiny,
                                   double* dinv, double* doff, int* ptype_g, int* counters) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nt = WARP ? 32 : blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   for (int t = tid; t < k; t += nt) lp[t] = t;
   if (tid == 0) sh[2] = 0;
   int c_neg = 0, c_forced = 0, c_tiny = 0, c_2x2 = 0;  // only meaningful on thread 0
   int j = 0, kend = k, progress = 0;
   bool forced = false;
-  __syncthreads();
+  gsync<WARP>();
   while (j < k) {
     if (j == kend) {  // no candidate left in this pass
       if (progress > 0) { kend = k; progress = 0; }
@@ -179,23 +186,23 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       }
       if (lane == 0) { sh[0] = type; sh[1] = r; }
     }
-    __syncthreads();
+    gsync<WARP>();
     const int type = sh[0], r = sh[1], noise = sh[2];
-    __syncthreads();  // everyone has read sh before it is rewritten
+    gsync<WARP>();  // everyone has read sh before it is rewritten
     if (type == 0) {  // reject for now: park column j at the end of the candidate range
       if (j != kend - 1) {
-        swap_sym(F, ld, f, j, kend - 1);
+        swap_sym<WARP>(F, ld, f, j, kend - 1);
         if (tid == 0) { int t = lp[j]; lp[j] = lp[kend - 1]; lp[kend - 1] = t; }
       }
       --kend;
       continue;
     }
     if (type == 2 && r != j) {
-      swap_sym(F, ld, f, j, r);
+      swap_sym<WARP>(F, ld, f, j, r);
       if (tid == 0) { int t = lp[j]; lp[j] = lp[r]; lp[r] = t; }
     }
     if (type == 3 && r != j + 1) {
-      swap_sym(F, ld, f, j + 1, r);
+      swap_sym<WARP>(F, ld, f, j + 1, r);
       if (tid == 0) { int t = lp[j + 1]; lp[j + 1] = lp[r]; lp[r] = t; }
     }
     if (type != 3) {
@@ -208,7 +215,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         } else if (tid == 0) ++c_forced;
       }
       const double dv = d;
-      __syncthreads();
+      gsync<WARP>();
       for (int i = j + 1 + tid; i < f; i += nt) {
         double c = F[i + j * ld];
         cv1[i] = c;
@@ -218,19 +225,19 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         pt[j] = 1; dinv[j] = 1.0 / dv; doff[j] = 0.0; ptype_g[j] = 1;
         if (dv < 0.0) ++c_neg;
       }
-      __syncthreads();
+      gsync<WARP>();
       for (int m = j + 1 + warp; m < f; m += nwarp) {
         const double cm = cv1[m];
         if (cm != 0.0)
           for (int i = j + 1 + lane; i < f; i += 32) F[i + m * ld] -= F[i + j * ld] * cm;
       }
-      __syncthreads();
+      gsync<WARP>();
       j += 1;
     } else {
       // ---------------- 2x2 pivot at (j, j+1) ----------------
       const double a = F[j + j * ld], b = F[j + 1 + j * ld], c = F[j + 1 + (j + 1) * ld];
       const double det = a * c - b * b;
-      __syncthreads();
+      gsync<WARP>();
       for (int i = j + 2 + tid; i < f; i += nt) {
         double c1 = F[i + j * ld], c2 = F[i + (j + 1) * ld];
         cv1[i] = c1; cv2[i] = c2;
@@ -243,14 +250,14 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         ++c_2x2;
         if (det < 0.0) c_neg += 1; else if (a < 0.0) c_neg += 2;
       }
-      __syncthreads();
+      gsync<WARP>();
       for (int m = j + 2 + warp; m < f; m += nwarp) {
         const double m1 = cv1[m], m2 = cv2[m];
         if (m1 != 0.0 || m2 != 0.0)
           for (int i = j + 2 + lane; i < f; i += 32)
             F[i + m * ld] -= F[i + j * ld] * m1 + F[i + (j + 1) * ld] * m2;
       }
-      __syncthreads();
+      gsync<WARP>();
       j += 2;
     }
     ++progress;
@@ -261,29 +268,33 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
     if (c_tiny) atomicAdd(counters + CNT_TINY, c_tiny);
     if (c_2x2) atomicAdd(counters + CNT_2X2, c_2x2);
   }
-  __syncthreads();
+  gsync<WARP>();
 }
 
 // --------------------------------------------------------------------------------------------
 // Class S/M: one CTA per front, everything in shared memory.
 // smem: F[ld*f] | cv1[f] | cv2[f] | lp[k] | pt[k] | sh[8]
 // --------------------------------------------------------------------------------------------
-__global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_list) {
+template <bool WARP>
+__global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_list, int nfronts,
+                             int smem_per_group /*bytes, WARP mode only*/) {
   extern __shared__ double smem[];
-  const int s = front_list[blockIdx.x];
+  const int group = WARP ? (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : blockIdx.x;
+  if (group >= nfronts) return;
+  const int s = front_list[group];
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const int f = k + r, ld = f | 1;
-  double* F = smem;
+  double* F = WARP ? (double*)((char*)smem + (size_t)(threadIdx.x >> 5) * smem_per_group) : smem;
   double* cv1 = F + (size_t)ld * f;
   double* cv2 = cv1 + f;
   int* lp = (int*)(cv2 + f);
   int* pt = lp + k;
   int* sh = pt + k;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nt = WARP ? 32 : blockDim.x;
 
   for (int t = tid; t < ld * f; t += nt) F[t] = 0.0;
-  __syncthreads();
+  gsync<WARP>();
   // original entries (unique -> no write conflicts)
   for (long long uu = S.uent_ptr[s] + tid; uu < S.uent_ptr[s + 1]; uu += nt) {
     unsigned d = S.u_dst[uu];
@@ -292,7 +303,7 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
     F[lr + lc * ld] = v;
     F[lc + lr * ld] = v;
   }
-  __syncthreads();
+  gsync<WARP>();
   // extend-add of the children contribution blocks, one child at a time (deterministic)
   for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
     const int c = S.child_idx[q];
@@ -308,11 +319,11 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
         if (li != lj) F[lj + li * ld] += v;
       }
     }
-    __syncthreads();
+    gsync<WARP>();
   }
 
-  factor_front_smem(F, ld, f, k, lp, pt, cv1, cv2, sh, N.u, N.tiny, N.dinv + c0, N.doff + c0,
-                    N.ptype + c0, N.counters);
+  factor_front_smem<WARP>(F, ld, f, k, lp, pt, cv1, cv2, sh, N.u, N.tiny, N.dinv + c0, N.doff + c0,
+                          N.ptype + c0, N.counters);
 
   // write L panel (f x k, ld = f), unit diagonal, zero strictly-upper part of the pivot block
   double* __restrict__ P = N.L + S.L_off[s];
@@ -385,9 +396,9 @@ __global__ void k_big_extend_add(DevSym S, DevNum N, const int* __restrict__ fro
   }
 }
 
-// factor the NB x NB diagonal block at panel offset jb (pivoting restricted to the block)
-// smem: B[33*32] | cv1[32] | cv2[32] | lp[32] | pt[32] | sh[8]
-__global__ void k_big_diag(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
+// factor the NB x NB diagonal block at panel offset jb (pivoting restricted to the block).
+// ONE WARP per front (warp-synchronous, no block barriers).
+__global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
   __shared__ double B[33 * NB];
   __shared__ double cv1[NB], cv2[NB];
   __shared__ int lp[NB], pt[NB], sh[8];
@@ -397,43 +408,35 @@ __global__ void k_big_diag(DevSym S, DevNum N, const int* __restrict__ front_lis
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const int nb = min(NB, k - jb), ld = 33;
   double* P = N.L + S.L_off[s];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int t = tid; t < nb * nb; t += nt) {
-    int i = t % nb, j = t / nb;
-    if (i >= j) {
-      double v = P[(jb + i) + (size_t)(jb + j) * f];
-      B[i + j * ld] = v;
-      B[j + i * ld] = v;
+  const int lane = threadIdx.x;
+  for (int j = 0; j < nb; ++j)
+    if (lane >= j && lane < nb) {
+      double v = P[(jb + lane) + (size_t)(jb + j) * f];
+      B[lane + j * ld] = v;
+      B[j + lane * ld] = v;
     }
-  }
-  __syncthreads();
-  factor_front_smem(B, ld, nb, nb, lp, pt, cv1, cv2, sh, N.u, N.tiny, N.dinv + c0 + jb,
-                    N.doff + c0 + jb, N.ptype + c0 + jb, N.counters);
-  for (int t = tid; t < nb * nb; t += nt) {
-    int i = t % nb, j = t / nb;
-    double v;
-    if (i < j) v = 0.0;
-    else if (i == j) v = 1.0;
-    else if (pt[j] == 2 && i == j + 1) v = 0.0;
-    else v = B[i + j * ld];
-    P[(jb + i) + (size_t)(jb + j) * f] = v;
-  }
-  for (int t = tid; t < nb; t += nt) {
-    N.bperm[c0 + jb + t] = lp[t];
-    N.lperm[c0 + jb + t] = jb + lp[t];
-  }
-  // apply the block's row interchanges to the already-computed L columns on the left
-  for (int c = tid; c < jb; c += nt) {
-    double tmp[NB];
-    double* col = P + (size_t)c * f + jb;
-#pragma unroll
-    for (int t = 0; t < NB; ++t) tmp[t] = (t < nb) ? col[t] : 0.0;
-    for (int t = 0; t < nb; ++t) col[t] = tmp[lp[t]];
+  __syncwarp();
+  factor_front_smem<true>(B, ld, nb, nb, lp, pt, cv1, cv2, sh, N.u, N.tiny, N.dinv + c0 + jb,
+                          N.doff + c0 + jb, N.ptype + c0 + jb, N.counters);
+  for (int j = 0; j < nb; ++j)
+    if (lane < nb) {
+      double v;
+      if (lane < j) v = 0.0;
+      else if (lane == j) v = 1.0;
+      else if (pt[j] == 2 && lane == j + 1) v = 0.0;
+      else v = B[lane + j * ld];
+      P[(jb + lane) + (size_t)(jb + j) * f] = v;
+    }
+  if (lane < nb) {
+    N.bperm[c0 + jb + lane] = lp[lane];
+    N.lperm[c0 + jb + lane] = jb + lp[lane];
   }
 }
 
-// rows below the diagonal block: W = A_perm * L_bb^-T (= L*D), L = W * D^-1
-__global__ void k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
+// rows below the diagonal block: W = A_perm * L_bb^-T (= L*D), L = W * D^-1.
+// CTAs with blockIdx.x >= nrowblk apply the block's row interchanges to the L columns on the left.
+__global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
+                                                  int nrowblk) {
   __shared__ double Lb[33 * NB];
   __shared__ double di[NB], dof[NB];
   __shared__ int pty[NB], bp[NB];
@@ -443,10 +446,32 @@ __global__ void k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_lis
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const int nb = min(NB, k - jb);
   const int row0 = jb + nb;
-  if ((long long)blockIdx.x * blockDim.x >= f - row0) return;
   double* P = N.L + S.L_off[s];
-  double* Wp = N.W + S.L_off[s];
   const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= nrowblk) {
+    // ---- left part: rows jb..jb+nb of columns [0, jb) get the block permutation ----
+    const int c = ((int)blockIdx.x - nrowblk) * blockDim.x + tid;
+    if (tid < nb) bp[tid] = N.bperm[c0 + jb + tid];
+    __syncthreads();
+    if (c >= jb) return;
+    double tmp[NB];
+    double* col = P + (size_t)c * f + jb;
+#pragma unroll
+    for (int t = 0; t < NB; ++t) tmp[t] = (t < nb) ? col[t] : 0.0;
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+      if (t < nb) {
+        const int src = bp[t];
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) v = (q == src) ? tmp[q] : v;
+        col[t] = v;
+      }
+    }
+    return;
+  }
+  if ((long long)blockIdx.x * blockDim.x >= f - row0) return;
+  double* Wp = N.W + S.L_off[s];
   for (int t = tid; t < nb * nb; t += blockDim.x) {
     int i = t % nb, j = t / nb;
     Lb[i + j * 33] = P[(jb + i) + (size_t)(jb + j) * f];
@@ -479,7 +504,7 @@ __global__ void k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_lis
       double l;
       const int ty = pty[t];
       if (ty == 1) l = x[t] * di[t];
-      else if (ty == 2) l = x[t] * di[t] + ((t + 1 < NB) ? x[(t + 1 < NB) ? t + 1 : t] : 0.0) * dof[t];
+      else if (ty == 2) l = x[t] * di[t] + x[(t + 1 < NB) ? t + 1 : t] * dof[t];
       else l = x[(t > 0) ? t - 1 : 0] * dof[(t > 0) ? t - 1 : 0] + x[t] * di[t];
       Wp[i + (size_t)(jb + t) * f] = x[t];
       P[i + (size_t)(jb + t) * f] = l;

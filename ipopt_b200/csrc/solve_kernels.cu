@@ -52,14 +52,20 @@ __global__ void k_fwd_front(DevSym S, DevNum N, const int* __restrict__ front_li
   for (int i = tid; i < f; i += nt) v[i] = (i < k) ? w[lp[i]] : w[i];
   __syncthreads();
   const double* __restrict__ P = N.L + S.L_off[s];
+  __shared__ double Lb[SB * (SB + 1)];
   for (int t0 = 0; t0 < k; t0 += SB) {
     const int nb = min(SB, k - t0);
-    // diagonal block: unit lower triangular solve by warp 0 (lane i owns row t0+i)
+    // stage the diagonal block in shared memory (coalesced), then a warp solves it from there
+    for (int t = tid; t < nb * nb; t += nt) {
+      int i = t % nb, q = t / nb;
+      Lb[i + q * (SB + 1)] = P[(t0 + i) + (size_t)(t0 + q) * f];
+    }
+    __syncthreads();
     if (warp == 0) {
       double yi = (lane < nb) ? v[t0 + lane] : 0.0;
       for (int q = 0; q < nb; ++q) {
         double yq = __shfl_sync(0xffffffffu, yi, q);
-        if (lane > q && lane < nb) yi -= P[(t0 + lane) + (size_t)(t0 + q) * f] * yq;
+        if (lane > q && lane < nb) yi -= Lb[lane + q * (SB + 1)] * yq;
       }
       if (lane < nb) v[t0 + lane] = yi;
     }
@@ -100,9 +106,14 @@ __global__ void k_bwd_front(DevSym S, DevNum N, const int* __restrict__ front_li
   for (int i = tid; i < f; i += nt) v[i] = (i < k) ? x[c0 + i] : x[S.rows[ro + (i - k)]];
   __syncthreads();
   const double* __restrict__ P = N.L + S.L_off[s];
+  __shared__ double Lb[SB * (SB + 1)];
   const int nblk = (k + SB - 1) / SB;
   for (int b = nblk - 1; b >= 0; --b) {
     const int t0 = b * SB, nb = min(SB, k - t0);
+    for (int t = tid; t < nb * nb; t += nt) {
+      int i = t % nb, q = t / nb;
+      Lb[i + q * (SB + 1)] = P[(t0 + i) + (size_t)(t0 + q) * f];
+    }
     // v[t] -= sum_{i >= t0+nb} L[i,t] * v[i]   (one warp per column, coalesced down the column)
     for (int q = warp; q < nb; q += nwarp) {
       const double* col = P + (size_t)(t0 + q) * f;
@@ -118,7 +129,7 @@ __global__ void k_bwd_front(DevSym S, DevNum N, const int* __restrict__ front_li
       double zi = (lane < nb) ? v[t0 + lane] : 0.0;
       for (int q = nb - 1; q >= 0; --q) {
         double zq = __shfl_sync(0xffffffffu, zi, q);
-        if (lane < q) zi -= P[(t0 + q) + (size_t)(t0 + lane) * f] * zq;
+        if (lane < q) zi -= Lb[q + lane * (SB + 1)] * zq;
       }
       if (lane < nb) v[t0 + lane] = zi;
     }

@@ -1,0 +1,24 @@
+"""One analyse + NF factorisations + NS solves of a synthetic MBndryCntrl1-shaped KKT (profiling target)."""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+from ipopt_b200 import B200Ldlt
+from ipopt_b200.kkt import mbndry_kkt
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+NF = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+dim, irn, jcn, val, nc = mbndry_kkt(N, sigma_spread=3.0, seed=1)
+_, _, _, v0, _ = mbndry_kkt(N, w_zero=True)
+s = B200Ldlt(verbose=1)
+s.InitializeStructure(dim, len(irn), irn, jcn)
+a = s.GetValuesArrayPtr()
+a[:] = v0
+print("first", s.factor(True, nc))
+a[:] = val
+b = np.random.default_rng(0).standard_normal(dim)
+for it in range(NF):
+    st, neg = s.factor(True, nc)
+    x = b.copy(); s.solve(x)
+    i = s.info()
+    print("factor %.3f ms (%d launches)  solve %.3f ms (%d launches) st=%d neg=%d" % (i["ms_factor_gpu"], i["launches_factor"], i["ms_solve_gpu"], i["launches_solve"], st, neg))
+r, xi, bi = s.residual(x, b)
+print("resid", r / bi, "info", {k: v for k, v in i.items() if k in ("nnz_L", "flops_panel", "flops_schur", "nsupernodes", "nlevels", "max_front")})

@@ -105,8 +105,19 @@ static double wall_now()
    return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
 
+extern "C" void openblas_set_num_threads(int);
+extern "C" int omp_get_max_threads(void);
+
 int main(int argc, char** argv)
 {
+   // The host BLAS (OpenBLAS, pthread build) sizes its pool from the machine's hardware threads, not from the
+   // container's quota; on a many-core GPU box that turns every level-1 BLAS call of the IP loop into a storm of
+   // spinning workers.  Level-1 ops on <1e6 doubles are memory-bound anyway: keep the host BLAS single-threaded
+   // unless asked otherwise.
+   {
+      const char* e = getenv("B200_HOST_BLAS_THREADS");
+      openblas_set_num_threads(e ? atoi(e) : 1);
+   }
    std::string backend = "b200", problem = "hs071", json_path, final_path, dump_prefix;
    int N = 0, print_level = 5;
    std::vector<std::pair<std::string, std::string> > opts;
@@ -196,9 +207,9 @@ int main(int argc, char** argv)
    snprintf(buf, sizeof(buf),
             "{\"backend\": \"%s\", \"problem\": \"%s\", \"N\": %d, \"status\": %d, \"iterations\": %d, \"objective\": %.17g, "
             "\"kkt_dim\": %d, \"kkt_nnz\": %d, \"n_factor\": %d, \"n_solve\": %d, \"n_rhs\": %d, \"n_singular\": %d, "
-            "\"n_wrong_inertia\": %d, \"t_first_factor_s\": %.6f, \"t_factor_s\": %.6f, \"t_solve_s\": %.6f, \"t_total_s\": %.6f}",
+            "\"n_wrong_inertia\": %d, \"t_first_factor_s\": %.6f, \"t_factor_s\": %.6f, \"t_solve_s\": %.6f, \"t_total_s\": %.6f, \"host_threads\": %d}",
             be->name, problem.c_str(), N, (int) st, iters, obj, S.dim, S.nonzeros, S.n_factor, S.n_solve, S.n_rhs,
-            S.n_singular, S.n_wrong_inertia, S.t_first_factor, S.t_factor, S.t_solve, total);
+            S.n_singular, S.n_wrong_inertia, S.t_first_factor, S.t_factor, S.t_solve, total, omp_get_max_threads());
    printf("DRIVER_JSON %s\n", buf);
    if( !json_path.empty() ) { FILE* fp = fopen(json_path.c_str(), "w"); if( fp ) { fprintf(fp, "%s\n", buf); fclose(fp); } }
    if( !final_path.empty() )
