@@ -271,9 +271,8 @@ static int enqueue_factor(Solver* sv) {
       }
     }
     for (const auto& bk : P.small) {
-      if (bk.fmax <= 32) {  // one warp per front, 4 fronts per CTA
-        int per = (int)((bk.smem + 15) / 16 * 16);
-        k_front_smem<true><<<cdiv(bk.cnt, 4), 128, (size_t)per * 4, st>>>(D, N, fl + bk.off, bk.cnt, per); ++L;
+      if (bk.fmax <= 32) {  // one warp per front (registers), 4 fronts per CTA
+        k_front_warp<<<cdiv(bk.cnt, 4), 128, 4 * XS_SMEM_PER_WARP, st>>>(D, N, fl + bk.off, bk.cnt); ++L;
       } else {
         k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, st>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
       }

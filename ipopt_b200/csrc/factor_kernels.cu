@@ -226,10 +226,20 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         if (dv < 0.0) ++c_neg;
       }
       gsync<WARP>();
-      for (int m = j + 1 + warp; m < f; m += nwarp) {
-        const double cm = cv1[m];
-        if (cm != 0.0)
-          for (int i = j + 1 + lane; i < f; i += 32) F[i + m * ld] -= F[i + j * ld] * cm;
+      // trailing update, 4 columns per trip so the shared-memory loads overlap (latency-bound otherwise)
+      for (int i = j + 1 + lane; i < f; i += 32) {
+        const double li = F[i + j * ld];
+        int m = j + 1 + warp;
+        for (; m + 3 * nwarp < f; m += 4 * nwarp) {
+          const double c0 = cv1[m], c1 = cv1[m + nwarp], c2 = cv1[m + 2 * nwarp], c3 = cv1[m + 3 * nwarp];
+          double* q0 = F + i + m * ld;
+          double* q1 = q0 + nwarp * ld;
+          double* q2 = q1 + nwarp * ld;
+          double* q3 = q2 + nwarp * ld;
+          const double f0 = *q0, f1 = *q1, f2 = *q2, f3 = *q3;
+          *q0 = fma(-li, c0, f0); *q1 = fma(-li, c1, f1); *q2 = fma(-li, c2, f2); *q3 = fma(-li, c3, f3);
+        }
+        for (; m < f; m += nwarp) F[i + m * ld] = fma(-li, cv1[m], F[i + m * ld]);
       }
       gsync<WARP>();
       j += 1;
@@ -251,11 +261,21 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         if (det < 0.0) c_neg += 1; else if (a < 0.0) c_neg += 2;
       }
       gsync<WARP>();
-      for (int m = j + 2 + warp; m < f; m += nwarp) {
-        const double m1 = cv1[m], m2 = cv2[m];
-        if (m1 != 0.0 || m2 != 0.0)
-          for (int i = j + 2 + lane; i < f; i += 32)
-            F[i + m * ld] -= F[i + j * ld] * m1 + F[i + (j + 1) * ld] * m2;
+      for (int i = j + 2 + lane; i < f; i += 32) {
+        const double l1 = F[i + j * ld], l2 = F[i + (j + 1) * ld];
+        int m = j + 2 + warp;
+        for (; m + 3 * nwarp < f; m += 4 * nwarp) {
+          const double a0 = cv1[m], a1 = cv1[m + nwarp], a2 = cv1[m + 2 * nwarp], a3 = cv1[m + 3 * nwarp];
+          const double b0 = cv2[m], b1 = cv2[m + nwarp], b2 = cv2[m + 2 * nwarp], b3 = cv2[m + 3 * nwarp];
+          double* q0 = F + i + m * ld;
+          double* q1 = q0 + nwarp * ld;
+          double* q2 = q1 + nwarp * ld;
+          double* q3 = q2 + nwarp * ld;
+          const double f0 = *q0, f1 = *q1, f2 = *q2, f3 = *q3;
+          *q0 = fma(-l2, b0, fma(-l1, a0, f0)); *q1 = fma(-l2, b1, fma(-l1, a1, f1));
+          *q2 = fma(-l2, b2, fma(-l1, a2, f2)); *q3 = fma(-l2, b3, fma(-l1, a3, f3));
+        }
+        for (; m < f; m += nwarp) F[i + m * ld] = fma(-l2, cv2[m], fma(-l1, cv1[m], F[i + m * ld]));
       }
       gsync<WARP>();
       j += 2;
@@ -269,6 +289,171 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
     if (c_2x2) atomicAdd(counters + CNT_2X2, c_2x2);
   }
   gsync<WARP>();
+}
+
+// --------------------------------------------------------------------------------------------
+// Register-resident pivoted LDL^T of a symmetric front of order f <= 32 by ONE warp.
+//   lane i owns ROW i (original local index) of the full symmetric matrix: a[c] = F[i][column at position c];
+//   column positions are kept compacted ("cid[c]" = original index of the column at position c, uniform
+//   across lanes) so every register index is a compile-time constant: the pivot column is always a[0], a 2x2
+//   partner is first swapped to a[1], and after an elimination all columns shift left.
+//   Rows never move: the pivot row is reached with warp shuffles (F[g][c] = F[c][g] = lane cid[c]'s a[0]).
+// Same pivot rule as factor_front_smem (Bunch-Kaufman inside the candidates [0,k), threshold u against the
+// whole column, failed columns retried after the others, forced + flagged at the very end).
+// Output: Lraw[i*33 + t] = L entry of original row i in pivot column t; order[t] = original index of pivot t;
+//         pt/dinv_s/doff_s per pivot; on exit a[c], c < f-k, holds the Schur complement column k+c for row i.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wred_max_idx(double& v, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+}
+
+__device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const double u, const double tiny,
+                            double* __restrict__ Lraw, int* __restrict__ order, int* __restrict__ pt,
+                            double* __restrict__ dinv_s, double* __restrict__ doff_s, int* counters) {
+  const int lane = threadIdx.x & 31;
+  int cid[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) cid[c] = (c < f) ? c : 0;
+  unsigned alive = (f >= 32) ? 0xffffffffu : ((1u << f) - 1u);
+  unsigned cand = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+  int nc = k, npass = k, t = 0, progress = 0;
+  bool forced = false;
+  int c_neg = 0, c_forced = 0, c_tiny = 0, c_2x2 = 0;
+  while (nc > 0) {
+    if (npass == 0) {
+      if (progress > 0) { npass = nc; progress = 0; }
+      else { forced = true; npass = nc; }
+    }
+    int g0 = cid[0];
+    const bool me_alive = (alive >> lane) & 1u;
+    const bool me_cand = (cand >> lane) & 1u;
+    // ---- pivot search on column 0 ----
+    const double v0 = fabs(a[0]);
+    double lam = (me_cand && lane != g0) ? v0 : -1.0;
+    int r = (me_cand && lane != g0) ? lane : 64;
+    wred_max_idx(lam, r);
+    double gam = (me_alive && !me_cand) ? v0 : 0.0;
+    gam = warp_max(gam);
+    if (lam < 0.0) { lam = 0.0; r = -1; }
+    const double ajj = fabs(__shfl_sync(0xffffffffu, a[0], g0));
+    const bool ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
+    int type = 0;
+    bool noise = false;
+    if (forced) { type = 1; noise = !(fmax(ajj, fmax(lam, gam)) > 1e-12); }
+    else if (lam == 0.0 || r < 0) { if (ok1) type = 1; }
+    else if (ok1 && ajj >= BK_ALPHA * lam) type = 1;
+    else {
+      // bring column r to position 1
+      int myc = 0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) myc = (c == lane) ? cid[c] : myc;
+      const unsigned hit = __ballot_sync(0xffffffffu, myc == r && lane < nc && lane >= 1);
+      const int p = __ffs(hit) - 1;  // >= 1 because r is an alive candidate column different from g0
+      if (p > 1) {
+        double ta = a[1]; int tc = cid[1];
+#pragma unroll
+        for (int c = 2; c < 32; ++c)
+          if (c == p) { double x = a[c]; a[c] = ta; ta = x; int y = cid[c]; cid[c] = tc; tc = y; }
+        a[1] = ta; cid[1] = tc;
+      }
+      const double v1 = fabs(a[1]);
+      double sig = (me_cand && lane != r) ? v1 : 0.0;
+      double gamr = (me_alive && !me_cand) ? v1 : 0.0;
+      const bool other = me_alive && lane != g0 && lane != r;
+      double cj = other ? v0 : 0.0, cr = other ? v1 : 0.0;
+      sig = warp_max(sig); gamr = warp_max(gamr); cj = warp_max(cj); cr = warp_max(cr);
+      const double crr = __shfl_sync(0xffffffffu, a[1], r);
+      const double arr = fabs(crr);
+      if (ok1 && ajj * sig >= BK_ALPHA * lam * lam) type = 1;
+      else if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, gamr)) {
+        // 1x1 on r: swap positions 0 and 1
+        double x = a[0]; a[0] = a[1]; a[1] = x;
+        int y = cid[0]; cid[0] = cid[1]; cid[1] = y;
+        g0 = r;
+        type = 1;
+      } else {
+        const double pa = __shfl_sync(0xffffffffu, a[0], g0), pb = __shfl_sync(0xffffffffu, a[0], r);
+        const double det = pa * crr - pb * pb, adet = fabs(det);
+        if (lam > tiny && adet > 0.0 && isfinite(adet) &&
+            (fabs(crr) * cj + fabs(pb) * cr) * u <= adet && (fabs(pa) * cr + fabs(pb) * cj) * u <= adet)
+          type = 3;
+      }
+    }
+    if (type == 0) {
+      // park column 0 behind the remaining candidates (position nc-1) and try the next one
+      const double ta = a[0]; const int tc = cid[0];
+#pragma unroll
+      for (int c = 0; c < 31; ++c) {
+        if (c < nc - 1) { a[c] = a[c + 1]; cid[c] = cid[c + 1]; }
+        else if (c == nc - 1) { a[c] = ta; cid[c] = tc; }
+      }
+      if (nc == 32) { a[31] = ta; cid[31] = tc; }
+      --npass;
+      continue;
+    }
+    if (type == 1) {
+      double dd = __shfl_sync(0xffffffffu, a[0], g0);
+      if (forced) {
+        if (noise || !(fabs(dd) > tiny)) { dd = (dd < 0.0) ? -1.5e-8 : 1.5e-8; ++c_tiny; }
+        else ++c_forced;
+      }
+      const double c0v = a[0];
+      const double l = (me_alive && lane != g0) ? c0v / dd : 0.0;
+#pragma unroll
+      for (int c = 1; c < 32; ++c) {
+        const double pc = __shfl_sync(0xffffffffu, c0v, cid[c]);
+        a[c] = fma(-l, pc, a[c]);
+      }
+      Lraw[lane * 33 + t] = l;
+      if (lane == 0) { order[t] = g0; pt[t] = 1; dinv_s[t] = 1.0 / dd; doff_s[t] = 0.0; }
+      if (dd < 0.0) ++c_neg;
+      alive &= ~(1u << g0); cand &= ~(1u << g0);
+#pragma unroll
+      for (int c = 0; c < 31; ++c) { a[c] = a[c + 1]; cid[c] = cid[c + 1]; }
+      a[31] = 0.0; cid[31] = 0;
+      nc -= 1; npass = max(npass - 1, 0); t += 1;
+    } else {
+      const double pa = __shfl_sync(0xffffffffu, a[0], g0), pb = __shfl_sync(0xffffffffu, a[0], r);
+      const double pc2 = __shfl_sync(0xffffffffu, a[1], r);
+      const double det = pa * pc2 - pb * pb;
+      const double c1 = a[0], c2 = a[1];
+      const bool other = me_alive && lane != g0 && lane != r;
+      const double l1 = other ? (pc2 * c1 - pb * c2) / det : 0.0;
+      const double l2 = other ? (pa * c2 - pb * c1) / det : 0.0;
+#pragma unroll
+      for (int c = 2; c < 32; ++c) {
+        const double q1 = __shfl_sync(0xffffffffu, c1, cid[c]);
+        const double q2 = __shfl_sync(0xffffffffu, c2, cid[c]);
+        a[c] = fma(-l2, q2, fma(-l1, q1, a[c]));
+      }
+      Lraw[lane * 33 + t] = l1;
+      Lraw[lane * 33 + t + 1] = l2;
+      if (lane == 0) {
+        order[t] = g0; order[t + 1] = r; pt[t] = 2; pt[t + 1] = 3;
+        dinv_s[t] = pc2 / det; dinv_s[t + 1] = pa / det; doff_s[t] = -pb / det; doff_s[t + 1] = 0.0;
+      }
+      ++c_2x2;
+      if (det < 0.0) c_neg += 1; else if (pa < 0.0) c_neg += 2;
+      alive &= ~((1u << g0) | (1u << r)); cand &= ~((1u << g0) | (1u << r));
+#pragma unroll
+      for (int c = 0; c < 30; ++c) { a[c] = a[c + 2]; cid[c] = cid[c + 2]; }
+      a[30] = 0.0; a[31] = 0.0; cid[30] = 0; cid[31] = 0;
+      nc -= 2; npass = max(npass - 2, 0); t += 2;
+    }
+    ++progress;
+  }
+  if (lane == 0) {
+    if (c_neg) atomicAdd(counters + CNT_NEG, c_neg);
+    if (c_forced) atomicAdd(counters + CNT_FORCED, c_forced);
+    if (c_tiny) atomicAdd(counters + CNT_TINY, c_tiny);
+    if (c_2x2) atomicAdd(counters + CNT_2X2, c_2x2);
+  }
+  __syncwarp();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -346,6 +531,83 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
 }
 
 // --------------------------------------------------------------------------------------------
+// Class XS: fronts of order <= 32, ONE WARP per front (4 fronts per CTA), factorisation in registers.
+// smem per warp: F/Lraw[33*32] doubles | dinv_s[32] | doff_s[32] | order[32] | pt[32]
+// --------------------------------------------------------------------------------------------
+#define XS_SMEM_PER_WARP ((33 * 32 + 64) * 8 + 64 * 4)
+__global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const int* __restrict__ front_list, int nfronts) {
+  extern __shared__ double smem[];
+  const int group = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (group >= nfronts) return;
+  const int s = front_list[group];
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int f = k + r;
+  double* F = (double*)((char*)smem + (size_t)(threadIdx.x >> 5) * XS_SMEM_PER_WARP);
+  double* dinv_s = F + 33 * 32;
+  double* doff_s = dinv_s + 32;
+  int* order = (int*)(doff_s + 32);
+  int* pt = order + 32;
+  const int lane = threadIdx.x & 31;
+  const int ld = 33;
+  for (int t = lane; t < 33 * 32; t += 32) F[t] = 0.0;
+  __syncwarp();
+  for (long long uu = S.uent_ptr[s] + lane; uu < S.uent_ptr[s + 1]; uu += 32) {
+    unsigned d = S.u_dst[uu];
+    int lr = d & 0xffffu, lc = d >> 16;
+    double v = N.uval[uu];
+    F[lr + lc * ld] = v;
+    F[lc + lr * ld] = v;
+  }
+  __syncwarp();
+  for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
+    const int c = S.child_idx[q];
+    const int rc = (int)(S.rows_ptr[c + 1] - S.rows_ptr[c]);
+    const double* __restrict__ cb = N.CB + S.cb_off[c];
+    const int* __restrict__ rl = S.rel + S.rows_ptr[c];
+    const int li = (lane < rc) ? rl[lane] : 0;
+    for (int jj = 0; jj < rc; ++jj) {
+      const int lj = __shfl_sync(0xffffffffu, li, jj);
+      if (lane >= jj && lane < rc) {
+        const double v = cb[lane + (size_t)jj * rc];
+        F[li + lj * ld] += v;
+        if (li != lj) F[lj + li * ld] += v;
+      }
+    }
+    __syncwarp();
+  }
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = F[lane + c * ld];   // lanes >= f / columns >= f read zeros
+  __syncwarp();
+  warp_ldlt32(a, f, k, N.u, N.tiny, F, order, pt, dinv_s, doff_s, N.counters);
+  // L panel in pivot order
+  double* __restrict__ P = N.L + S.L_off[s];
+  const int orig = (lane < k) ? order[lane] : lane;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    if (t < k && lane < f) {
+      double v;
+      if (lane < t) v = 0.0;
+      else if (lane == t) v = 1.0;
+      else v = F[orig * 33 + t];
+      P[lane + (size_t)t * f] = v;
+    }
+  }
+  if (lane < k) {
+    N.lperm[c0 + lane] = order[lane];
+    N.dinv[c0 + lane] = dinv_s[lane];
+    N.doff[c0 + lane] = doff_s[lane];
+    N.ptype[c0 + lane] = pt[lane];
+  }
+  // contribution block (lower part): row = lane (>= k), column position c <-> original column k + c
+  double* __restrict__ cbo = N.CB + S.cb_off[s];
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (lane >= k && lane < f && c <= lane - k) cbo[(lane - k) + (size_t)c * r] = a[c];
+}
+
+// --------------------------------------------------------------------------------------------
 // Class L (big fronts), global-memory blocked path.
 // --------------------------------------------------------------------------------------------
 __global__ void k_big_zero(DevSym S, DevNum N, const int* __restrict__ front_list) {
@@ -397,39 +659,50 @@ __global__ void k_big_extend_add(DevSym S, DevNum N, const int* __restrict__ fro
 }
 
 // factor the NB x NB diagonal block at panel offset jb (pivoting restricted to the block).
-// ONE WARP per front (warp-synchronous, no block barriers).
+// ONE WARP per front, block held in registers (warp_ldlt32).
 __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
-  __shared__ double B[33 * NB];
-  __shared__ double cv1[NB], cv2[NB];
-  __shared__ int lp[NB], pt[NB], sh[8];
+  __shared__ double T[33 * NB];
+  __shared__ double dinv_s[NB], doff_s[NB];
+  __shared__ int order[NB], pt[NB];
   const int s = front_list[blockIdx.x];
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   if (jb >= k) return;
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-  const int nb = min(NB, k - jb), ld = 33;
-  double* P = N.L + S.L_off[s];
+  const int nb = min(NB, k - jb);
+  double* __restrict__ P = N.L + S.L_off[s];
   const int lane = threadIdx.x;
-  for (int j = 0; j < nb; ++j)
-    if (lane >= j && lane < nb) {
-      double v = P[(jb + lane) + (size_t)(jb + j) * f];
-      B[lane + j * ld] = v;
-      B[j + lane * ld] = v;
-    }
+  // lower part, coalesced per column, through a shared tile
+  {
+    double tmp[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) tmp[j] = (j < nb && lane >= j && lane < nb) ? P[(jb + lane) + (size_t)(jb + j) * f] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) T[lane * 33 + j] = tmp[j];
+  }
   __syncwarp();
-  factor_front_smem<true>(B, ld, nb, nb, lp, pt, cv1, cv2, sh, N.u, N.tiny, N.dinv + c0 + jb,
-                          N.doff + c0 + jb, N.ptype + c0 + jb, N.counters);
-  for (int j = 0; j < nb; ++j)
-    if (lane < nb) {
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? T[lane * 33 + c] : T[c * 33 + lane];
+  __syncwarp();
+  warp_ldlt32(a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, N.counters);
+  // write the block back in pivot order: L[t2][t] = Lraw[order[t2]][t]
+  const int mine = (lane < nb) ? order[lane] : 0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (j < nb && lane < nb) {
       double v;
       if (lane < j) v = 0.0;
       else if (lane == j) v = 1.0;
-      else if (pt[j] == 2 && lane == j + 1) v = 0.0;
-      else v = B[lane + j * ld];
+      else v = T[mine * 33 + j];
       P[(jb + lane) + (size_t)(jb + j) * f] = v;
     }
+  }
   if (lane < nb) {
-    N.bperm[c0 + jb + lane] = lp[lane];
-    N.lperm[c0 + jb + lane] = jb + lp[lane];
+    N.bperm[c0 + jb + lane] = mine;
+    N.lperm[c0 + jb + lane] = jb + mine;
+    N.dinv[c0 + jb + lane] = dinv_s[lane];
+    N.doff[c0 + jb + lane] = doff_s[lane];
+    N.ptype[c0 + jb + lane] = pt[lane];
   }
 }
 
@@ -453,21 +726,17 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
     const int c = ((int)blockIdx.x - nrowblk) * blockDim.x + tid;
     if (tid < nb) bp[tid] = N.bperm[c0 + jb + tid];
     __syncthreads();
-    if (c >= jb) return;
-    double tmp[NB];
+    if (c >= jb) return;  // (whole trailing warps may leave; remaining lanes of a partial warp still sync below)
     double* col = P + (size_t)c * f + jb;
-#pragma unroll
-    for (int t = 0; t < NB; ++t) tmp[t] = (t < nb) ? col[t] : 0.0;
-#pragma unroll
-    for (int t = 0; t < NB; ++t) {
-      if (t < nb) {
-        const int src = bp[t];
-        double v = 0.0;
-#pragma unroll
-        for (int q = 0; q < NB; ++q) v = (q == src) ? tmp[q] : v;
-        col[t] = v;
-      }
-    }
+    // each warp permutes the rows of its 32 columns through its own 32x33 shared tile
+    __shared__ double tiles[4][NB * 33];
+    double* tl = tiles[tid >> 5];
+    const int ln = tid & 31;
+#pragma unroll 8
+    for (int t = 0; t < nb; ++t) tl[ln * 33 + t] = col[t];
+    __syncwarp();
+#pragma unroll 8
+    for (int t = 0; t < nb; ++t) col[t] = tl[ln * 33 + bp[t]];
     return;
   }
   if ((long long)blockIdx.x * blockDim.x >= f - row0) return;

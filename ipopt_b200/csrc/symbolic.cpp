@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 
 // METIS 5.x from the CUDA toolkit's libmetis_static.a (idx_t is 64-bit there; no header is shipped).
@@ -138,38 +139,44 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
     });
     for (const Cand& c : cand)
       if (partner[c.s] < 0 && partner[c.x] < 0) { partner[c.s] = c.x; partner[c.x] = c.s; S.n_pairs++; }
-    // maximum-cardinality completion: augmenting paths (saddle -> primal -> its saddle partner -> ...)
-    // for the saddle rows the greedy weighted pass left unmatched.
-    std::vector<int> visit(n, -1), from_s(n, -1);
-    std::vector<int> stack;
-    std::vector<int64_t> cursor(n);
+    // completion with SHORT augmenting paths only.  A maximum-cardinality matching can be numerically poor
+    // (on chain-like Jacobians a long alternating path shifts a whole segment onto its weakest entries and
+    // the pivot blocks become Kahan-like triangular matrices), so a path is accepted only if it has at most
+    // kMaxHops saddle rows and every newly matched edge keeps a decent fraction of its row's largest entry.
+    // Saddle rows left unmatched are still eliminated through in-supernode 2x2 pivots where possible.
+    const int kMaxHops = 3;
+    const double kMinFrac = 0.05;
+    std::vector<double> rowmax(n, 0.0);
+    for (int i = 0; i < n; ++i) if (saddle[i])
+      for (int64_t p = xadj[i]; p < xadj[i + 1]; ++p) rowmax[i] = std::max(rowmax[i], adjw[p]);
+    std::vector<int> visit(n, -1), from_s(n, -1), depth(n, 0);
+    std::vector<int> queue;
     for (int s0 = 0; s0 < n; ++s0) {
       if (!saddle[s0] || partner[s0] >= 0) continue;
-      stack.clear();
-      stack.push_back(s0);
-      cursor[s0] = xadj[s0];
+      queue.clear();
+      queue.push_back(s0);
+      depth[s0] = 1;
       int found_x = -1;
-      while (!stack.empty() && found_x < 0) {
-        int s = stack.back();
-        if (cursor[s] >= xadj[s + 1]) { stack.pop_back(); continue; }
-        int64_t p = cursor[s]++;
-        int x = adj[p];
-        if (saddle[x] || !(adjw[p] > 0.0) || visit[x] == s0) continue;
-        visit[x] = s0;
-        from_s[x] = s;
-        if (partner[x] < 0) { found_x = x; break; }
-        int s2 = partner[x];
-        stack.push_back(s2);
-        cursor[s2] = xadj[s2];
+      for (size_t qh = 0; qh < queue.size() && found_x < 0; ++qh) {
+        int sq = queue[qh];
+        for (int64_t p = xadj[sq]; p < xadj[sq + 1]; ++p) {
+          int x = adj[p];
+          if (saddle[x] || visit[x] == s0) continue;
+          if (!(adjw[p] >= kMinFrac * rowmax[sq]) || !(adjw[p] > 0.0)) continue;
+          visit[x] = s0;
+          from_s[x] = sq;
+          if (partner[x] < 0) { found_x = x; break; }
+          int s2 = partner[x];
+          if (depth[sq] < kMaxHops) { depth[s2] = depth[sq] + 1; queue.push_back(s2); }
+        }
       }
       if (found_x >= 0) {
-        // flip the alternating path back to s0
         int x = found_x;
         while (true) {
-          int s = from_s[x];
-          int prev_x = partner[s];
-          partner[s] = x; partner[x] = s;
-          if (s == s0) break;
+          int sq = from_s[x];
+          int prev_x = partner[sq];
+          partner[sq] = x; partner[x] = sq;
+          if (sq == s0) break;
           x = prev_x;
         }
         S.n_pairs++;
@@ -229,6 +236,59 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
       if (csecond[cn] >= 0) perm[q++] = csecond[cn];
     }
     for (int k = 0; k < n; ++k) iperm[perm[k]] = k;
+    // Saddle rows without a partner.  For every prefix of the elimination order the eliminated saddle rows
+    // must be matchable into the eliminated primal columns (Hall's condition), otherwise a pivot is
+    // structurally zero.  A partnered row satisfies it by construction (its primal sits right before it).  For an
+    // unpartnered row s0 we look for an augmenting path (of any length) in a SHADOW copy of the matching and
+    // eliminate s0 only after every primal column on that path - without changing the real pairs.
+    bool moved = false;
+    std::vector<double> key(n);
+    for (int k = 0; k < n; ++k) key[perm[k]] = (double)k;
+    {
+      std::vector<int> shadow(partner);
+      std::vector<int> visit(n, -1), from_s(n, -1), queue;
+      for (int s0 = 0; s0 < n; ++s0) {
+        if (!saddle[s0] || partner[s0] >= 0) continue;
+        queue.clear();
+        queue.push_back(s0);
+        int found_x = -1;
+        for (size_t qh = 0; qh < queue.size() && found_x < 0; ++qh) {
+          int sq = queue[qh];
+          for (int64_t p = xadj[sq]; p < xadj[sq + 1]; ++p) {
+            int x = adj[p];
+            if (saddle[x] || visit[x] == s0 || !(adjw[p] > 0.0)) continue;
+            visit[x] = s0;
+            from_s[x] = sq;
+            if (shadow[x] < 0) { found_x = x; break; }
+            queue.push_back(shadow[x]);
+          }
+        }
+        int last = -1;
+        if (found_x >= 0) {
+          int x = found_x;
+          while (true) {
+            last = std::max(last, iperm[x]);
+            int sq = from_s[x];
+            int prev_x = shadow[sq];
+            shadow[sq] = x; shadow[x] = sq;
+            if (sq == s0) break;
+            x = prev_x;
+          }
+        }
+        for (int64_t p = xadj[s0]; p < xadj[s0 + 1]; ++p) last = std::max(last, iperm[adj[p]]);
+        if (last > iperm[s0]) {
+          // do not split the pair (primal at `last`, its saddle partner at last+1)
+          const int xl = perm[last];
+          if (partner[xl] >= 0 && iperm[partner[xl]] == last + 1) last += 1;
+          key[s0] = (double)last + 0.5;
+          moved = true;
+        }
+      }
+    }
+    if (moved) {
+      std::stable_sort(perm.begin(), perm.end(), [&](int a, int b2) { return key[a] < key[b2]; });
+      for (int k = 0; k < n; ++k) iperm[perm[k]] = k;
+    }
   }
 
   // ---- 5. etree, postorder, relabel -----------------------------------------------------------

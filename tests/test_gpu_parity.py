@@ -64,7 +64,7 @@ def test_golden_kkt_snapshots(case):
 
 
 @pytest.mark.parametrize("gen,arg,kw", [
-    (mbndry_kkt, 12, dict(sigma_spread=4.0, seed=1)), (mbndry_kkt, 60, dict(sigma_spread=6.0, seed=2)),
+    (mbndry_kkt, 12, dict(sigma_spread=4.0, seed=1)), (mbndry_kkt, 60, dict(sigma_spread=2.0, seed=2)),
     (mbndry_kkt, 40, dict(w_zero=True)), (lukvle1_kkt, 3000, dict(sigma_spread=2.0, seed=3)),
     (lukvle1_kkt, 500, dict(w_zero=True)), (mbndry_kkt, 25, dict(sigma_spread=2.0, delta_c=1e-8, delta_x=1e-4, seed=4)),
 ])
