@@ -13,6 +13,7 @@
 
 #include "factor_kernels.cu"
 #include "solve_kernels.cu"
+#include "solve_dataflow.cu"
 #include "symbolic.hpp"
 
 namespace b200 {
@@ -81,6 +82,16 @@ struct Solver {
   DevSym DS;
   DevNum DN;
   int launches = 0;
+  // dataflow solve
+  DevBuf<SolveTask> d_tasks_f, d_tasks_b;
+  DevBuf<int> d_bundle, d_done_f, d_done_b, d_gflag, d_bflag_f, d_bflag_b, d_bcnt, d_bcnt_b, d_boff;
+  DevBuf<long long> d_bigv_off;
+  DevBuf<double> d_bigv, d_bigy;
+  DevBuf<unsigned long long> d_ticket;
+  DevSolve DV;
+  int solve_epoch = 0, df_grid = 0;
+  unsigned long long ticket_f = 0, ticket_b = 0;
+  int num_sms = 148;
 
   ~Solver() {
     if (h_vals) cudaFreeHost(h_vals);
@@ -215,6 +226,88 @@ static int run_analysis(Solver* sv, const double* vals) {
   CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute(k_bwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaStreamSynchronize(st));
+
+
+  // ---- dataflow solve: task lists (topological), flags, scratch ---------------------------------
+  {
+    const int MIDMAX = 256;
+    std::vector<SolveTask> tf, tb;
+    std::vector<int> bundle, boff(S.nsn, 0);
+    std::vector<long long> bigv_off(S.nsn, 0);
+    long long bv = 0; int bo = 0;
+    for (int s = 0; s < S.nsn; ++s) if (S.f(s) > MIDMAX) {
+      boff[s] = bo; bo += (S.f(s) + DF_BLK - 1) / DF_BLK;
+      bigv_off[s] = bv; bv += S.f(s) + (S.f(s) & 1);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<SolveTask>& T = pass == 0 ? tf : tb;
+      for (int li = 0; li < S.nlevels; ++li) {
+        const int l = pass == 0 ? li : S.nlevels - 1 - li;
+        std::vector<int> smalls;
+        // big first (longest), then mid, then small bundles
+        for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+          int s = S.level_sn[q];
+          if (S.f(s) <= MIDMAX) continue;
+          if (pass == 0) {
+            T.push_back({ST_BIG_GATHER, s, 0, 0});
+            int nb = (S.f(s) + DF_BLK - 1) / DF_BLK;
+            for (int b = 0; b < nb; ++b) T.push_back({ST_BIG_BLOCK, s, b, 0});
+          } else {
+            int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK;
+            for (int b = nkb - 1; b >= 0; --b) T.push_back({ST_BIG_BLOCK, s, b, 0});
+          }
+        }
+        for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+          int s = S.level_sn[q];
+          if (S.f(s) > MIDMAX) continue;
+          if (S.f(s) > 32) T.push_back({ST_MID, s, 0, 0});
+          else smalls.push_back(s);
+        }
+        for (size_t q = 0; q < smalls.size(); q += 8) {
+          int cnt = (int)std::min<size_t>(8, smalls.size() - q);
+          T.push_back({ST_SMALL, (int)bundle.size(), cnt, 0});
+          for (int w = 0; w < cnt; ++w) bundle.push_back(smalls[q + w]);
+        }
+      }
+    }
+    CU(sv->d_tasks_f.upload(tf, st));
+    CU(sv->d_tasks_b.upload(tb, st));
+    if (bundle.empty()) bundle.push_back(0);
+    CU(sv->d_bundle.upload(bundle, st));
+    CU(sv->d_boff.upload(boff, st));
+    CU(sv->d_bigv_off.upload(bigv_off, st));
+    CU(sv->d_done_f.alloc(S.nsn)); CU(sv->d_done_b.alloc(S.nsn)); CU(sv->d_gflag.alloc(S.nsn));
+    CU(sv->d_bcnt.alloc(S.nsn)); CU(sv->d_bcnt_b.alloc(S.nsn));
+    CU(sv->d_bflag_f.alloc(std::max(bo, 1))); CU(sv->d_bflag_b.alloc(std::max(bo, 1)));
+    CU(sv->d_bigv.alloc(std::max<long long>(bv, 1))); CU(sv->d_bigy.alloc(std::max<long long>(bv, 1)));
+    CU(sv->d_ticket.alloc(2));
+    CU(cudaMemsetAsync(sv->d_done_f.p, 0, S.nsn * sizeof(int), st));
+    CU(cudaMemsetAsync(sv->d_done_b.p, 0, S.nsn * sizeof(int), st));
+    CU(cudaMemsetAsync(sv->d_gflag.p, 0, S.nsn * sizeof(int), st));
+    CU(cudaMemsetAsync(sv->d_bcnt.p, 0, S.nsn * sizeof(int), st));
+    CU(cudaMemsetAsync(sv->d_bcnt_b.p, 0, S.nsn * sizeof(int), st));
+    CU(cudaMemsetAsync(sv->d_bflag_f.p, 0, std::max(bo, 1) * sizeof(int), st));
+    CU(cudaMemsetAsync(sv->d_bflag_b.p, 0, std::max(bo, 1) * sizeof(int), st));
+    CU(cudaMemsetAsync(sv->d_ticket.p, 0, 2 * sizeof(unsigned long long), st));
+    sv->solve_epoch = 0; sv->ticket_f = sv->ticket_b = 0;
+    DevSolve& V = sv->DV;
+    V.tasks = sv->d_tasks_f.p; V.tasks_bwd = sv->d_tasks_b.p;
+    V.ntasks_fwd = (int)tf.size(); V.ntasks_bwd = (int)tb.size();
+    V.bundle = sv->d_bundle.p; V.done_f = sv->d_done_f.p; V.done_b = sv->d_done_b.p; V.gflag = sv->d_gflag.p;
+    V.bflag_f = sv->d_bflag_f.p; V.bflag_b = sv->d_bflag_b.p; V.bcnt = sv->d_bcnt.p; V.bcnt_b = sv->d_bcnt_b.p;
+    V.boff = sv->d_boff.p; V.bigv_off = sv->d_bigv_off.p; V.bigv = sv->d_bigv.p; V.bigy = sv->d_bigy.p;
+    V.ticket = sv->d_ticket.p;
+    const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
+    CU(cudaFuncSetAttribute(k_solve_dataflow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
+    CU(cudaFuncSetAttribute(k_solve_dataflow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_dataflow<true>, DF_THREADS, df_smem));
+    CU(cudaDeviceGetAttribute(&sv->num_sms, cudaDevAttrMultiProcessorCount, sv->dev));
+    sv->df_grid = std::max(1, occ) * sv->num_sms;
+    if (sv->opt.verbose)
+      fprintf(stderr, "[b200ldlt] dataflow solve: %d fwd / %d bwd tasks, %d big-front blocks, grid %d x %d thr, %d B smem\n",
+              V.ntasks_fwd, V.ntasks_bwd, bo, sv->df_grid, DF_THREADS, df_smem);
+  }
 
   b200ldlt_info& I = sv->info;
   I.n = n; I.nnz_in = S.nnz_in; I.nnz_unique = S.nnz_u;
@@ -360,6 +453,20 @@ static int enqueue_solve(Solver* sv, const double* d_b, double* d_out) {
   const int* fl = sv->d_front_list.p;
   int& L = sv->launches;
   k_rhs_in<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, d_b, sv->d_x.p); ++L;
+  if (sv->opt.use_graph != 2) {   // default: persistent dataflow sweeps (use_graph == 2 selects the level-per-launch kernels)
+    const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
+    sv->solve_epoch++;
+    const DevSolve& V = sv->DV;
+    k_solve_dataflow<true><<<std::min(sv->df_grid, std::max(V.ntasks_fwd, 1)), DF_THREADS, df_smem, st>>>(
+        sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p); ++L;
+    sv->ticket_f += (unsigned long long)V.ntasks_fwd + std::min(sv->df_grid, std::max(V.ntasks_fwd, 1));
+    k_solve_dataflow<false><<<std::min(sv->df_grid, std::max(V.ntasks_bwd, 1)), DF_THREADS, df_smem, st>>>(
+        sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p); ++L;
+    sv->ticket_b += (unsigned long long)V.ntasks_bwd + std::min(sv->df_grid, std::max(V.ntasks_bwd, 1));
+    k_sol_out<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, sv->d_x.p, d_out); ++L;
+    CU(cudaGetLastError());
+    return B200LDLT_SUCCESS;
+  }
   for (int l = 0; l < S.nlevels; ++l) {
     const LevelPlan& P = sv->plan[l];
     int threads = P.fmax <= 64 ? 64 : (P.fmax <= 256 ? 256 : 1024);
@@ -451,6 +558,8 @@ int b200ldlt_analyse(b200ldlt_handle h, int dim, int nonzeros, const int* irn, c
   CU(cudaHostAlloc((void**)&sv->h_vals, std::max<size_t>(nonzeros, 1) * sizeof(double), cudaHostAllocDefault));
   memset(sv->h_vals, 0, std::max<size_t>(nonzeros, 1) * sizeof(double));
   sv->analysed = false; sv->factored = false; sv->have_dev_vals = false;
+  if (sv->h_rhs) { cudaFreeHost(sv->h_rhs); sv->h_rhs = nullptr; }
+  sv->rhs_cap = 0;   // staging buffers are sized by dim: a new structure invalidates them
   return B200LDLT_SUCCESS;
 }
 

@@ -1,0 +1,490 @@
+// Persistent dataflow triangular solve (forward L, D^-1, backward L^T) -- ONE kernel per sweep.
+//
+// The level-per-launch version (solve_kernels.cu) spends its time in launch gaps and in single-CTA big
+// fronts.  Here every front (or 64-row / 64-column block of a big front) is a TASK in a topologically
+// sorted list; persistent CTAs take tasks with an atomic ticket and wait for their producers through
+// acquire/release flags in global memory.  A task only ever waits for tasks that precede it in the list,
+// and every ticket is held by a resident CTA, so the scheme cannot deadlock.  L is streamed exactly once
+// per sweep (HBM-bound, SURVEY.md 8d: 2*8*nnz(L) bytes per right-hand side); no atomics on the data path
+// (children -> parent through per-front update vectors gathered by the parent), so results are
+// bit-reproducible.  Replaces the vendor back-solve of the reference (MUMPS job=3,
+// reference src/Algorithm/LinearSolvers/IpMumpsSolverInterface.cpp:543-583).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "kernels.cuh"
+
+namespace b200 {
+
+#define DF_THREADS 256
+#define DF_BLK 64          // block-row / block-column size of the big-front tasks
+#define DF_SMALL_SMEM (33 * 32 + 64)   // doubles per warp for a small front
+
+enum { ST_SMALL = 0, ST_MID = 1, ST_BIG_GATHER = 2, ST_BIG_BLOCK = 3 };
+
+struct SolveTask { int type, a, b, c; };
+
+struct DevSolve {
+  const SolveTask* tasks;      // forward list
+  const SolveTask* tasks_bwd;  // backward list
+  int ntasks_fwd, ntasks_bwd;
+  const int* bundle;           // front ids of the small bundles
+  int* done_f;                 // nsn : epoch when the forward work of a front is complete
+  int* done_b;                 // nsn : same for backward
+  int* gflag;                  // nsn : big-front gather done
+  int* bflag_f;                // per (big front, block): y block published
+  int* bflag_b;                // per (big front, block): x block published
+  int* bcnt;                   // nsn : finished forward block counter (monotonic)
+  int* bcnt_b;                 // nsn : finished backward block counter (monotonic)
+  const int* boff;             // nsn : offset of a big front's blocks in bflag_*
+  const long long* bigv_off;   // nsn : offset into bigv (f doubles) / bigy (k doubles at the same offset)
+  double* bigv;                // assembled+permuted rhs of big fronts
+  double* bigy;                // y / x blocks of big fronts in pivoted order
+  unsigned long long* ticket;  // [0] fwd, [1] bwd (monotonic)
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_eq(const int* p, int epoch) {
+  while (ld_acquire(p) != epoch) __nanosleep(32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small fronts (order <= 32): one warp per front, panel staged in shared memory
+// ------------------------------------------------------------------------------------------------
+__device__ void small_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+                          double* __restrict__ x, double* __restrict__ cbv) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const long long ro = S.rows_ptr[s];
+  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  double* Ls = sm;            // f x k, ld 33
+  double* w = sm + 33 * 32;   // 32
+  const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
+  // stage the panel first: it does not depend on the children
+  const double* __restrict__ P = N.L + S.L_off[s];
+  for (int tb = 0; tb < k; tb += 8) {   // 8 independent loads in flight per lane
+    double tmp[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tmp[q] = (lane < f && tb + q < k) ? P[lane + (size_t)(tb + q) * f] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (tb + q < k) Ls[lane + (tb + q) * 33] = tmp[q];
+  }
+  w[lane] = (lane < k) ? x[c0 + lane] : 0.0;
+  for (int q = ch0 + lane; q < ch1; q += 32) wait_eq(V.done_f + S.child_idx[q], epoch);
+  __syncwarp();
+  for (int q = ch0; q < ch1; ++q) {
+    const int c = S.child_idx[q];
+    const long long o = S.rows_ptr[c];
+    const int rc = (int)(S.rows_ptr[c + 1] - o);
+    if (lane < rc) w[S.rel[o + lane]] += __ldcg(cbv + o + lane);
+    __syncwarp();
+  }
+  double v = 0.0;
+  if (lane < f) v = (lane < k) ? w[N.lperm[c0 + lane]] : w[lane];
+  for (int t = 0; t < k; ++t) {
+    const double yt = __shfl_sync(0xffffffffu, v, t);
+    if (lane > t && lane < f) v = fma(-Ls[lane + t * 33], yt, v);
+  }
+  // D^-1 (2x2 partners are neighbouring lanes)
+  const double vn = __shfl_down_sync(0xffffffffu, v, 1), vp = __shfl_up_sync(0xffffffffu, v, 1);
+  if (lane < k) {
+    const int ty = N.ptype[c0 + lane];
+    double y;
+    if (ty == 1) y = v * N.dinv[c0 + lane];
+    else if (ty == 2) y = v * N.dinv[c0 + lane] + vn * N.doff[c0 + lane];
+    else y = vp * N.doff[c0 + lane - 1] + v * N.dinv[c0 + lane];
+    x[c0 + lane] = y;
+  } else if (lane < f) cbv[ro + lane - k] = v;
+  __syncwarp();
+  if (lane == 0) { __threadfence(); st_release(V.done_f + s, epoch); }
+}
+
+__device__ void small_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+                          double* __restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const long long ro = S.rows_ptr[s];
+  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  double* Ls = sm;
+  const double* __restrict__ P = N.L + S.L_off[s];
+  for (int tb = 0; tb < k; tb += 8) {   // 8 independent loads in flight per lane
+    double tmp[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tmp[q] = (lane < f && tb + q < k) ? P[lane + (size_t)(tb + q) * f] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (tb + q < k) Ls[lane + (tb + q) * 33] = tmp[q];
+  }
+  const int par = S.sn_parent[s];
+  if (par >= 0 && lane == 0) wait_eq(V.done_b + par, epoch);
+  __syncwarp();
+  double v = 0.0;  // lane i holds entry i of [D^-1 y ; x(rows)]
+  if (lane < k) v = x[c0 + lane];
+  else if (lane < f) v = __ldcg(x + S.rows[ro + lane - k]);
+  // columns from the last to the first: v_t -= sum_{i>t} L[i,t] v_i.  Lane t owns column t.
+  for (int i = f - 1; i >= 1; --i) {
+    const double vi = __shfl_sync(0xffffffffu, v, i);
+    if (lane < i && lane < k) v = fma(-Ls[i + lane * 33], vi, v);
+  }
+  if (lane < k) x[c0 + N.lperm[c0 + lane]] = v;
+  __syncwarp();
+  if (lane == 0) { __threadfence(); st_release(V.done_b + s, epoch); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mid fronts (33 .. mid_max): one CTA, blocked by 32 (same algorithm as solve_kernels.cu)
+// smem: v[f] | w[f] | Lb[32*33]
+// ------------------------------------------------------------------------------------------------
+__device__ void mid_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+                        double* __restrict__ x, double* __restrict__ cbv) {
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]), f = k + r;
+  double* v = sm;
+  double* w = sm + f;
+  double* Lb = sm + 2 * f;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
+  for (int q = ch0 + tid; q < ch1; q += nt) wait_eq(V.done_f + S.child_idx[q], epoch);
+  for (int i = tid; i < f; i += nt) w[i] = (i < k) ? x[c0 + i] : 0.0;
+  __syncthreads();
+  for (int q = ch0; q < ch1; ++q) {
+    const int c = S.child_idx[q];
+    const long long o = S.rows_ptr[c];
+    const int rc = (int)(S.rows_ptr[c + 1] - o);
+    for (int t = tid; t < rc; t += nt) w[S.rel[o + t]] += __ldcg(cbv + o + t);
+    __syncthreads();
+  }
+  const int* __restrict__ lp = N.lperm + c0;
+  for (int i = tid; i < f; i += nt) v[i] = (i < k) ? w[lp[i]] : w[i];
+  __syncthreads();
+  const double* __restrict__ P = N.L + S.L_off[s];
+  for (int t0 = 0; t0 < k; t0 += 32) {
+    const int nb = min(32, k - t0);
+    for (int t = tid; t < nb * nb; t += nt) {
+      int i = t % nb, q = t / nb;
+      Lb[i + q * 33] = P[(t0 + i) + (size_t)(t0 + q) * f];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double yi = (lane < nb) ? v[t0 + lane] : 0.0;
+      for (int q = 0; q < nb; ++q) {
+        double yq = __shfl_sync(0xffffffffu, yi, q);
+        if (lane > q && lane < nb) yi = fma(-Lb[lane + q * 33], yq, yi);
+      }
+      if (lane < nb) v[t0 + lane] = yi;
+    }
+    __syncthreads();
+    for (int i = t0 + nb + tid; i < f; i += nt) {
+      double acc = 0.0;
+#pragma unroll 8
+      for (int q = 0; q < nb; ++q) acc = fma(P[i + (size_t)(t0 + q) * f], v[t0 + q], acc);
+      v[i] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < k; t += nt) {
+    const int ty = N.ptype[c0 + t];
+    double y;
+    if (ty == 1) y = v[t] * N.dinv[c0 + t];
+    else if (ty == 2) y = v[t] * N.dinv[c0 + t] + v[t + 1] * N.doff[c0 + t];
+    else y = v[t - 1] * N.doff[c0 + t - 1] + v[t] * N.dinv[c0 + t];
+    x[c0 + t] = y;
+  }
+  double* __restrict__ out = cbv + S.rows_ptr[s];
+  for (int i = tid; i < r; i += nt) out[i] = v[k + i];
+  __syncthreads();
+  if (tid == 0) { __threadfence(); st_release(V.done_f + s, epoch); }
+}
+
+__device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+                        double* __restrict__ x) {
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const long long ro = S.rows_ptr[s];
+  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  double* v = sm;
+  double* Lb = sm + 2 * f;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int par = S.sn_parent[s];
+  if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
+  __syncthreads();
+  for (int i = tid; i < f; i += nt) v[i] = (i < k) ? x[c0 + i] : __ldcg(x + S.rows[ro + (i - k)]);
+  __syncthreads();
+  const double* __restrict__ P = N.L + S.L_off[s];
+  const int nblk = (k + 31) / 32;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int t0 = b * 32, nb = min(32, k - t0);
+    for (int t = tid; t < nb * nb; t += nt) {
+      int i = t % nb, q = t / nb;
+      Lb[i + q * 33] = P[(t0 + i) + (size_t)(t0 + q) * f];
+    }
+    for (int q = warp; q < nb; q += nwarp) {
+      const double* col = P + (size_t)(t0 + q) * f;
+      double acc = 0.0;
+      for (int i = t0 + nb + lane; i < f; i += 32) acc = fma(col[i], v[i], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) v[t0 + q] -= acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double zi = (lane < nb) ? v[t0 + lane] : 0.0;
+      for (int q = nb - 1; q >= 0; --q) {
+        double zq = __shfl_sync(0xffffffffu, zi, q);
+        if (lane < q) zi = fma(-Lb[q + lane * 33], zq, zi);
+      }
+      if (lane < nb) v[t0 + lane] = zi;
+    }
+    __syncthreads();
+  }
+  const int* __restrict__ lp = N.lperm + c0;
+  for (int t = tid; t < k; t += nt) x[c0 + lp[t]] = v[t];
+  __syncthreads();
+  if (tid == 0) { __threadfence(); st_release(V.done_b + s, epoch); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// big fronts: gather task + one task per 64-row block (forward) / 64-column block (backward)
+// ------------------------------------------------------------------------------------------------
+__device__ void big_gather(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch,
+                           const double* __restrict__ x, const double* __restrict__ cbv) {
+  // w = [x(cols) ; 0] + scatter(children update vectors), then the in-front pivot permutation; result in bigv.
+  // Children write disjoint... no: two children may hit the same parent row, so children are applied one
+  // after the other (deterministic), each child fully parallel.
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]), f = k + r;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* w = V.bigv + V.bigv_off[s];      // scratch (pre-permutation) lives in bigy, result in bigv
+  double* tmp = V.bigy + V.bigv_off[s];    // f doubles available (bigy has the same per-front extent)
+  const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
+  for (int q = ch0 + tid; q < ch1; q += nt) wait_eq(V.done_f + S.child_idx[q], epoch);
+  for (int i = tid; i < f; i += nt) tmp[i] = (i < k) ? x[c0 + i] : 0.0;
+  __syncthreads();
+  for (int q = ch0; q < ch1; ++q) {
+    const int c = S.child_idx[q];
+    const long long o = S.rows_ptr[c];
+    const int rc = (int)(S.rows_ptr[c + 1] - o);
+    for (int t = tid; t < rc; t += nt) tmp[S.rel[o + t]] += __ldcg(cbv + o + t);
+    __syncthreads();
+  }
+  const int* __restrict__ lp = N.lperm + c0;
+  for (int i = tid; i < f; i += nt) w[i] = (i < k) ? tmp[lp[i]] : tmp[i];
+  __syncthreads();
+  if (tid == 0) { __threadfence(); st_release(V.gflag + s, epoch); }
+}
+
+// forward block row b of big front s: rows [64b, min(f, 64b+64))
+// smem: ys[64] | part[4*64] | Lsq[64*65]
+__device__ void big_fwd_block(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
+                              double* sm, double* __restrict__ x, double* __restrict__ cbv) {
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]), f = k + r;
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31, warp = tid >> 5;
+  double* ys = sm;
+  double* part = sm + 64;
+  double* Lsq = sm + 64 + 256;
+  const int r0 = b * DF_BLK, nrow = min(DF_BLK, f - r0);
+  const int ncolblk_left = min(b, (k + DF_BLK - 1) / DF_BLK);   // column blocks strictly left of the diagonal block
+  const double* __restrict__ P = N.L + S.L_off[s];
+  const int* bf = V.bflag_f + V.boff[s];
+  const double* yb = V.bigy + V.bigv_off[s];
+  double acc = 0.0;
+  const int row = r0 + tx;
+  for (int c = 0; c < ncolblk_left; ++c) {
+    const int t0 = c * DF_BLK, ncol = min(DF_BLK, k - t0);
+    // the L tile does not depend on y: fetch it BEFORE waiting for the producer of y_c
+    double lt[16];
+    {
+      const double* base = P + row + (size_t)t0 * f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; lt[q] = (tx < nrow && t < ncol) ? base[(size_t)t * f] : 0.0; }
+    }
+    if (tid == 0) wait_eq(bf + c, epoch);
+    __syncthreads();
+    if (tid < ncol) ys[tid] = __ldcg(yb + t0 + tid);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; if (t < ncol) acc = fma(lt[q], ys[t], acc); }
+    __syncthreads();
+  }
+  part[ty * 64 + tx] = acc;
+  // v = w - acc ; then the diagonal part (columns [r0, min(k, r0+64)))
+  const int ndiag = max(0, min(k - r0, DF_BLK));
+  if (ndiag > 0) {
+    for (int t = tid; t < nrow * ndiag; t += blockDim.x) {
+      int i = t % nrow, q = t / nrow;
+      Lsq[i + q * 65] = P[(r0 + i) + (size_t)(r0 + q) * f];
+    }
+  }
+  if (tid == 0) wait_eq(V.gflag + s, epoch);
+  __syncthreads();
+  if (tid < 64) ys[tid] = (tid < nrow) ? __ldcg(V.bigv + V.bigv_off[s] + r0 + tid) - (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]) : 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    double v0 = ys[lane], v1 = ys[lane + 32];
+    for (int t = 0; t < ndiag; ++t) {
+      const double yt = (t < 32) ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
+      if (lane > t) v0 = fma(-Lsq[lane + t * 65], yt, v0);
+      if (lane + 32 > t) v1 = fma(-Lsq[lane + 32 + t * 65], yt, v1);
+    }
+    ys[lane] = v0; ys[lane + 32] = v1;
+  }
+  __syncthreads();
+  if (tid < nrow) {
+    const int i = r0 + tid;
+    if (i < k) {
+      V.bigy[V.bigv_off[s] + i] = ys[tid];   // y block for the rows below (pivoted order)
+      const int ty2 = N.ptype[c0 + i];
+      double y;
+      if (ty2 == 1) y = ys[tid] * N.dinv[c0 + i];
+      else if (ty2 == 2) y = ys[tid] * N.dinv[c0 + i] + ys[tid + 1] * N.doff[c0 + i];
+      else y = ys[tid - 1] * N.doff[c0 + i - 1] + ys[tid] * N.dinv[c0 + i];
+      x[c0 + i] = y;
+    } else cbv[S.rows_ptr[s] + (i - k)] = ys[tid];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (r0 < k) st_release((int*)bf + b, epoch);
+    const int nblk = (f + DF_BLK - 1) / DF_BLK;
+    const int old = atomicAdd(V.bcnt + s, 1);
+    if ((old + 1) % nblk == 0) { __threadfence(); st_release(V.done_f + s, epoch); }
+  }
+}
+
+// backward block column b of big front s: columns [64b, min(k, 64b+64))
+// smem: xs[64] | red[DF_THREADS*16 -> done with shuffles] ...
+__device__ void big_bwd_block(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
+                              double* sm, double* __restrict__ x) {
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const long long ro = S.rows_ptr[s];
+  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31, warp = tid >> 5;
+  double* xs = sm;                 // 64
+  double* colacc = sm + 64;        // 64
+  double* red = sm + 128;          // 8 warps x 16
+  double* Lsq = sm + 128 + 128;    // 64 x 65
+  const int t0 = b * DF_BLK, ncol = min(DF_BLK, k - t0), t1 = t0 + ncol;
+  const int nkb = (k + DF_BLK - 1) / DF_BLK;
+  const double* __restrict__ P = N.L + S.L_off[s];
+  const int* bf = V.bflag_b + V.boff[s];
+  double pacc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
+  // stage the diagonal block first (independent of everything we wait for)
+  for (int t = tid; t < ncol * ncol; t += blockDim.x) {
+    int i = t % ncol, q = t / ncol;
+    Lsq[i + q * 65] = P[(t0 + i) + (size_t)(t0 + q) * f];
+  }
+  const int par = S.sn_parent[s];
+  if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
+  __syncthreads();
+  // rows below the block are processed in chunks of 64: first the contribution-block rows (ancestors'
+  // final values), then this front's later pivot blocks from the last one down as they get published.
+  const int nchunk_cb = (r + DF_BLK - 1) / DF_BLK;
+  for (int ch = 0; ch < nchunk_cb + (nkb - 1 - b); ++ch) {
+    int rbase, nr, c = -1;
+    if (ch < nchunk_cb) { rbase = k + ch * DF_BLK; nr = min(DF_BLK, f - rbase); }
+    else { c = nkb - 1 - (ch - nchunk_cb); rbase = c * DF_BLK; nr = min(DF_BLK, k - rbase); }
+    // the L tile does not depend on x: fetch it BEFORE waiting for the producer of this row chunk
+    double lt[16];
+    {
+      const double* base = P + (rbase + tx) + (size_t)t0 * f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; lt[q] = (tx < nr && t < ncol) ? base[(size_t)t * f] : 0.0; }
+    }
+    if (c < 0) {
+      if (tid < nr) xs[tid] = __ldcg(x + S.rows[ro + (rbase - k) + tid]);
+    } else {
+      if (tid == 0) wait_eq(bf + c, epoch);
+      __syncthreads();
+      if (tid < nr) xs[tid] = __ldcg(V.bigy + V.bigv_off[s] + rbase + tid);
+    }
+    __syncthreads();
+    if (tx < nr) {
+      const double xi = xs[tx];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], xi, pacc[q]);
+    }
+    __syncthreads();
+  }
+  // reduce pacc over the 64 row-threads of each ty group: warp shuffle then across the two half-warps
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    double a = pacc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[warp * 16 + q] = a;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    // column t = tid: ty = t & 3, q = t >> 2 ; warps 2*ty and 2*ty+1 hold the two halves
+    const int tyc = tid & 3, q = tid >> 2;
+    colacc[tid] = red[(2 * tyc) * 16 + q] + red[(2 * tyc + 1) * 16 + q];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double z0 = (lane < ncol) ? x[c0 + t0 + lane] - colacc[lane] : 0.0;
+    double z1 = (lane + 32 < ncol) ? x[c0 + t0 + lane + 32] - colacc[lane + 32] : 0.0;
+    for (int q = ncol - 1; q >= 0; --q) {
+      const double zq = (q < 32) ? __shfl_sync(0xffffffffu, z0, q) : __shfl_sync(0xffffffffu, z1, q - 32);
+      if (lane < q) z0 = fma(-Lsq[q + lane * 65], zq, z0);
+      if (lane + 32 < q) z1 = fma(-Lsq[q + (lane + 32) * 65], zq, z1);
+    }
+    xs[lane] = z0; xs[lane + 32] = z1;
+  }
+  __syncthreads();
+  if (tid < ncol) {
+    V.bigy[V.bigv_off[s] + t0 + tid] = xs[tid];                 // pivoted order, for the blocks to the left
+    x[c0 + N.lperm[c0 + t0 + tid]] = xs[tid];                   // final value (permutation is panel-local)
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    st_release((int*)bf + b, epoch);
+    const int old = atomicAdd(V.bcnt_b + s, 1);
+    if ((old + 1) % nkb == 0) { __threadfence(); st_release(V.done_b + s, epoch); }
+  }
+  (void)t1;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool FWD>
+__global__ void __launch_bounds__(DF_THREADS) k_solve_dataflow(DevSym S, DevNum N, DevSolve V, int epoch,
+                                                                unsigned long long ticket_base,
+                                                                double* __restrict__ x, double* __restrict__ cbv) {
+  extern __shared__ double sm[];
+  __shared__ unsigned long long s_ticket;
+  const SolveTask* tasks = FWD ? V.tasks : V.tasks_bwd;
+  const int ntasks = FWD ? V.ntasks_fwd : V.ntasks_bwd;
+  while (true) {
+    if (threadIdx.x == 0) s_ticket = atomicAdd(V.ticket + (FWD ? 0 : 1), 1ull) - ticket_base;
+    __syncthreads();
+    const unsigned long long tk = s_ticket;
+    __syncthreads();
+    if (tk >= (unsigned long long)ntasks) return;
+    const SolveTask T = tasks[tk];
+    if (T.type == ST_SMALL) {
+      const int w = threadIdx.x >> 5;
+      if (w < T.b) {
+        const int s = V.bundle[T.a + w];
+        double* wsm = sm + (size_t)w * DF_SMALL_SMEM;
+        if (FWD) small_fwd(S, N, V, s, epoch, wsm, x, cbv); else small_bwd(S, N, V, s, epoch, wsm, x);
+      }
+    } else if (T.type == ST_MID) {
+      if (FWD) mid_fwd(S, N, V, T.a, epoch, sm, x, cbv); else mid_bwd(S, N, V, T.a, epoch, sm, x);
+    } else if (T.type == ST_BIG_GATHER) {
+      big_gather(S, N, V, T.a, epoch, x, cbv);
+    } else {
+      if (FWD) big_fwd_block(S, N, V, T.a, T.b, epoch, sm, x, cbv); else big_bwd_block(S, N, V, T.a, T.b, epoch, sm, x);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace b200

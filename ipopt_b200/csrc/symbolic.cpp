@@ -126,7 +126,14 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
   if (vals && opt.pair_saddle) {
     std::vector<double> diag(n, 0.0);
     for (int64_t u = 0; u < nu; ++u) if (ur[u] == uc[u]) diag[ur[u]] = uv[u];
-    for (int i = 0; i < n; ++i) if (diag[i] == 0.0) { saddle[i] = 1; S.n_saddle++; }
+    // saddle row = (numerically) zero diagonal relative to its off-diagonal entries: the constraint block of the
+    // KKT system arrives as explicit zeros, or as -delta_c ~ 1e-8 after a regularisation
+    // (reference src/Algorithm/IpStdAugSystemSolver.cpp:420-426)
+    for (int i = 0; i < n; ++i) {
+      double om = 0.0;
+      for (int64_t p = xadj[i]; p < xadj[i + 1]; ++p) om = std::max(om, adjw[p]);
+      if (std::fabs(diag[i]) <= 1e-4 * om || (diag[i] == 0.0)) { saddle[i] = 1; S.n_saddle++; }
+    }
     struct Cand { double w; int s, x; };
     std::vector<Cand> cand;
     for (int i = 0; i < n; ++i) if (saddle[i])
