@@ -132,7 +132,7 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
     for (int i = 0; i < n; ++i) {
       double om = 0.0;
       for (int64_t p = xadj[i]; p < xadj[i + 1]; ++p) om = std::max(om, adjw[p]);
-      if (std::fabs(diag[i]) <= 1e-4 * om || (diag[i] == 0.0)) { saddle[i] = 1; S.n_saddle++; }
+      if (std::fabs(diag[i]) <= 1e-7 * om || (diag[i] == 0.0)) { saddle[i] = 1; S.n_saddle++; }
     }
     struct Cand { double w; int s, x; };
     std::vector<Cand> cand;
