@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -76,7 +77,7 @@ struct Solver {
   DevBuf<int> d_useg_src, d_u_row, d_u_col, d_irn, d_jcn;
   DevBuf<long long> d_rows_ptr, d_uent_ptr, d_u_dst64, d_L_off, d_cb_off, d_useg_ptr;
   DevBuf<unsigned> d_u_dst;
-  DevBuf<double> d_vals, d_uval, d_L, d_W, d_CB, d_dinv, d_doff, d_scale, d_x, d_cbv, d_rhs, d_res;
+  DevBuf<double> d_vals, d_uval, d_L, d_W, d_CB, d_dinv, d_doff, d_scale, d_x, d_cbv, d_rhs, d_res, d_colmax;
   DevBuf<int> d_ptype, d_lperm, d_bperm, d_counters;
   DevBuf<unsigned long long> d_rmax;
   DevSym DS;
@@ -87,11 +88,16 @@ struct Solver {
   DevBuf<int> d_bundle, d_done_f, d_done_b, d_gflag, d_bflag_f, d_bflag_b, d_bcnt, d_bcnt_b, d_boff;
   DevBuf<long long> d_bigv_off;
   DevBuf<double> d_bigv, d_bigy;
-  DevBuf<unsigned long long> d_ticket;
+  DevBuf<unsigned long long> d_ticket, d_tlog;
+  std::vector<SolveTask> h_tasks;   // fwd then bwd (debug timeline)
   DevSolve DV;
   int solve_epoch = 0, df_grid = 0;
   unsigned long long ticket_f = 0, ticket_b = 0;
   int num_sms = 148;
+  cudaGraph_t fgraph = nullptr;
+  cudaGraphExec_t fgraph_exec = nullptr;
+  double fgraph_u = -1.0;
+  int fgraph_launches = 0;
 
   ~Solver() {
     if (h_vals) cudaFreeHost(h_vals);
@@ -99,6 +105,8 @@ struct Solver {
     if (h_counters) cudaFreeHost(h_counters);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (fgraph_exec) cudaGraphExecDestroy(fgraph_exec);
+    if (fgraph) cudaGraphDestroy(fgraph);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -114,6 +122,8 @@ struct Solver {
   } while (0)
 
 static int run_analysis(Solver* sv, const double* vals) {
+  if (sv->fgraph_exec) { cudaGraphExecDestroy(sv->fgraph_exec); sv->fgraph_exec = nullptr; }
+  if (sv->fgraph) { cudaGraphDestroy(sv->fgraph); sv->fgraph = nullptr; }
   AnalyseOptions ao;
   ao.ordering = sv->opt.ordering;
   ao.pair_saddle = sv->opt.pair_saddle;
@@ -154,6 +164,7 @@ static int run_analysis(Solver* sv, const double* vals) {
   CU(sv->d_cbv.alloc(std::max<size_t>(S.rows.size(), 1)));
   CU(sv->d_ptype.alloc(n)); CU(sv->d_lperm.alloc(n)); CU(sv->d_bperm.alloc(n));
   CU(sv->d_counters.alloc(CNT_N));
+  CU(sv->d_colmax.alloc(n));
   CU(sv->d_rmax.alloc(n));
   CU(cudaMemsetAsync(sv->d_rmax.p, 0, n * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(sv->d_L.p, 0, sv->d_L.n * sizeof(double), st));
@@ -168,7 +179,7 @@ static int run_analysis(Solver* sv, const double* vals) {
   DevNum& N = sv->DN;
   N.L = sv->d_L.p; N.W = sv->d_W.p; N.CB = sv->d_CB.p; N.uval = sv->d_uval.p;
   N.dinv = sv->d_dinv.p; N.doff = sv->d_doff.p; N.ptype = sv->d_ptype.p;
-  N.lperm = sv->d_lperm.p; N.bperm = sv->d_bperm.p; N.counters = sv->d_counters.p;
+  N.lperm = sv->d_lperm.p; N.bperm = sv->d_bperm.p; N.counters = sv->d_counters.p; N.colmax = sv->d_colmax.p;
 
   // ---- launch plan: per level, big fronts first then small ones by descending order --------
   const int smax = sv->opt.smem_front_max;
@@ -260,8 +271,8 @@ static int run_analysis(Solver* sv, const double* vals) {
         for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
           int s = S.level_sn[q];
           if (S.f(s) > MIDMAX) continue;
-          if (S.f(s) > 32) T.push_back({ST_MID, s, 0, 0});
-          else smalls.push_back(s);
+          if (S.f(s) > 64) T.push_back({ST_MID, s, 0, 0});
+          else smalls.push_back(s);   // warp-per-front classes (<= 32 staged in smem, 33..64 streamed)
         }
         for (size_t q = 0; q < smalls.size(); q += 8) {
           int cnt = (int)std::min<size_t>(8, smalls.size() - q);
@@ -297,6 +308,12 @@ static int run_analysis(Solver* sv, const double* vals) {
     V.bflag_f = sv->d_bflag_f.p; V.bflag_b = sv->d_bflag_b.p; V.bcnt = sv->d_bcnt.p; V.bcnt_b = sv->d_bcnt_b.p;
     V.boff = sv->d_boff.p; V.bigv_off = sv->d_bigv_off.p; V.bigv = sv->d_bigv.p; V.bigy = sv->d_bigy.p;
     V.ticket = sv->d_ticket.p;
+    V.tlog = nullptr;
+    if (getenv("B200_SOLVE_TIMELINE")) {
+      CU(sv->d_tlog.alloc(2 * (tf.size() + tb.size())));
+      V.tlog = sv->d_tlog.p;
+      sv->h_tasks = tf; sv->h_tasks.insert(sv->h_tasks.end(), tb.begin(), tb.end());
+    }
     const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
     CU(cudaFuncSetAttribute(k_solve_dataflow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
     CU(cudaFuncSetAttribute(k_solve_dataflow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
@@ -344,6 +361,7 @@ static int enqueue_factor(Solver* sv) {
   int& L = sv->launches;
   L = 0;
   CU(cudaMemsetAsync(sv->d_counters.p, 0, CNT_N * sizeof(int), st));
+  CU(cudaMemsetAsync(sv->d_colmax.p, 0, (size_t)n * sizeof(double), st));
   k_sum_dups<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_useg_ptr.p, sv->d_useg_src.p, sv->d_vals.p, sv->d_uval.p); ++L;
   k_fill<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_scale.p, 1.0); ++L;
   for (int sw = 0; sw < sv->opt.scaling; ++sw) {
@@ -372,6 +390,7 @@ static int enqueue_factor(Solver* sv) {
     }
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
+      k_big_colmax0<<<P.big_cnt, 256, 0, st>>>(D, N, bl); ++L;
       for (int jb = 0; jb < P.big_kmax; jb += NB) {
         k_big_diag<<<P.big_cnt, 32, 0, st>>>(D, N, bl, jb); ++L;
         int rows_below = P.big_fmax - jb;  // upper bound
@@ -441,8 +460,27 @@ static int do_factor(Solver* sv, const double* d_vals_ext, bool from_host, int c
     CU(cudaMemcpyAsync(sv->d_vals.p, d_vals_ext, sv->nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
   sv->have_dev_vals = true;
   if (!from_host) CU(cudaEventRecord(sv->ev0, st));  // device-resident timing excludes the staging copy
-  int rc = enqueue_factor(sv);
-  if (rc != B200LDLT_SUCCESS) return rc;
+  int rc;
+  if (sv->opt.use_graph == 1) {
+    // the launch sequence is fixed by the symbolic structure: capture it once, replay it every factorisation
+    if (!sv->fgraph_exec || sv->fgraph_u != sv->pivtol) {
+      if (sv->fgraph_exec) { cudaGraphExecDestroy(sv->fgraph_exec); sv->fgraph_exec = nullptr; }
+      if (sv->fgraph) { cudaGraphDestroy(sv->fgraph); sv->fgraph = nullptr; }
+      CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue_factor(sv);
+      cudaError_t ce = cudaStreamEndCapture(st, &sv->fgraph);
+      if (rc != B200LDLT_SUCCESS) return rc;
+      CU(ce);
+      CU(cudaGraphInstantiate(&sv->fgraph_exec, sv->fgraph, 0));
+      sv->fgraph_u = sv->pivtol;
+      sv->fgraph_launches = sv->launches;
+    }
+    sv->launches = sv->fgraph_launches;
+    CU(cudaGraphLaunch(sv->fgraph_exec, st));
+  } else {
+    rc = enqueue_factor(sv);
+    if (rc != B200LDLT_SUCCESS) return rc;
+  }
   return finish_factor(sv, check_inertia, expected_neg, num_neg);
 }
 
@@ -501,7 +539,7 @@ void b200ldlt_default_options(b200ldlt_options* o) {
   o->pivtolmax = 1e-4;
   o->tiny = 1e-15;
   o->smem_front_max = 128;
-  o->use_graph = 0;
+  o->use_graph = 1;   /* 1 = CUDA-graph replay of the factorisation + dataflow solve; 0 = plain launches; 2 = level-per-launch solve */
   o->verbose = 0;
 }
 
@@ -638,6 +676,24 @@ int b200ldlt_solve(b200ldlt_handle h, int nrhs, double* rhs) {
   cudaEventElapsedTime(&sv->info.ms_solve_gpu, sv->ev0, sv->ev1);
   sv->info.launches_solve = sv->launches;
   memcpy(rhs, sv->h_rhs, n * nrhs * sizeof(double));
+  return B200LDLT_SUCCESS;
+}
+
+/* debug: write the per-task timeline of the last solve (needs env B200_SOLVE_TIMELINE=1 at analyse time) */
+int b200ldlt_dump_solve_timeline(b200ldlt_handle h, const char* path) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->DV.tlog) return B200LDLT_FATAL_ERROR;
+  std::vector<unsigned long long> t(sv->d_tlog.n);
+  CU(cudaMemcpy(t.data(), sv->d_tlog.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  FILE* fp = fopen(path, "w");
+  if (!fp) return B200LDLT_FATAL_ERROR;
+  for (size_t i = 0; i < sv->h_tasks.size(); ++i) {
+    const SolveTask& T = sv->h_tasks[i];
+    int s = T.type == ST_SMALL ? -1 : T.a;
+    fprintf(fp, "%zu %d %d %d %d %d %llu %llu\n", i, i < (size_t)sv->DV.ntasks_fwd ? 0 : 1, T.type, T.a, T.b,
+            s >= 0 ? sv->S.sn_level[s] : -1, t[2 * i], t[2 * i + 1]);
+  }
+  fclose(fp);
   return B200LDLT_SUCCESS;
 }
 

@@ -212,7 +212,13 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         if (noise || !(fabs(d) > tiny)) {  // zero (or NaN) pivot: static perturbation, reported as SINGULAR
           d = (d < 0.0) ? -1.5e-8 : 1.5e-8;
           if (tid == 0) ++c_tiny;
-        } else if (tid == 0) ++c_forced;
+        } else {
+          // static pivoting: lift the pivot to the threshold (see warp_ldlt32); cv2[j] holds max|column j|
+          double offmax = 0.0;
+          for (int i = j + 1; i < f; ++i) offmax = fmax(offmax, fabs(F[i + j * ld]));
+          d = copysign(fmax(fabs(d), 1e-8 * offmax), d);
+          if (tid == 0) ++c_forced;
+        }
       }
       const double dv = d;
       gsync<WARP>();
@@ -314,11 +320,15 @@ __device__ __forceinline__ void wred_max_idx(double& v, int& idx) {
 
 __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const double u, const double tiny,
                             double* __restrict__ Lraw, int* __restrict__ order, int* __restrict__ pt,
-                            double* __restrict__ dinv_s, double* __restrict__ doff_s, int* counters) {
+                            double* __restrict__ dinv_s, double* __restrict__ doff_s,
+                            double* __restrict__ colbuf /* 64 doubles of shared memory, 16-byte aligned */,
+                            const double gext /* lane c: max |entry| of column c in rows OUTSIDE the block (0 if none) */,
+                            int* counters) {
   const int lane = threadIdx.x & 31;
-  int cid[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) cid[c] = (c < f) ? c : 0;
+  // mypos = current POSITION of the column whose original index is this lane (columns stay compacted)
+  int mypos = lane;
+  colbuf[lane] = 0.0; colbuf[32 + lane] = 0.0;
+  __syncwarp();
   unsigned alive = (f >= 32) ? 0xffffffffu : ((1u << f) - 1u);
   unsigned cand = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   int nc = k, npass = k, t = 0, progress = 0;
@@ -329,37 +339,35 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       if (progress > 0) { npass = nc; progress = 0; }
       else { forced = true; npass = nc; }
     }
-    int g0 = cid[0];
     const bool me_alive = (alive >> lane) & 1u;
     const bool me_cand = (cand >> lane) & 1u;
+    int g0 = __ffs(__ballot_sync(0xffffffffu, me_alive && mypos == 0)) - 1;
     // ---- pivot search on column 0 ----
     const double v0 = fabs(a[0]);
     double lam = (me_cand && lane != g0) ? v0 : -1.0;
     int r = (me_cand && lane != g0) ? lane : 64;
     wred_max_idx(lam, r);
     double gam = (me_alive && !me_cand) ? v0 : 0.0;
-    gam = warp_max(gam);
+    gam = fmax(warp_max(gam), __shfl_sync(0xffffffffu, gext, g0));
     if (lam < 0.0) { lam = 0.0; r = -1; }
     const double ajj = fabs(__shfl_sync(0xffffffffu, a[0], g0));
     const bool ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
     int type = 0;
     bool noise = false;
-    if (forced) { type = 1; noise = !(fmax(ajj, fmax(lam, gam)) > 1e-12); }
+    const double colmax_f = fmax(lam, gam);
+    if (forced) { type = 1; noise = !(fmax(ajj, colmax_f) > 1e-12); }
     else if (lam == 0.0 || r < 0) { if (ok1) type = 1; }
     else if (ok1 && ajj >= BK_ALPHA * lam) type = 1;
     else {
       // bring column r to position 1
-      int myc = 0;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) myc = (c == lane) ? cid[c] : myc;
-      const unsigned hit = __ballot_sync(0xffffffffu, myc == r && lane < nc && lane >= 1);
-      const int p = __ffs(hit) - 1;  // >= 1 because r is an alive candidate column different from g0
+      const int p = __shfl_sync(0xffffffffu, mypos, r);
       if (p > 1) {
-        double ta = a[1]; int tc = cid[1];
+        double ta = a[1];
 #pragma unroll
         for (int c = 2; c < 32; ++c)
-          if (c == p) { double x = a[c]; a[c] = ta; ta = x; int y = cid[c]; cid[c] = tc; tc = y; }
-        a[1] = ta; cid[1] = tc;
+          if (c == p) { double x = a[c]; a[c] = ta; ta = x; }
+        a[1] = ta;
+        if (mypos == 1) mypos = p; else if (mypos == p) mypos = 1;
       }
       const double v1 = fabs(a[1]);
       double sig = (me_cand && lane != r) ? v1 : 0.0;
@@ -367,13 +375,17 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       const bool other = me_alive && lane != g0 && lane != r;
       double cj = other ? v0 : 0.0, cr = other ? v1 : 0.0;
       sig = warp_max(sig); gamr = warp_max(gamr); cj = warp_max(cj); cr = warp_max(cr);
+      {
+        const double ge_r = __shfl_sync(0xffffffffu, gext, r), ge_j = __shfl_sync(0xffffffffu, gext, g0);
+        gamr = fmax(gamr, ge_r); cr = fmax(cr, ge_r); cj = fmax(cj, ge_j);
+      }
       const double crr = __shfl_sync(0xffffffffu, a[1], r);
       const double arr = fabs(crr);
       if (ok1 && ajj * sig >= BK_ALPHA * lam * lam) type = 1;
       else if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, gamr)) {
         // 1x1 on r: swap positions 0 and 1
         double x = a[0]; a[0] = a[1]; a[1] = x;
-        int y = cid[0]; cid[0] = cid[1]; cid[1] = y;
+        if (mypos == 0) mypos = 1; else if (mypos == 1) mypos = 0;
         g0 = r;
         type = 1;
       } else {
@@ -386,13 +398,14 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
     }
     if (type == 0) {
       // park column 0 behind the remaining candidates (position nc-1) and try the next one
-      const double ta = a[0]; const int tc = cid[0];
+      const double ta = a[0];
 #pragma unroll
       for (int c = 0; c < 31; ++c) {
-        if (c < nc - 1) { a[c] = a[c + 1]; cid[c] = cid[c + 1]; }
-        else if (c == nc - 1) { a[c] = ta; cid[c] = tc; }
+        if (c < nc - 1) a[c] = a[c + 1];
+        else if (c == nc - 1) a[c] = ta;
       }
-      if (nc == 32) { a[31] = ta; cid[31] = tc; }
+      if (nc == 32) a[31] = ta;
+      if (mypos == 0) mypos = nc - 1; else if (mypos < nc) mypos -= 1;
       --npass;
       continue;
     }
@@ -400,37 +413,55 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       double dd = __shfl_sync(0xffffffffu, a[0], g0);
       if (forced) {
         if (noise || !(fabs(dd) > tiny)) { dd = (dd < 0.0) ? -1.5e-8 : 1.5e-8; ++c_tiny; }
-        else ++c_forced;
+        else {
+          // static pivoting: a pivot that fails the threshold test everywhere in its supernode is lifted to the
+          // threshold (|l_ij| stays <= 1e8; the factors are those of a matrix perturbed by <= 1e-8 |column|,
+          // which the caller's iterative refinement absorbs).  Counted and reported in num_forced.
+          dd = copysign(fmax(fabs(dd), 1e-8 * colmax_f), dd);
+          ++c_forced;
+        }
       }
       const double c0v = a[0];
       const double l = (me_alive && lane != g0) ? c0v / dd : 0.0;
+      // pivot row by position: F[g0][col at position c] = F[that col's row][g0] = that lane's a[0]
+      if (me_alive) colbuf[mypos] = c0v;
+      __syncwarp();
+      const double2* cb2 = reinterpret_cast<const double2*>(colbuf);
 #pragma unroll
-      for (int c = 1; c < 32; ++c) {
-        const double pc = __shfl_sync(0xffffffffu, c0v, cid[c]);
-        a[c] = fma(-l, pc, a[c]);
+      for (int c2 = 0; c2 < 16; ++c2) {
+        const double2 pp = cb2[c2];
+        if (c2 > 0) a[2 * c2] = fma(-l, pp.x, a[2 * c2]);
+        a[2 * c2 + 1] = fma(-l, pp.y, a[2 * c2 + 1]);
       }
+      __syncwarp();
       Lraw[lane * 33 + t] = l;
       if (lane == 0) { order[t] = g0; pt[t] = 1; dinv_s[t] = 1.0 / dd; doff_s[t] = 0.0; }
       if (dd < 0.0) ++c_neg;
       alive &= ~(1u << g0); cand &= ~(1u << g0);
 #pragma unroll
-      for (int c = 0; c < 31; ++c) { a[c] = a[c + 1]; cid[c] = cid[c + 1]; }
-      a[31] = 0.0; cid[31] = 0;
+      for (int c = 0; c < 31; ++c) a[c] = a[c + 1];
+      a[31] = 0.0;
+      mypos -= 1;
       nc -= 1; npass = max(npass - 1, 0); t += 1;
     } else {
       const double pa = __shfl_sync(0xffffffffu, a[0], g0), pb = __shfl_sync(0xffffffffu, a[0], r);
       const double pc2 = __shfl_sync(0xffffffffu, a[1], r);
       const double det = pa * pc2 - pb * pb;
-      const double c1 = a[0], c2 = a[1];
+      const double c1 = a[0], c2v = a[1];
       const bool other = me_alive && lane != g0 && lane != r;
-      const double l1 = other ? (pc2 * c1 - pb * c2) / det : 0.0;
-      const double l2 = other ? (pa * c2 - pb * c1) / det : 0.0;
+      const double l1 = other ? (pc2 * c1 - pb * c2v) / det : 0.0;
+      const double l2 = other ? (pa * c2v - pb * c1) / det : 0.0;
+      if (me_alive) { colbuf[mypos] = c1; colbuf[32 + mypos] = c2v; }
+      __syncwarp();
+      const double2* cb1 = reinterpret_cast<const double2*>(colbuf);
+      const double2* cb2 = reinterpret_cast<const double2*>(colbuf + 32);
 #pragma unroll
-      for (int c = 2; c < 32; ++c) {
-        const double q1 = __shfl_sync(0xffffffffu, c1, cid[c]);
-        const double q2 = __shfl_sync(0xffffffffu, c2, cid[c]);
-        a[c] = fma(-l2, q2, fma(-l1, q1, a[c]));
+      for (int q = 1; q < 16; ++q) {
+        const double2 p1 = cb1[q], p2 = cb2[q];
+        a[2 * q] = fma(-l2, p2.x, fma(-l1, p1.x, a[2 * q]));
+        a[2 * q + 1] = fma(-l2, p2.y, fma(-l1, p1.y, a[2 * q + 1]));
       }
+      __syncwarp();
       Lraw[lane * 33 + t] = l1;
       Lraw[lane * 33 + t + 1] = l2;
       if (lane == 0) {
@@ -441,8 +472,9 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       if (det < 0.0) c_neg += 1; else if (pa < 0.0) c_neg += 2;
       alive &= ~((1u << g0) | (1u << r)); cand &= ~((1u << g0) | (1u << r));
 #pragma unroll
-      for (int c = 0; c < 30; ++c) { a[c] = a[c + 2]; cid[c] = cid[c + 2]; }
-      a[30] = 0.0; a[31] = 0.0; cid[30] = 0; cid[31] = 0;
+      for (int c = 0; c < 30; ++c) a[c] = a[c + 2];
+      a[30] = 0.0; a[31] = 0.0;
+      mypos -= 2;
       nc -= 2; npass = max(npass - 2, 0); t += 2;
     }
     ++progress;
@@ -534,7 +566,7 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
 // Class XS: fronts of order <= 32, ONE WARP per front (4 fronts per CTA), factorisation in registers.
 // smem per warp: F/Lraw[33*32] doubles | dinv_s[32] | doff_s[32] | order[32] | pt[32]
 // --------------------------------------------------------------------------------------------
-#define XS_SMEM_PER_WARP ((33 * 32 + 64) * 8 + 64 * 4)
+#define XS_SMEM_PER_WARP ((33 * 32 + 64 + 64) * 8 + 64 * 4)
 __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const int* __restrict__ front_list, int nfronts) {
   extern __shared__ double smem[];
   const int group = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -544,7 +576,8 @@ __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const in
   const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const int f = k + r;
   double* F = (double*)((char*)smem + (size_t)(threadIdx.x >> 5) * XS_SMEM_PER_WARP);
-  double* dinv_s = F + 33 * 32;
+  double* colbuf = F + 33 * 32;       // 64 doubles (offset 8448 B: 16-byte aligned)
+  double* dinv_s = colbuf + 64;
   double* doff_s = dinv_s + 32;
   int* order = (int*)(doff_s + 32);
   int* pt = order + 32;
@@ -580,7 +613,7 @@ __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const in
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = F[lane + c * ld];   // lanes >= f / columns >= f read zeros
   __syncwarp();
-  warp_ldlt32(a, f, k, N.u, N.tiny, F, order, pt, dinv_s, doff_s, N.counters);
+  warp_ldlt32(a, f, k, N.u, N.tiny, F, order, pt, dinv_s, doff_s, colbuf, 0.0, N.counters);
   // L panel in pivot order
   double* __restrict__ P = N.L + S.L_off[s];
   const int orig = (lane < k) ? order[lane] : lane;
@@ -658,10 +691,27 @@ __global__ void k_big_extend_add(DevSym S, DevNum N, const int* __restrict__ fro
   }
 }
 
+// column maxima of the first panel below its diagonal block (later panels get theirs from k_big_update)
+__global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_list) {
+  const int s = front_list[blockIdx.x];
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int nb = min(NB, k);
+  const double* __restrict__ P = N.L + S.L_off[s];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int j = warp; j < nb; j += nwarp) {
+    double m = 0.0;
+    for (int i = nb + lane; i < f; i += 32) m = fmax(m, fabs(P[i + (size_t)j * f]));
+    m = warp_max(m);
+    if (lane == 0) N.colmax[c0 + j] = m;
+  }
+}
+
 // factor the NB x NB diagonal block at panel offset jb (pivoting restricted to the block).
 // ONE WARP per front, block held in registers (warp_ldlt32).
 __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
   __shared__ double T[33 * NB];
+  __shared__ __align__(16) double colbuf[64];
   __shared__ double dinv_s[NB], doff_s[NB];
   __shared__ int order[NB], pt[NB];
   const int s = front_list[blockIdx.x];
@@ -684,7 +734,8 @@ __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* 
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? T[lane * 33 + c] : T[c * 33 + lane];
   __syncwarp();
-  warp_ldlt32(a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, N.counters);
+  const double gext = (lane < nb) ? N.colmax[c0 + jb + lane] : 0.0;
+  warp_ldlt32(a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colbuf, gext, N.counters);
   // write the block back in pivot order: L[t2][t] = Lraw[order[t2]][t]
   const int mine = (lane < nb) ? order[lane] : 0;
 #pragma unroll
@@ -790,7 +841,7 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
 __device__ __forceinline__ void tile_syrk(double* __restrict__ C, long long ldc,
                                           const double* __restrict__ A,
                                           const double* __restrict__ Bm, long long ld, int M, int Nn,
-                                          int K, int ti, int tj) {
+                                          int K, int ti, int tj, double* colmax_next = nullptr) {
   __shared__ double As[TK][TM + 1];
   __shared__ double Bs[TK][TM + 1];
   const int i0 = ti * TM, j0 = tj * TM;
@@ -826,7 +877,13 @@ __device__ __forceinline__ void tile_syrk(double* __restrict__ C, long long ldc,
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       int gi = i0 + tx + 16 * q, gj = j0 + ty + 16 * p;
-      if (gi < M && gj < Nn && gi >= gj) C[gi + (long long)gj * ldc] -= acc[q][p];
+      if (gi < M && gj < Nn && gi >= gj) {
+        const double nv = C[gi + (long long)gj * ldc] - acc[q][p];
+        C[gi + (long long)gj * ldc] = nv;
+        // the first 32 trailing columns are the NEXT panel: record their maxima below its diagonal block
+        if (colmax_next && gj < NB && gi >= NB)
+          atomicMax(reinterpret_cast<unsigned long long*>(colmax_next + gj), (unsigned long long)__double_as_longlong(fabs(nv)));
+      }
     }
 }
 
@@ -842,7 +899,7 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
   double* P = N.L + S.L_off[s];
   const double* Wp = N.W + S.L_off[s];
   tile_syrk(P + o + (long long)o * f, f, P + o + (long long)jb * f, Wp + o + (long long)jb * f, f, M, Nn,
-            NB, blockIdx.x, blockIdx.y);
+            NB, blockIdx.x, blockIdx.y, N.colmax + S.sn_start[s] + o);
 }
 
 // Schur complement: CB -= L21 * (L21 D)^T  (the dense contraction of the front)

@@ -33,6 +33,7 @@ struct DevNum {
   int* ptype;       // n : 1 = 1x1, 2 = first of 2x2, 3 = second of 2x2
   int* lperm;       // n : pivot position t of supernode s holds pre-pivot local column lperm[start+t]
   int* bperm;       // n : block-local permutation of the last panel step (big fronts)
+  double* colmax;   // n : big fronts only: max |entry| of a panel column BELOW its 32x32 diagonal block at panel start
   int* counters;    // CNT_N
   double u;         // pivot threshold
   double tiny;      // zero-pivot threshold (scaled matrix)

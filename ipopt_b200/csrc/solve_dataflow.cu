@@ -41,6 +41,7 @@ struct DevSolve {
   double* bigv;                // assembled+permuted rhs of big fronts
   double* bigy;                // y / x blocks of big fronts in pivoted order
   unsigned long long* ticket;  // [0] fwd, [1] bwd (monotonic)
+  unsigned long long* tlog;    // optional (debug): 2 timestamps per task, fwd then bwd; nullptr = off
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -103,7 +104,7 @@ __device__ void small_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, i
     x[c0 + lane] = y;
   } else if (lane < f) cbv[ro + lane - k] = v;
   __syncwarp();
-  if (lane == 0) { __threadfence(); st_release(V.done_f + s, epoch); }
+  if (lane == 0) { st_release(V.done_f + s, epoch); }
 }
 
 __device__ void small_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
@@ -134,7 +135,115 @@ __device__ void small_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, i
   }
   if (lane < k) x[c0 + N.lperm[c0 + lane]] = v;
   __syncwarp();
-  if (lane == 0) { __threadfence(); st_release(V.done_b + s, epoch); }
+  if (lane == 0) { st_release(V.done_b + s, epoch); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fronts of order 33..64: one warp per front, two rows per lane (lane, lane+32), no shared-memory staging:
+// the L loads do not depend on the running vector, so they are issued ahead of the shuffle chain.
+// smem per warp: w[64]
+// ------------------------------------------------------------------------------------------------
+__device__ void w64_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+                        double* __restrict__ x, double* __restrict__ cbv) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const long long ro = S.rows_ptr[s];
+  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  double* w = sm;  // 64
+  const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
+  const int i0 = lane, i1 = lane + 32;
+  w[i0] = (i0 < k) ? x[c0 + i0] : 0.0;
+  w[i1] = (i1 < k) ? x[c0 + i1] : 0.0;
+  for (int q = ch0 + lane; q < ch1; q += 32) wait_eq(V.done_f + S.child_idx[q], epoch);
+  __syncwarp();
+  for (int q = ch0; q < ch1; ++q) {
+    const int c = S.child_idx[q];
+    const long long o = S.rows_ptr[c];
+    const int rc = (int)(S.rows_ptr[c + 1] - o);
+    for (int t = lane; t < rc; t += 32) w[S.rel[o + t]] += __ldcg(cbv + o + t);
+    __syncwarp();
+  }
+  double v0 = 0.0, v1 = 0.0;
+  if (i0 < f) v0 = (i0 < k) ? w[N.lperm[c0 + i0]] : w[i0];
+  if (i1 < f) v1 = (i1 < k) ? w[N.lperm[c0 + i1]] : w[i1];
+  const double* __restrict__ P = N.L + S.L_off[s];
+  for (int tb = 0; tb < k; tb += 8) {
+    double l0[8], l1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tb + q;
+      l0[q] = (t < k && i0 > t && i0 < f) ? P[i0 + (size_t)t * f] : 0.0;
+      l1[q] = (t < k && i1 > t && i1 < f) ? P[i1 + (size_t)t * f] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tb + q;
+      if (t < k) {
+        const double yt = (t < 32) ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
+        v0 = fma(-l0[q], yt, v0);
+        v1 = fma(-l1[q], yt, v1);
+      }
+    }
+  }
+  // D^-1: partner values through shared memory (w is free now)
+  __syncwarp();
+  w[i0] = v0; w[i1] = v1;
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    const double v = h ? v1 : v0;
+    if (i < k) {
+      const int ty = N.ptype[c0 + i];
+      double y;
+      if (ty == 1) y = v * N.dinv[c0 + i];
+      else if (ty == 2) y = v * N.dinv[c0 + i] + w[i + 1] * N.doff[c0 + i];
+      else y = w[i - 1] * N.doff[c0 + i - 1] + v * N.dinv[c0 + i];
+      x[c0 + i] = y;
+    } else if (i < f) cbv[ro + i - k] = v;
+  }
+  __syncwarp();
+  if (lane == 0) { st_release(V.done_f + s, epoch); }
+}
+
+__device__ void w64_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+                        double* __restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const long long ro = S.rows_ptr[s];
+  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  const int i0 = lane, i1 = lane + 32;
+  const double* __restrict__ P = N.L + S.L_off[s];
+  const int par = S.sn_parent[s];
+  if (par >= 0 && lane == 0) wait_eq(V.done_b + par, epoch);
+  __syncwarp();
+  double v0 = 0.0, v1 = 0.0;  // entries i0 / i1 of [D^-1 y ; x(rows)]
+  if (i0 < k) v0 = x[c0 + i0]; else if (i0 < f) v0 = __ldcg(x + S.rows[ro + i0 - k]);
+  if (i1 < k) v1 = x[c0 + i1]; else if (i1 < f) v1 = __ldcg(x + S.rows[ro + i1 - k]);
+  // columns from the last to the first: v_t -= sum_{i>t} L[i,t] v_i  (column read coalesced, warp-sum)
+  for (int tb = k - 1; tb >= 0; tb -= 8) {
+    double l0[8], l1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tb - q;
+      l0[q] = (t >= 0 && i0 > t && i0 < f) ? P[i0 + (size_t)t * f] : 0.0;
+      l1[q] = (t >= 0 && i1 > t && i1 < f) ? P[i1 + (size_t)t * f] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tb - q;
+      if (t >= 0) {
+        double part = fma(l0[q], v0, l1[q] * v1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (t < 32) { if (lane == t) v0 -= part; } else { if (lane == t - 32) v1 -= part; }
+      }
+    }
+  }
+  if (i0 < k) x[c0 + N.lperm[c0 + i0]] = v0;
+  if (i1 < k) x[c0 + N.lperm[c0 + i1]] = v1;
+  __syncwarp();
+  if (lane == 0) { st_release(V.done_b + s, epoch); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -199,7 +308,7 @@ __device__ void mid_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
   double* __restrict__ out = cbv + S.rows_ptr[s];
   for (int i = tid; i < r; i += nt) out[i] = v[k + i];
   __syncthreads();
-  if (tid == 0) { __threadfence(); st_release(V.done_f + s, epoch); }
+  if (tid == 0) { st_release(V.done_f + s, epoch); }
 }
 
 __device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
@@ -245,7 +354,7 @@ __device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
   const int* __restrict__ lp = N.lperm + c0;
   for (int t = tid; t < k; t += nt) x[c0 + lp[t]] = v[t];
   __syncthreads();
-  if (tid == 0) { __threadfence(); st_release(V.done_b + s, epoch); }
+  if (tid == 0) { st_release(V.done_b + s, epoch); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,7 +384,7 @@ __device__ void big_gather(const DevSym& S, const DevNum& N, const DevSolve& V, 
   const int* __restrict__ lp = N.lperm + c0;
   for (int i = tid; i < f; i += nt) w[i] = (i < k) ? tmp[lp[i]] : tmp[i];
   __syncthreads();
-  if (tid == 0) { __threadfence(); st_release(V.gflag + s, epoch); }
+  if (tid == 0) { st_release(V.gflag + s, epoch); }
 }
 
 // forward block row b of big front s: rows [64b, min(f, 64b+64))
@@ -295,14 +404,37 @@ __device__ void big_fwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
   const double* yb = V.bigy + V.bigv_off[s];
   double acc = 0.0;
   const int row = r0 + tx;
+  // everything that does not depend on the y blocks is fetched first: the diagonal block and (after the gather
+  // flag, which is long set by the time the left blocks arrive) this block's slice of the assembled rhs
+  const int ndiag = max(0, min(k - r0, DF_BLK));
+  if (ndiag > 0) {
+    for (int t = tid; t < nrow * ndiag; t += blockDim.x) {
+      int i = t % nrow, q = t / nrow;
+      Lsq[i + q * 65] = P[(r0 + i) + (size_t)(r0 + q) * f];
+    }
+  }
+  if (tid == 0) wait_eq(V.gflag + s, epoch);
+  __syncthreads();
+  double wmine = 0.0;
+  if (tid < nrow) wmine = __ldcg(V.bigv + V.bigv_off[s] + r0 + tid);
+  // software pipeline: the L tile of column block c+1 is in flight while block c is consumed
+  double ltn[16];
+  if (ncolblk_left > 0) {
+    const int nc0 = min(DF_BLK, k);
+    const double* base = P + row;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nrow && t < nc0) ? base[(size_t)t * f] : 0.0; }
+  }
   for (int c = 0; c < ncolblk_left; ++c) {
     const int t0 = c * DF_BLK, ncol = min(DF_BLK, k - t0);
-    // the L tile does not depend on y: fetch it BEFORE waiting for the producer of y_c
     double lt[16];
-    {
-      const double* base = P + row + (size_t)t0 * f;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; lt[q] = (tx < nrow && t < ncol) ? base[(size_t)t * f] : 0.0; }
+    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+    if (c + 1 < ncolblk_left) {
+      const int t0n = t0 + DF_BLK, ncn = min(DF_BLK, k - t0n);
+      const double* base = P + row + (size_t)t0n * f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nrow && t < ncn) ? base[(size_t)t * f] : 0.0; }
     }
     if (tid == 0) wait_eq(bf + c, epoch);
     __syncthreads();
@@ -313,20 +445,12 @@ __device__ void big_fwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
     __syncthreads();
   }
   part[ty * 64 + tx] = acc;
-  // v = w - acc ; then the diagonal part (columns [r0, min(k, r0+64)))
-  const int ndiag = max(0, min(k - r0, DF_BLK));
-  if (ndiag > 0) {
-    for (int t = tid; t < nrow * ndiag; t += blockDim.x) {
-      int i = t % nrow, q = t / nrow;
-      Lsq[i + q * 65] = P[(r0 + i) + (size_t)(r0 + q) * f];
-    }
-  }
-  if (tid == 0) wait_eq(V.gflag + s, epoch);
   __syncthreads();
-  if (tid < 64) ys[tid] = (tid < nrow) ? __ldcg(V.bigv + V.bigv_off[s] + r0 + tid) - (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]) : 0.0;
+  if (tid < 64) ys[tid] = (tid < nrow) ? wmine - (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]) : 0.0;
   __syncthreads();
   if (warp == 0) {
     double v0 = ys[lane], v1 = ys[lane + 32];
+#pragma unroll 8
     for (int t = 0; t < ndiag; ++t) {
       const double yt = (t < 32) ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
       if (lane > t) v0 = fma(-Lsq[lane + t * 65], yt, v0);
@@ -349,11 +473,10 @@ __device__ void big_fwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
   }
   __syncthreads();
   if (tid == 0) {
-    __threadfence();
     if (r0 < k) st_release((int*)bf + b, epoch);
     const int nblk = (f + DF_BLK - 1) / DF_BLK;
     const int old = atomicAdd(V.bcnt + s, 1);
-    if ((old + 1) % nblk == 0) { __threadfence(); st_release(V.done_f + s, epoch); }
+    if ((old + 1) % nblk == 0) { st_release(V.done_f + s, epoch); }
   }
 }
 
@@ -387,16 +510,32 @@ __device__ void big_bwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
   // rows below the block are processed in chunks of 64: first the contribution-block rows (ancestors'
   // final values), then this front's later pivot blocks from the last one down as they get published.
   const int nchunk_cb = (r + DF_BLK - 1) / DF_BLK;
-  for (int ch = 0; ch < nchunk_cb + (nkb - 1 - b); ++ch) {
-    int rbase, nr, c = -1;
-    if (ch < nchunk_cb) { rbase = k + ch * DF_BLK; nr = min(DF_BLK, f - rbase); }
+  const int nchunk = nchunk_cb + (nkb - 1 - b);
+  // chunk geometry: first the contribution-block rows, then the later pivot blocks from the last one down
+  auto chunk_geom = [&](int ch, int& rbase, int& nr, int& c) {
+    if (ch < nchunk_cb) { c = -1; rbase = k + ch * DF_BLK; nr = min(DF_BLK, f - rbase); }
     else { c = nkb - 1 - (ch - nchunk_cb); rbase = c * DF_BLK; nr = min(DF_BLK, k - rbase); }
-    // the L tile does not depend on x: fetch it BEFORE waiting for the producer of this row chunk
-    double lt[16];
-    {
-      const double* base = P + (rbase + tx) + (size_t)t0 * f;
+  };
+  double ltn[16];
+  if (nchunk > 0) {
+    int rbase, nr, c;
+    chunk_geom(0, rbase, nr, c);
+    const double* base = P + (rbase + tx) + (size_t)t0 * f;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; lt[q] = (tx < nr && t < ncol) ? base[(size_t)t * f] : 0.0; }
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncol) ? base[(size_t)t * f] : 0.0; }
+  }
+  for (int ch = 0; ch < nchunk; ++ch) {
+    int rbase, nr, c;
+    chunk_geom(ch, rbase, nr, c);
+    double lt[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+    if (ch + 1 < nchunk) {   // next tile in flight while this chunk is consumed (it does not depend on x)
+      int rb2, nr2, c2;
+      chunk_geom(ch + 1, rb2, nr2, c2);
+      const double* base = P + (rb2 + tx) + (size_t)t0 * f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
     }
     if (c < 0) {
       if (tid < nr) xs[tid] = __ldcg(x + S.rows[ro + (rbase - k) + tid]);
@@ -431,6 +570,7 @@ __device__ void big_bwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
   if (warp == 0) {
     double z0 = (lane < ncol) ? x[c0 + t0 + lane] - colacc[lane] : 0.0;
     double z1 = (lane + 32 < ncol) ? x[c0 + t0 + lane + 32] - colacc[lane + 32] : 0.0;
+#pragma unroll 8
     for (int q = ncol - 1; q >= 0; --q) {
       const double zq = (q < 32) ? __shfl_sync(0xffffffffu, z0, q) : __shfl_sync(0xffffffffu, z1, q - 32);
       if (lane < q) z0 = fma(-Lsq[q + lane * 65], zq, z0);
@@ -445,10 +585,9 @@ __device__ void big_bwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
   }
   __syncthreads();
   if (tid == 0) {
-    __threadfence();
     st_release((int*)bf + b, epoch);
     const int old = atomicAdd(V.bcnt_b + s, 1);
-    if ((old + 1) % nkb == 0) { __threadfence(); st_release(V.done_b + s, epoch); }
+    if ((old + 1) % nkb == 0) { st_release(V.done_b + s, epoch); }
   }
   (void)t1;
 }
@@ -469,12 +608,16 @@ __global__ void __launch_bounds__(DF_THREADS) k_solve_dataflow(DevSym S, DevNum 
     __syncthreads();
     if (tk >= (unsigned long long)ntasks) return;
     const SolveTask T = tasks[tk];
+    unsigned long long t_start = 0;
+    if (V.tlog && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
     if (T.type == ST_SMALL) {
       const int w = threadIdx.x >> 5;
       if (w < T.b) {
         const int s = V.bundle[T.a + w];
         double* wsm = sm + (size_t)w * DF_SMALL_SMEM;
-        if (FWD) small_fwd(S, N, V, s, epoch, wsm, x, cbv); else small_bwd(S, N, V, s, epoch, wsm, x);
+        const int fs = (S.sn_start[s + 1] - S.sn_start[s]) + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+        if (fs <= 32) { if (FWD) small_fwd(S, N, V, s, epoch, wsm, x, cbv); else small_bwd(S, N, V, s, epoch, wsm, x); }
+        else { if (FWD) w64_fwd(S, N, V, s, epoch, wsm, x, cbv); else w64_bwd(S, N, V, s, epoch, wsm, x); }
       }
     } else if (T.type == ST_MID) {
       if (FWD) mid_fwd(S, N, V, T.a, epoch, sm, x, cbv); else mid_bwd(S, N, V, T.a, epoch, sm, x);
@@ -484,6 +627,12 @@ __global__ void __launch_bounds__(DF_THREADS) k_solve_dataflow(DevSym S, DevNum 
       if (FWD) big_fwd_block(S, N, V, T.a, T.b, epoch, sm, x, cbv); else big_bwd_block(S, N, V, T.a, T.b, epoch, sm, x);
     }
     __syncthreads();
+    if (V.tlog && threadIdx.x == 0) {
+      unsigned long long t_end;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+      unsigned long long* rec = V.tlog + 2 * ((FWD ? 0 : (unsigned long long)V.ntasks_fwd) + tk);
+      rec[0] = t_start; rec[1] = t_end;
+    }
   }
 }
 
