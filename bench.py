@@ -169,7 +169,8 @@ def main():
     snaps, src = get_snapshots(rank)
     s0 = snaps[0]
     dim, nnz = s0["dim"], len(s0["irn"])
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(local_rank)     # a real stream (handle 0 would make the library create its own)
+    torch.cuda.set_stream(stream)              # torch copies / events below run on the stream the kernels are launched on
     solver = B200Ldlt(device=local_rank, stream=stream.cuda_stream)
     assert solver.InitializeStructure(dim, nnz, s0["irn"], s0["jcn"]) == 0
     # one-off symbolic phase on the first matrix (not part of a step)

@@ -116,6 +116,19 @@ int b200ldlt_analyse_now(b200ldlt_handle h, const double* vals);
  * (original, unscaled values), returns max-norms. Used by tests/bench for parity checks. */
 int b200ldlt_residual(b200ldlt_handle h, const double* x, const double* b, double* r_inf, double* x_inf, double* b_inf);
 
+/* ---- multi-GPU elimination-tree sharding (one process / handle per GPU) -----------------
+ * The exchange itself (contribution blocks of the cut -> rank 0, update vectors, top solution back) is done by the
+ * caller with NCCL send/recv on the device pointers below; ipopt_b200/sharded.py is the reference orchestration. */
+int b200ldlt_shard_setup(b200ldlt_handle h, int rank, int world);
+/* "owner" (per supernode: owning rank, -1 = top part on rank 0), "cut_roots", "top_fronts" */
+int64_t b200ldlt_shard_array(b200ldlt_handle h, const char* name, int64_t* out, int64_t cap);
+/* device arrays of the handle: "CB" (contribution blocks, offsets cb_off), "cbv" (update vectors, offsets rows_ptr),
+ * "x" (permuted solution vector), "counters" (8 ints), "vals" (triplet values) */
+void* b200ldlt_device_ptr(b200ldlt_handle h, const char* name);
+int b200ldlt_shard_factor(b200ldlt_handle h, int phase, int from_host);
+int b200ldlt_shard_factor_finish(b200ldlt_handle h, const int* counters_total, int check_inertia, int expected_neg, int* num_neg);
+int b200ldlt_shard_solve(b200ldlt_handle h, int phase, double* d_rhs);
+
 #ifdef __cplusplus
 }
 #endif

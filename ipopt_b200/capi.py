@@ -90,6 +90,8 @@ def load_library():
     L.b200ldlt_symbolic_free.restype = None
     L.b200ldlt_symbolic_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.c_longlong]
     L.b200ldlt_symbolic_get.restype = C.c_longlong
+    L.b200ldlt_symbolic_shard.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.c_longlong]
+    L.b200ldlt_symbolic_shard.restype = C.c_longlong
     _lib = L
     return L
 
@@ -131,6 +133,13 @@ class SymbolicAnalysis:
 
     def stats(self):
         return dict(zip(self.STATS, self.get("stats").tolist()))
+
+    def shard(self, world):
+        """(owner per supernode [-1 = top part, factorised by rank 0], number of subtrees below the cut)."""
+        nsn = len(self.get("sn_start")) - 1
+        out = np.zeros(max(nsn, 1), dtype=np.int64)
+        nsub = self._L.b200ldlt_symbolic_shard(self._h, int(world), out.ctypes.data_as(C.POINTER(C.c_longlong)), nsn)
+        return out[:nsn], int(nsub)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -94,6 +94,15 @@ struct Solver {
   int solve_epoch = 0, df_grid = 0;
   unsigned long long ticket_f = 0, ticket_b = 0;
   int num_sms = 148;
+  struct Shard {
+    bool active = false;
+    int rank = 0, world = 1, nsub = 0;
+    std::vector<int> owner, cut_roots, top_fronts;
+    std::vector<LevelPlan> plan[2];          // [0] my subtrees, [1] top part
+    DevBuf<int> d_fl[2], d_bundle[2], d_mark_cut, d_mark_top;
+    DevBuf<SolveTask> d_tf[2], d_tb[2];
+    DevSolve DV[2];
+  } shard;
   cudaGraph_t fgraph = nullptr;
   cudaGraphExec_t fgraph_exec = nullptr;
   double fgraph_u = -1.0;
@@ -120,6 +129,96 @@ struct Solver {
       return B200LDLT_FATAL_ERROR;                                                       \
     }                                                                                    \
   } while (0)
+
+// per level: big fronts first, then the shared-memory classes by descending front order; only fronts with take[s]
+static void build_level_plans(const Symbolic& S, int smax, const std::vector<char>& take, std::vector<int>& fl,
+                              std::vector<LevelPlan>& plan) {
+  fl.clear();
+  fl.reserve(S.nsn);
+  plan.assign(S.nlevels, LevelPlan());
+  for (int l = 0; l < S.nlevels; ++l) {
+    LevelPlan& P = plan[l];
+    P.all_off = (int)fl.size();
+    P.big_off = (int)fl.size();
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      int s = S.level_sn[q];
+      if (!take[s]) continue;
+      P.fmax = std::max(P.fmax, S.f(s));
+      if (S.f(s) > smax) {
+        fl.push_back(s);
+        P.big_cnt++;
+        P.big_kmax = std::max(P.big_kmax, S.k(s));
+        P.big_fmax = std::max(P.big_fmax, S.f(s));
+        P.big_rmax = std::max(P.big_rmax, S.r(s));
+        P.big_chmax = std::max(P.big_chmax, S.child_ptr[s + 1] - S.child_ptr[s]);
+        P.big_entmax = std::max<long long>(P.big_entmax, S.uent_ptr[s + 1] - S.uent_ptr[s]);
+        P.big_zero_max = std::max<long long>(P.big_zero_max, (long long)S.f(s) * S.k(s) + (long long)S.r(s) * S.r(s));
+      }
+    }
+    // small fronts (level_sn is sorted by f descending inside a level)
+    const int lim[3] = {64, 32, 0};
+    const int thr[3] = {256, 128, 64};
+    int b = 0;
+    LevelPlan::Bucket cur{(int)fl.size(), 0, 0, 0, thr[0], 0};
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      int s = S.level_sn[q];
+      int f = S.f(s);
+      if (!take[s] || f > smax) continue;
+      while (b < 2 && f <= lim[b]) {
+        if (cur.cnt) P.small.push_back(cur);
+        ++b;
+        cur = LevelPlan::Bucket{(int)fl.size(), 0, 0, 0, thr[b], 0};
+      }
+      fl.push_back(s);
+      cur.cnt++;
+      cur.fmax = std::max(cur.fmax, f);
+      cur.kmax = std::max(cur.kmax, S.k(s));
+    }
+    if (cur.cnt) P.small.push_back(cur);
+    for (auto& bk : P.small) {
+      size_t ld = (size_t)(bk.fmax | 1);
+      bk.smem = (ld * bk.fmax + 2 * (size_t)bk.fmax) * sizeof(double) + (2 * (size_t)bk.kmax + 8) * sizeof(int);
+    }
+    P.all_cnt = (int)fl.size() - P.all_off;
+  }
+}
+
+// topologically sorted solve task lists (forward: levels ascending, backward: descending) for the fronts in take[]
+static void build_solve_tasks(const Symbolic& S, const std::vector<char>& take, std::vector<SolveTask>& tf,
+                              std::vector<SolveTask>& tb, std::vector<int>& bundle) {
+  const int MIDMAX = 256;
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<SolveTask>& T = pass == 0 ? tf : tb;
+    for (int li = 0; li < S.nlevels; ++li) {
+      const int l = pass == 0 ? li : S.nlevels - 1 - li;
+      std::vector<int> smalls;
+      // big first (longest), then mid, then small bundles
+      for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+        int s = S.level_sn[q];
+        if (!take[s] || S.f(s) <= MIDMAX) continue;
+        if (pass == 0) {
+          T.push_back({ST_BIG_GATHER, s, 0, 0});
+          int nb = (S.f(s) + DF_BLK - 1) / DF_BLK;
+          for (int b = 0; b < nb; ++b) T.push_back({ST_BIG_BLOCK, s, b, 0});
+        } else {
+          int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK;
+          for (int b = nkb - 1; b >= 0; --b) T.push_back({ST_BIG_BLOCK, s, b, 0});
+        }
+      }
+      for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+        int s = S.level_sn[q];
+        if (!take[s] || S.f(s) > MIDMAX) continue;
+        if (S.f(s) > 64) T.push_back({ST_MID, s, 0, 0});
+        else smalls.push_back(s);   // warp-per-front classes (<= 32 staged in smem, 33..64 streamed)
+      }
+      for (size_t q = 0; q < smalls.size(); q += 8) {
+        int cnt = (int)std::min<size_t>(8, smalls.size() - q);
+        T.push_back({ST_SMALL, (int)bundle.size(), cnt, 0});
+        for (int w = 0; w < cnt; ++w) bundle.push_back(smalls[q + w]);
+      }
+    }
+  }
+}
 
 static int run_analysis(Solver* sv, const double* vals) {
   if (sv->fgraph_exec) { cudaGraphExecDestroy(sv->fgraph_exec); sv->fgraph_exec = nullptr; }
@@ -182,54 +281,10 @@ static int run_analysis(Solver* sv, const double* vals) {
   N.lperm = sv->d_lperm.p; N.bperm = sv->d_bperm.p; N.counters = sv->d_counters.p; N.colmax = sv->d_colmax.p;
 
   // ---- launch plan: per level, big fronts first then small ones by descending order --------
-  const int smax = sv->opt.smem_front_max;
   std::vector<int> fl;
-  fl.reserve(S.nsn);
-  sv->plan.assign(S.nlevels, LevelPlan());
-  for (int l = 0; l < S.nlevels; ++l) {
-    LevelPlan& P = sv->plan[l];
-    P.all_off = (int)fl.size();
-    P.big_off = (int)fl.size();
-    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
-      int s = S.level_sn[q];
-      P.fmax = std::max(P.fmax, S.f(s));
-      if (S.f(s) > smax) {
-        fl.push_back(s);
-        P.big_cnt++;
-        P.big_kmax = std::max(P.big_kmax, S.k(s));
-        P.big_fmax = std::max(P.big_fmax, S.f(s));
-        P.big_rmax = std::max(P.big_rmax, S.r(s));
-        P.big_chmax = std::max(P.big_chmax, S.child_ptr[s + 1] - S.child_ptr[s]);
-        P.big_entmax = std::max<long long>(P.big_entmax, S.uent_ptr[s + 1] - S.uent_ptr[s]);
-        P.big_zero_max = std::max<long long>(P.big_zero_max, (long long)S.f(s) * S.k(s) + (long long)S.r(s) * S.r(s));
-      }
-    }
-    // small fronts (level_sn is sorted by f descending inside a level)
-    const int lim[3] = {64, 32, 0};
-    const int thr[3] = {256, 128, 64};
-    int b = 0;
-    LevelPlan::Bucket cur{(int)fl.size(), 0, 0, 0, thr[0], 0};
-    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
-      int s = S.level_sn[q];
-      int f = S.f(s);
-      if (f > smax) continue;
-      while (b < 2 && f <= lim[b]) {
-        if (cur.cnt) P.small.push_back(cur);
-        ++b;
-        cur = LevelPlan::Bucket{(int)fl.size(), 0, 0, 0, thr[b], 0};
-      }
-      fl.push_back(s);
-      cur.cnt++;
-      cur.fmax = std::max(cur.fmax, f);
-      cur.kmax = std::max(cur.kmax, S.k(s));
-    }
-    if (cur.cnt) P.small.push_back(cur);
-    for (auto& bk : P.small) {
-      size_t ld = (size_t)(bk.fmax | 1);
-      bk.smem = (ld * bk.fmax + 2 * (size_t)bk.fmax) * sizeof(double) + (2 * (size_t)bk.kmax + 8) * sizeof(int);
-      // k can exceed kmax of another front with smaller f only inside the bucket; kmax covers the bucket
-    }
-    P.all_cnt = (int)fl.size() - P.all_off;
+  {
+    std::vector<char> take(S.nsn, 1);
+    build_level_plans(S, sv->opt.smem_front_max, take, fl, sv->plan);
   }
   CU(sv->d_front_list.upload(fl, st));
   CU(cudaFuncSetAttribute(k_front_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -244,42 +299,16 @@ static int run_analysis(Solver* sv, const double* vals) {
     const int MIDMAX = 256;
     std::vector<SolveTask> tf, tb;
     std::vector<int> bundle, boff(S.nsn, 0);
+    sv->shard.active = false;
     std::vector<long long> bigv_off(S.nsn, 0);
     long long bv = 0; int bo = 0;
     for (int s = 0; s < S.nsn; ++s) if (S.f(s) > MIDMAX) {
       boff[s] = bo; bo += (S.f(s) + DF_BLK - 1) / DF_BLK;
       bigv_off[s] = bv; bv += S.f(s) + (S.f(s) & 1);
     }
-    for (int pass = 0; pass < 2; ++pass) {
-      std::vector<SolveTask>& T = pass == 0 ? tf : tb;
-      for (int li = 0; li < S.nlevels; ++li) {
-        const int l = pass == 0 ? li : S.nlevels - 1 - li;
-        std::vector<int> smalls;
-        // big first (longest), then mid, then small bundles
-        for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
-          int s = S.level_sn[q];
-          if (S.f(s) <= MIDMAX) continue;
-          if (pass == 0) {
-            T.push_back({ST_BIG_GATHER, s, 0, 0});
-            int nb = (S.f(s) + DF_BLK - 1) / DF_BLK;
-            for (int b = 0; b < nb; ++b) T.push_back({ST_BIG_BLOCK, s, b, 0});
-          } else {
-            int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK;
-            for (int b = nkb - 1; b >= 0; --b) T.push_back({ST_BIG_BLOCK, s, b, 0});
-          }
-        }
-        for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
-          int s = S.level_sn[q];
-          if (S.f(s) > MIDMAX) continue;
-          if (S.f(s) > 64) T.push_back({ST_MID, s, 0, 0});
-          else smalls.push_back(s);   // warp-per-front classes (<= 32 staged in smem, 33..64 streamed)
-        }
-        for (size_t q = 0; q < smalls.size(); q += 8) {
-          int cnt = (int)std::min<size_t>(8, smalls.size() - q);
-          T.push_back({ST_SMALL, (int)bundle.size(), cnt, 0});
-          for (int w = 0; w < cnt; ++w) bundle.push_back(smalls[q + w]);
-        }
-      }
+    {
+      std::vector<char> take(S.nsn, 1);
+      build_solve_tasks(S, take, tf, tb, bundle);
     }
     CU(sv->d_tasks_f.upload(tf, st));
     CU(sv->d_tasks_b.upload(tb, st));
@@ -348,7 +377,8 @@ static int run_analysis(Solver* sv, const double* vals) {
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 // enqueue the whole numeric factorisation of the values in d_vals
-static int enqueue_factor(Solver* sv) {
+static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nullptr, const int* fl_p = nullptr,
+                          bool prologue = true) {
   Symbolic& S = sv->S;
   cudaStream_t st = sv->stream;
   DevSym& D = sv->DS;
@@ -357,8 +387,10 @@ static int enqueue_factor(Solver* sv) {
   N.tiny = sv->opt.tiny;
   const int n = S.n;
   const long long nu = S.nnz_u;
-  const int* fl = sv->d_front_list.p;
+  const int* fl = fl_p ? fl_p : sv->d_front_list.p;
+  const std::vector<LevelPlan>& plan = plan_p ? *plan_p : sv->plan;
   int& L = sv->launches;
+  if (prologue) {
   L = 0;
   CU(cudaMemsetAsync(sv->d_counters.p, 0, CNT_N * sizeof(int), st));
   CU(cudaMemsetAsync(sv->d_colmax.p, 0, (size_t)n * sizeof(double), st));
@@ -371,8 +403,9 @@ static int enqueue_factor(Solver* sv) {
   if (sv->opt.scaling > 0) {
     k_apply_scale<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_u_row.p, sv->d_u_col.p, sv->d_scale.p, sv->d_uval.p); ++L;
   }
+  }  // prologue
   for (int l = 0; l < S.nlevels; ++l) {
-    const LevelPlan& P = sv->plan[l];
+    const LevelPlan& P = plan[l];
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
       k_big_zero<<<dim3(std::min<unsigned>(cdiv(P.big_zero_max, 1024), 592), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
@@ -517,6 +550,87 @@ static int enqueue_solve(Solver* sv, const double* d_b, double* d_out) {
   }
   k_sol_out<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, sv->d_x.p, d_out); ++L;
   CU(cudaGetLastError());
+  return B200LDLT_SUCCESS;
+}
+
+
+__global__ void k_mark_flags(int* flags, const int* __restrict__ list, int n, int value) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[list[i]] = value;
+}
+
+static int launch_dataflow(Solver* sv, const DevSolve& V, bool fwd) {
+  cudaStream_t st = sv->stream;
+  const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
+  const int nt = fwd ? V.ntasks_fwd : V.ntasks_bwd;
+  if (nt <= 0) return B200LDLT_SUCCESS;
+  const int grid = std::min(sv->df_grid, nt);
+  if (fwd) {
+    k_solve_dataflow<true><<<grid, DF_THREADS, df_smem, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p);
+    sv->ticket_f += (unsigned long long)nt + grid;
+  } else {
+    k_solve_dataflow<false><<<grid, DF_THREADS, df_smem, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p);
+    sv->ticket_b += (unsigned long long)nt + grid;
+  }
+  ++sv->launches;
+  CU(cudaGetLastError());
+  return B200LDLT_SUCCESS;
+}
+
+static int shard_setup(Solver* sv, int rank, int world) {
+  Symbolic& S = sv->S;
+  cudaStream_t st = sv->stream;
+  Solver::Shard& H = sv->shard;
+  H.rank = rank; H.world = world;
+  H.nsub = shard_plan(S, world, H.owner);
+  H.cut_roots.clear(); H.top_fronts.clear();
+  std::vector<char> take[2];
+  take[0].assign(S.nsn, 0); take[1].assign(S.nsn, 0);
+  std::vector<int> mark_cut;
+  for (int s = 0; s < S.nsn; ++s) {
+    if (H.owner[s] < 0) { take[1][s] = (rank == 0); H.top_fronts.push_back(s); }
+    else {
+      take[0][s] = (H.owner[s] == rank);
+      const int p = S.sn_parent[s];
+      if (p >= 0 && H.owner[p] < 0) { H.cut_roots.push_back(s); if (H.owner[s] != 0) mark_cut.push_back(s); }
+    }
+  }
+  for (int ph = 0; ph < 2; ++ph) {
+    std::vector<int> fl, bundle;
+    std::vector<SolveTask> tf, tb;
+    build_level_plans(S, sv->opt.smem_front_max, take[ph], fl, H.plan[ph]);
+    build_solve_tasks(S, take[ph], tf, tb, bundle);
+    if (fl.empty()) fl.push_back(0);
+    if (bundle.empty()) bundle.push_back(0);
+    if (tf.empty()) tf.push_back({ST_SMALL, 0, 0, 0});
+    const int ntf = (int)tf.size() - ((tf.size() == 1 && tf[0].b == 0 && tf[0].type == ST_SMALL) ? 1 : 0);
+    if (tb.empty()) tb.push_back({ST_SMALL, 0, 0, 0});
+    const int ntb = (int)tb.size() - ((tb.size() == 1 && tb[0].b == 0 && tb[0].type == ST_SMALL) ? 1 : 0);
+    CU(H.d_fl[ph].upload(fl, st));
+    CU(H.d_bundle[ph].upload(bundle, st));
+    CU(H.d_tf[ph].upload(tf, st));
+    CU(H.d_tb[ph].upload(tb, st));
+    H.DV[ph] = sv->DV;
+    H.DV[ph].tasks = H.d_tf[ph].p; H.DV[ph].tasks_bwd = H.d_tb[ph].p;
+    H.DV[ph].ntasks_fwd = ntf; H.DV[ph].ntasks_bwd = ntb;
+    H.DV[ph].bundle = H.d_bundle[ph].p;
+    H.DV[ph].tlog = nullptr;
+  }
+  if (mark_cut.empty()) mark_cut.push_back(0), H.d_mark_cut.n = 0;
+  {
+    std::vector<int> mc;
+    for (int s : H.cut_roots) if (H.owner[s] != 0) mc.push_back(s);
+    size_t cnt = mc.size();
+    if (mc.empty()) mc.push_back(0);
+    CU(H.d_mark_cut.upload(mc, st));
+    H.d_mark_cut.n = cnt;
+    std::vector<int> mt = H.top_fronts;
+    cnt = mt.size();
+    if (mt.empty()) mt.push_back(0);
+    CU(H.d_mark_top.upload(mt, st));
+    H.d_mark_top.n = cnt;
+  }
+  H.active = true;
   return B200LDLT_SUCCESS;
 }
 
@@ -695,6 +809,108 @@ int b200ldlt_dump_solve_timeline(b200ldlt_handle h, const char* path) {
   }
   fclose(fp);
   return B200LDLT_SUCCESS;
+}
+
+/* ---- multi-GPU elimination-tree sharding -------------------------------------------
+ * One process per GPU, each with its own handle and the SAME matrix.  After the (replicated, deterministic)
+ * analysis, rank g factorises the subtrees it owns; the contribution blocks of the cut are moved to rank 0 by the
+ * caller (NCCL send/recv through torch.distributed on the device pointers exported below), which then factorises
+ * the top part.  The solve mirrors it.  See ipopt_b200/sharded.py for the orchestration. */
+int b200ldlt_shard_setup(b200ldlt_handle h, int rank, int world) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->analysed || world < 1 || rank < 0 || rank >= world) { if (sv) sv->err = "shard_setup: analyse first / bad rank"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  return shard_setup(sv, rank, world);
+}
+
+int64_t b200ldlt_shard_array(b200ldlt_handle h, const char* name, int64_t* out, int64_t cap) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->shard.active || !name) return -1;
+  const Solver::Shard& H = sv->shard;
+  std::string nm(name);
+  const std::vector<int>* v = nullptr;
+  if (nm == "owner") v = &H.owner;
+  else if (nm == "cut_roots") v = &H.cut_roots;
+  else if (nm == "top_fronts") v = &H.top_fronts;
+  if (!v) return -1;
+  if (out) for (int64_t i = 0; i < (int64_t)v->size() && i < cap; ++i) out[i] = (*v)[i];
+  return (int64_t)v->size();
+}
+
+void* b200ldlt_device_ptr(b200ldlt_handle h, const char* name) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->analysed || !name) return nullptr;
+  std::string nm(name);
+  if (nm == "CB") return sv->d_CB.p;
+  if (nm == "cbv") return sv->d_cbv.p;
+  if (nm == "x") return sv->d_x.p;
+  if (nm == "counters") return sv->d_counters.p;
+  if (nm == "vals") return sv->d_vals.p;
+  return nullptr;
+}
+
+/* phase 0: (optional H2D of the pinned values array,) scaling + the subtrees owned by this rank;
+ * phase 1: the top part (only rank 0 has work).  Enqueues on the handle's stream and returns. */
+int b200ldlt_shard_factor(b200ldlt_handle h, int phase, int from_host) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->shard.active || phase < 0 || phase > 1) { if (sv) sv->err = "shard_factor: shard_setup first"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  cudaStream_t st = sv->stream;
+  if (phase == 0) {
+    CU(cudaEventRecord(sv->ev0, st));
+    if (from_host) CU(cudaMemcpyAsync(sv->d_vals.p, sv->h_vals, sv->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+    sv->have_dev_vals = true;
+  }
+  return enqueue_factor(sv, &sv->shard.plan[phase], sv->shard.d_fl[phase].p, phase == 0);
+}
+
+/* counters_total: CNT_N ints already summed over the ranks (all-reduce of device_ptr("counters")) */
+int b200ldlt_shard_factor_finish(b200ldlt_handle h, const int* counters_total, int check_inertia, int expected_neg, int* num_neg) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->shard.active || !counters_total) return B200LDLT_FATAL_ERROR;
+  CU(cudaSetDevice(sv->dev));
+  CU(cudaEventRecord(sv->ev1, sv->stream));
+  CU(cudaStreamSynchronize(sv->stream));
+  cudaEventElapsedTime(&sv->info.ms_factor_gpu, sv->ev0, sv->ev1);
+  b200ldlt_info& I = sv->info;
+  I.launches_factor = sv->launches;
+  I.num_neg = counters_total[CNT_NEG]; I.num_forced = counters_total[CNT_FORCED]; I.num_tiny = counters_total[CNT_TINY];
+  I.num_growth = counters_total[CNT_GROWTH]; I.num_2x2 = counters_total[CNT_2X2];
+  sv->num_neg = I.num_neg;
+  if (num_neg) *num_neg = I.num_neg;
+  sv->factored = true;
+  if (I.num_tiny > 0) return B200LDLT_SINGULAR;
+  if (check_inertia && I.num_neg != expected_neg) return B200LDLT_WRONG_INERTIA;
+  return B200LDLT_SUCCESS;
+}
+
+/* phase 0: permute+scale rhs, forward sweep over my subtrees;  phase 1 (rank 0): forward + backward over the top;
+ * phase 2: backward sweep over my subtrees;  phase 3: un-permute/un-scale into d_rhs.  d_rhs: dim doubles on the device. */
+int b200ldlt_shard_solve(b200ldlt_handle h, int phase, double* d_rhs) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->shard.active || !sv->factored) { if (sv) sv->err = "shard_solve: factor first"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  cudaStream_t st = sv->stream;
+  Solver::Shard& H = sv->shard;
+  const int n = sv->n;
+  int rc = B200LDLT_SUCCESS;
+  if (phase == 0) {
+    sv->launches = 0;
+    k_rhs_in<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, d_rhs, sv->d_x.p);
+    sv->solve_epoch++;
+    rc = launch_dataflow(sv, H.DV[0], true);
+  } else if (phase == 1) {
+    if (H.d_mark_cut.n) k_mark_flags<<<cdiv((long long)H.d_mark_cut.n, 256), 256, 0, st>>>(sv->d_done_f.p, H.d_mark_cut.p, (int)H.d_mark_cut.n, sv->solve_epoch);
+    rc = launch_dataflow(sv, H.DV[1], true);
+    if (rc == B200LDLT_SUCCESS) rc = launch_dataflow(sv, H.DV[1], false);
+  } else if (phase == 2) {
+    if (H.rank != 0 && H.d_mark_top.n) k_mark_flags<<<cdiv((long long)H.d_mark_top.n, 256), 256, 0, st>>>(sv->d_done_b.p, H.d_mark_top.p, (int)H.d_mark_top.n, sv->solve_epoch);
+    rc = launch_dataflow(sv, H.DV[0], false);
+  } else if (phase == 3) {
+    k_sol_out<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, sv->d_x.p, d_rhs);
+  } else return B200LDLT_FATAL_ERROR;
+  CU(cudaGetLastError());
+  return rc;
 }
 
 int b200ldlt_num_neg(b200ldlt_handle h) { return h ? ((Solver*)h)->num_neg : -1; }

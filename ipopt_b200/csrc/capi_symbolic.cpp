@@ -64,4 +64,14 @@ long long b200ldlt_symbolic_get(void* p, const char* name, long long* out, long 
   return -1;
 }
 
+
+/* owner[s] for every supernode (rank of its subtree, -1 = top part); returns the number of subtrees below the cut */
+long long b200ldlt_symbolic_shard(void* p, int world, long long* out, long long cap) {
+  if (!p) return -1;
+  std::vector<int> owner;
+  int nsub = shard_plan(((SymHandle*)p)->S, world, owner);
+  if (out) for (long long i = 0; i < (long long)owner.size() && i < cap; ++i) out[i] = owner[i];
+  return nsub;
+}
+
 }  // extern "C"

@@ -539,4 +539,55 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
   return 0;
 }
 
+
+int shard_plan(const Symbolic& S, int world, std::vector<int>& owner) {
+  const int nsn = S.nsn;
+  owner.assign(nsn, 0);
+  if (world <= 1 || nsn == 0) return 1;
+  std::vector<double> w(nsn), sub(nsn);
+  for (int s = 0; s < nsn; ++s) {
+    const double k = S.k(s), r = S.r(s);
+    w[s] = k * k * k / 3.0 + k * k * r + k * r * (r + 1.0) + 50.0 * (k + r);  // + a latency term per front
+    sub[s] = w[s];
+  }
+  for (int s = 0; s < nsn; ++s) if (S.sn_parent[s] >= 0) sub[S.sn_parent[s]] += sub[s];  // children precede parents
+  std::vector<char> top(nsn, 0);
+  std::vector<int> frontier;
+  for (int s = 0; s < nsn; ++s) if (S.sn_parent[s] < 0) frontier.push_back(s);
+  double below = 0;
+  for (int s : frontier) below += sub[s];
+  // expand the heaviest subtree until the cut exposes enough balanced subtrees
+  for (int iter = 0; iter < nsn; ++iter) {
+    int bi = -1;
+    for (int q = 0; q < (int)frontier.size(); ++q)
+      if (S.child_ptr[frontier[q] + 1] > S.child_ptr[frontier[q]] && (bi < 0 || sub[frontier[q]] > sub[frontier[bi]])) bi = q;
+    if (bi < 0) break;
+    const bool enough = (int)frontier.size() >= 4 * world && sub[frontier[bi]] <= below / (2.0 * world);
+    if (enough) break;
+    const int s = frontier[bi];
+    top[s] = 1;
+    below -= w[s];
+    frontier[bi] = frontier.back();
+    frontier.pop_back();
+    for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) frontier.push_back(S.child_idx[q]);
+  }
+  // LPT assignment of the subtrees
+  std::sort(frontier.begin(), frontier.end(), [&](int a, int b) { return sub[a] != sub[b] ? sub[a] > sub[b] : a < b; });
+  std::vector<double> load(world, 0.0);
+  std::vector<int> root_owner(nsn, -1);
+  for (int s : frontier) {
+    int g = 0;
+    for (int q = 1; q < world; ++q) if (load[q] < load[g]) g = q;
+    load[g] += sub[s];
+    root_owner[s] = g;
+  }
+  // propagate down (parents have larger indices than children)
+  for (int s = nsn - 1; s >= 0; --s) {
+    if (top[s]) owner[s] = -1;
+    else if (root_owner[s] >= 0) owner[s] = root_owner[s];
+    else owner[s] = owner[S.sn_parent[s]];
+  }
+  return (int)frontier.size();
+}
+
 }  // namespace b200

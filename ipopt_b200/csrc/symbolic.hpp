@@ -80,4 +80,11 @@ struct Symbolic {
 int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* vals,
             const AnalyseOptions& opt, Symbolic& S, std::string& err);
 
+
+// Elimination-tree sharding for multi-GPU runs: cut the supernodal tree into a TOP part
+// (owner -1, factorised by rank 0 after the contribution blocks of the cut arrive) and disjoint subtrees that
+// are assigned to `world` ranks by decreasing work (LPT).  owner[s] = rank of the subtree containing s, or -1.
+// Returns the number of independent subtrees below the cut.
+int shard_plan(const Symbolic& S, int world, std::vector<int>& owner);
+
 }  // namespace b200
