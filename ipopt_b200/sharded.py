@@ -78,6 +78,7 @@ class _Rank:
         self.cbv = self._view("cbv", max(int(self.rows_ptr[-1]), 1), "<f8", dev)
         self.x = self._view("x", dim, "<f8", dev)
         self.counters = self._view("counters", 8, "<i4", dev)
+        self.vals_dev = self._view("vals", len(irn), "<f8", dev)
         top_cols = [np.arange(self.sn_start[s], self.sn_start[s + 1]) for s in self.top_fronts]
         self.idx_top = torch.from_numpy(np.concatenate(top_cols) if top_cols else np.zeros(0, np.int64)).to(dev)
         self.rhs = torch.empty(dim, dtype=torch.float64, device=dev)
@@ -161,10 +162,24 @@ class ShardedLdlt:
         with self.torch.cuda.stream(self.stream):
             return self._solve(rhs)
 
-    def _factor(self, vals, check, expected):
+    def factor_device(self, d_vals, check=False, expected=0):
+        """Same as factor() with the triplet values already on this rank's GPU (torch float64 tensor)."""
+        with self.torch.cuda.stream(self.stream):
+            return self._factor(d_vals, check, expected, device=True)
+
+    def solve_device(self, d_rhs):
+        """rhs/solution as a device tensor (dim); the solution is valid on rank 0."""
+        with self.torch.cuda.stream(self.stream):
+            return self._solve(d_rhs, device=True)
+
+    def _factor(self, vals, check, expected, device=False):
         for R in self.ranks.values():
-            R.s.GetValuesArrayPtr()[:] = vals
-            R.factor_phase(0, True)
+            if device:
+                R.vals_dev.copy_(vals)
+                R.factor_phase(0, False)
+            else:
+                R.s.GetValuesArrayPtr()[:] = vals
+                R.factor_phase(0, True)
         any_r = self.ranks[self.my[0]]
         self._cut_to_root("CB", any_r.cb_off)
         if 0 in self.ranks:
@@ -183,10 +198,10 @@ class ShardedLdlt:
             self._neg = neg.value
         return st, self._neg
 
-    def _solve(self, rhs):
+    def _solve(self, rhs, device=False):
         torch = self.torch
         for R in self.ranks.values():
-            R.rhs.copy_(torch.from_numpy(np.ascontiguousarray(rhs)))
+            R.rhs.copy_(rhs if device else torch.from_numpy(np.ascontiguousarray(rhs)))
             R.solve_phase(0)
         any_r = self.ranks[self.my[0]]
         self._cut_to_root("cbv", any_r.rows_ptr)
@@ -216,6 +231,8 @@ class ShardedLdlt:
         out = None
         if 0 in self.ranks:
             self.ranks[0].solve_phase(3)
+            if device:
+                return self.ranks[0].rhs
             self.stream.synchronize()
             out = self.ranks[0].rhs.cpu().numpy()
         return out
