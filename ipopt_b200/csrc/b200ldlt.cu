@@ -56,6 +56,9 @@ struct Solver {
   std::string err;
   int dev = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // bulk (trsm / trailing update) stream of the big-front pipeline
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -116,7 +119,13 @@ struct Solver {
     if (ev1) cudaEventDestroy(ev1);
     if (fgraph_exec) cudaGraphExecDestroy(fgraph_exec);
     if (fgraph) cudaGraphDestroy(fgraph);
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    if (stream2) cudaStreamDestroy(stream2);
     if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+  cudaEvent_t next_event() {
+    if (ev_next == ev_pool.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ev_pool.push_back(e); }
+    return ev_pool[ev_next++];
   }
 };
 
@@ -392,6 +401,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
   int& L = sv->launches;
   if (prologue) {
   L = 0;
+  sv->ev_next = 0;
   CU(cudaMemsetAsync(sv->d_counters.p, 0, CNT_N * sizeof(int), st));
   CU(cudaMemsetAsync(sv->d_colmax.p, 0, (size_t)n * sizeof(double), st));
   k_sum_dups<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_useg_ptr.p, sv->d_useg_src.p, sv->d_vals.p, sv->d_uval.p); ++L;
@@ -424,15 +434,35 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
       k_big_colmax0<<<P.big_cnt, 256, 0, st>>>(D, N, bl); ++L;
+      // Panel pipeline on two streams (both inside the captured graph): the CHAIN  diag(p) -> trsm(p) -> diag(p+1)
+      // is the critical path; the trailing update of panel p runs on the bulk stream concurrently with diag(p+1),
+      // which applies panel p's rank-32 update to its own 32x32 block itself.
+      cudaStream_t sb = getenv("B200_ONE_STREAM") ? st : sv->stream2;
+      {
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, st));
+        CU(cudaStreamWaitEvent(sb, e, 0));
+      }
       for (int jb = 0; jb < P.big_kmax; jb += NB) {
         k_big_diag<<<P.big_cnt, 32, 0, st>>>(D, N, bl, jb); ++L;
+        cudaEvent_t ec = sv->next_event();
+        CU(cudaEventRecord(ec, st));
+        CU(cudaStreamWaitEvent(sb, ec, 0));
         int rows_below = P.big_fmax - jb;  // upper bound
         int nrowblk = std::max(1u, cdiv(rows_below, 128));
-        k_big_trsm<<<dim3(nrowblk + cdiv(jb, 128), P.big_cnt), 128, 0, st>>>(D, N, bl, jb, nrowblk); ++L;
+        k_big_trsm<<<dim3(nrowblk + cdiv(jb, 128), P.big_cnt), 128, 0, sb>>>(D, N, bl, jb, nrowblk); ++L;
+        cudaEvent_t et = sv->next_event();
+        CU(cudaEventRecord(et, sb));
+        CU(cudaStreamWaitEvent(st, et, 0));      // diag(p+1) needs L/W of its own rows from trsm(p)
         int rem_k = P.big_kmax - jb - NB;
         if (rem_k > 0) {
-          k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, st>>>(D, N, bl, jb); ++L;
+          k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, sb>>>(D, N, bl, jb); ++L;
         }
+      }
+      {
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, sb));
+        CU(cudaStreamWaitEvent(st, e, 0));
       }
       if (P.big_rmax > 0) {
         k_big_schur<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
@@ -680,6 +710,7 @@ b200ldlt_handle b200ldlt_create(const b200ldlt_options* opt) {
   }
   if (sv->opt.stream) sv->stream = (cudaStream_t)sv->opt.stream;
   else { cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking); sv->own_stream = true; }
+  cudaStreamCreateWithFlags(&sv->stream2, cudaStreamNonBlocking);
   cudaEventCreate(&sv->ev0);
   cudaEventCreate(&sv->ev1);
   cudaHostAlloc((void**)&sv->h_counters, CNT_N * sizeof(int), cudaHostAllocDefault);

@@ -696,12 +696,13 @@ __global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_
   const int s = front_list[blockIdx.x];
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-  const int nb = min(NB, k);
+  const int nb = min(2 * NB, k);   // panels 0 and 1 (panel 1's values lack panel 0's update: a one-panel-stale estimate)
   const double* __restrict__ P = N.L + S.L_off[s];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int j = warp; j < nb; j += nwarp) {
+    const int below = (j / NB + 1) * NB;
     double m = 0.0;
-    for (int i = nb + lane; i < f; i += 32) m = fmax(m, fabs(P[i + (size_t)j * f]));
+    for (int i = below + lane; i < f; i += 32) m = fmax(m, fabs(P[i + (size_t)j * f]));
     m = warp_max(m);
     if (lane == 0) N.colmax[c0 + j] = m;
   }
@@ -730,6 +731,27 @@ __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* 
     for (int j = 0; j < NB; ++j) T[lane * 33 + j] = tmp[j];
   }
   __syncwarp();
+  if (jb > 0) {
+    // previous panel (columns jb-32..jb): T[i][j] -= sum_t L[i,t] * W[j,t] for the rows/cols of this block
+    // (the bulk trailing update skips this 32x32 block, see tile_syrk)
+    __shared__ double Wb[33 * NB];
+    const double* __restrict__ Wp = N.W + S.L_off[s];
+    double lrow[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+      const size_t off = (size_t)(jb + lane) + (size_t)(jb - NB + t) * f;
+      lrow[t] = (lane < nb) ? P[off] : 0.0;
+      Wb[lane * 33 + t] = (lane < nb) ? Wp[off] : 0.0;
+    }
+    __syncwarp();
+    for (int j = 0; j < nb; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int t = 0; t < NB; ++t) acc = fma(lrow[t], Wb[j * 33 + t], acc);
+      if (lane >= j && lane < nb) T[lane * 33 + j] -= acc;
+    }
+    __syncwarp();
+  }
   double a[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? T[lane * 33 + c] : T[c * 33 + lane];
@@ -878,10 +900,15 @@ __device__ __forceinline__ void tile_syrk(double* __restrict__ C, long long ldc,
     for (int p = 0; p < 4; ++p) {
       int gi = i0 + tx + 16 * q, gj = j0 + ty + 16 * p;
       if (gi < M && gj < Nn && gi >= gj) {
+        // colmax_next != nullptr marks the panel update: the 32x32 block of the NEXT panel is left to the chain
+        // kernel (k_big_diag applies this panel's update to it itself, off the trailing update's critical path)
+        if (colmax_next && gi < min(NB, Nn) && gj < NB) continue;   // (a partial last panel has fewer than 32 columns)
         const double nv = C[gi + (long long)gj * ldc] - acc[q][p];
         C[gi + (long long)gj * ldc] = nv;
-        // the first 32 trailing columns are the NEXT panel: record their maxima below its diagonal block
-        if (colmax_next && gj < NB && gi >= NB)
+        // columns [32,64) of the trailing matrix are the panel AFTER next: record their maxima below its diagonal
+        // block (the next panel's chain kernel runs concurrently with this update, so it uses the values recorded
+        // one panel earlier)
+        if (colmax_next && gj >= NB && gj < 2 * NB && gi >= 2 * NB)
           atomicMax(reinterpret_cast<unsigned long long*>(colmax_next + gj), (unsigned long long)__double_as_longlong(fabs(nv)));
       }
     }
