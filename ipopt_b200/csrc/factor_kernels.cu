@@ -731,27 +731,6 @@ __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* 
     for (int j = 0; j < NB; ++j) T[lane * 33 + j] = tmp[j];
   }
   __syncwarp();
-  if (jb > 0) {
-    // previous panel (columns jb-32..jb): T[i][j] -= sum_t L[i,t] * W[j,t] for the rows/cols of this block
-    // (the bulk trailing update skips this 32x32 block, see tile_syrk)
-    __shared__ double Wb[33 * NB];
-    const double* __restrict__ Wp = N.W + S.L_off[s];
-    double lrow[NB];
-#pragma unroll
-    for (int t = 0; t < NB; ++t) {
-      const size_t off = (size_t)(jb + lane) + (size_t)(jb - NB + t) * f;
-      lrow[t] = (lane < nb) ? P[off] : 0.0;
-      Wb[lane * 33 + t] = (lane < nb) ? Wp[off] : 0.0;
-    }
-    __syncwarp();
-    for (int j = 0; j < nb; ++j) {
-      double acc = 0.0;
-#pragma unroll
-      for (int t = 0; t < NB; ++t) acc = fma(lrow[t], Wb[j * 33 + t], acc);
-      if (lane >= j && lane < nb) T[lane * 33 + j] -= acc;
-    }
-    __syncwarp();
-  }
   double a[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? T[lane * 33 + c] : T[c * 33 + lane];
@@ -784,6 +763,7 @@ __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* 
 __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
                                                   int nrowblk) {
   __shared__ double Lb[33 * NB];
+  __shared__ double tiles[4][NB * 33];   // row-swap CTAs: one tile per warp; trsm CTA 0: L / W rows of the next diagonal block
   __shared__ double di[NB], dof[NB];
   __shared__ int pty[NB], bp[NB];
   const int s = front_list[blockIdx.y];
@@ -802,7 +782,6 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
     if (c >= jb) return;  // (whole trailing warps may leave; remaining lanes of a partial warp still sync below)
     double* col = P + (size_t)c * f + jb;
     // each warp permutes the rows of its 32 columns through its own 32x33 shared tile
-    __shared__ double tiles[4][NB * 33];
     double* tl = tiles[tid >> 5];
     const int ln = tid & 31;
 #pragma unroll 8
@@ -824,10 +803,16 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
   }
   __syncthreads();
   const int i = row0 + blockIdx.x * blockDim.x + tid;
-  if (i >= f) return;
+  const bool active = i < f;
+  if (!active && blockIdx.x != 0) return;
+  // CTA 0 owns the rows of the NEXT panel's diagonal block: it also applies this panel's rank-32 update to that
+  // 32x32 block (the bulk trailing update skips it), so the next k_big_diag can start right after this kernel.
+  double* Ln = tiles[0];
+  double* Wn = tiles[1];
+  const int nb2 = (blockIdx.x == 0) ? max(0, min(NB, k - row0)) : 0;
   double x[NB];
 #pragma unroll
-  for (int t = 0; t < NB; ++t) x[t] = (t < nb) ? P[i + (size_t)(jb + bp[t]) * f] : 0.0;
+  for (int t = 0; t < NB; ++t) x[t] = (active && t < nb) ? P[i + (size_t)(jb + bp[t]) * f] : 0.0;
 #pragma unroll
   for (int t = 0; t < NB; ++t) {
     if (t < nb) {
@@ -848,9 +833,23 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
       if (ty == 1) l = x[t] * di[t];
       else if (ty == 2) l = x[t] * di[t] + x[(t + 1 < NB) ? t + 1 : t] * dof[t];
       else l = x[(t > 0) ? t - 1 : 0] * dof[(t > 0) ? t - 1 : 0] + x[t] * di[t];
-      Wp[i + (size_t)(jb + t) * f] = x[t];
-      P[i + (size_t)(jb + t) * f] = l;
-      if (fabs(l) > lim) bad = 1;
+      if (active) {
+        Wp[i + (size_t)(jb + t) * f] = x[t];
+        P[i + (size_t)(jb + t) * f] = l;
+        if (fabs(l) > lim) bad = 1;
+      }
+      if (tid < nb2) { Ln[tid * 33 + t] = l; Wn[tid * 33 + t] = x[t]; }
+    }
+  }
+  if (nb2 > 0) {
+    __syncthreads();
+    for (int e = tid; e < nb2 * nb2; e += blockDim.x) {
+      const int ii = e % nb2, jj = e / nb2;
+      if (ii >= jj) {
+        double acc = 0.0;
+        for (int t = 0; t < nb; ++t) acc = fma(Ln[ii * 33 + t], Wn[jj * 33 + t], acc);
+        P[(row0 + ii) + (size_t)(row0 + jj) * f] -= acc;
+      }
     }
   }
   if (bad) atomicAdd(N.counters + CNT_GROWTH, 1);
@@ -900,8 +899,8 @@ __device__ __forceinline__ void tile_syrk(double* __restrict__ C, long long ldc,
     for (int p = 0; p < 4; ++p) {
       int gi = i0 + tx + 16 * q, gj = j0 + ty + 16 * p;
       if (gi < M && gj < Nn && gi >= gj) {
-        // colmax_next != nullptr marks the panel update: the 32x32 block of the NEXT panel is left to the chain
-        // kernel (k_big_diag applies this panel's update to it itself, off the trailing update's critical path)
+        // colmax_next != nullptr marks the panel update: the 32x32 diagonal block of the NEXT panel is updated by
+        // CTA 0 of k_big_trsm instead, so the next k_big_diag does not have to wait for this (bulk) kernel
         if (colmax_next && gi < min(NB, Nn) && gj < NB) continue;   // (a partial last panel has fewer than 32 columns)
         const double nv = C[gi + (long long)gj * ldc] - acc[q][p];
         C[gi + (long long)gj * ldc] = nv;
