@@ -298,6 +298,7 @@ static int run_analysis(Solver* sv, const double* vals) {
   CU(sv->d_front_list.upload(fl, st));
   CU(cudaFuncSetAttribute(k_front_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CU(cudaFuncSetAttribute(k_front_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CU(cudaFuncSetAttribute(k_front_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
   CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute(k_bwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaStreamSynchronize(st));
@@ -427,6 +428,8 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
     for (const auto& bk : P.small) {
       if (bk.fmax <= 32) {  // one warp per front (registers), 4 fronts per CTA
         k_front_warp<<<cdiv(bk.cnt, 4), 128, 4 * XS_SMEM_PER_WARP, st>>>(D, N, fl + bk.off, bk.cnt); ++L;
+      } else if (getenv("B200_MID_PANEL")) {   // experimental panelised kernel (slower at 1 CTA/SM today; opt-in)
+        k_front_mid<<<bk.cnt, 256, mid_smem_bytes(bk.fmax), st>>>(D, N, fl + bk.off); ++L;
       } else {
         k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, st>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
       }

@@ -641,6 +641,175 @@ __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const in
 }
 
 // --------------------------------------------------------------------------------------------
+// Class M: fronts of order 33..128, one CTA, front in shared memory, PANELISED: the 32x32 diagonal block of each
+// panel is factorised in registers by warp 0 (warp_ldlt32, ~2.5x faster per pivot than the CTA-wide column loop of
+// k_front_smem), the panel rows and the trailing update are CTA-parallel.
+// smem: colbuf[64] | F[ld*f] | Lp[f*33] | Wp[f*33] | T[32*33] | dinv_s[32] | doff_s[32] | gmax[32] | order[32] | pt[32]
+// --------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t mid_smem_bytes(int f) {
+  const size_t ld = (size_t)(f | 1);
+  return (ld * f + 2 * (size_t)f * 33 + 32 * 33 + 64 + 32 + 32 + 32) * sizeof(double) + 64 * sizeof(int);
+}
+
+__global__ void __launch_bounds__(256) k_front_mid(DevSym S, DevNum N, const int* __restrict__ front_list) {
+  extern __shared__ double smem[];
+  const int s = front_list[blockIdx.x];
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int f = k + r, ld = f | 1;
+  double* colbuf = smem;                 // first: warp_ldlt32 reads it with 16-byte vector loads
+  double* F = colbuf + 64;
+  double* Lp = F + (size_t)ld * f;
+  double* Wp = Lp + (size_t)f * 33;
+  double* T = Wp + (size_t)f * 33;
+  double* dinv_s = T + 32 * 33;
+  double* doff_s = dinv_s + 32;
+  double* gmax = doff_s + 32;
+  int* order = (int*)(gmax + 32);
+  int* pt = order + 32;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+
+  for (int t = tid; t < ld * f; t += nt) F[t] = 0.0;
+  __syncthreads();
+  for (long long uu = S.uent_ptr[s] + tid; uu < S.uent_ptr[s + 1]; uu += nt) {
+    unsigned d = S.u_dst[uu];
+    int lr = d & 0xffffu, lc = d >> 16;
+    double v = N.uval[uu];
+    F[lr + lc * ld] = v;
+    F[lc + lr * ld] = v;
+  }
+  __syncthreads();
+  for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
+    const int c = S.child_idx[q];
+    const int rc = (int)(S.rows_ptr[c + 1] - S.rows_ptr[c]);
+    const double* __restrict__ cb = N.CB + S.cb_off[c];
+    const int* __restrict__ rl = S.rel + S.rows_ptr[c];
+    for (int jj = warp; jj < rc; jj += nwarp) {
+      const int lj = rl[jj];
+      for (int ii = jj + lane; ii < rc; ii += 32) {
+        const int li = rl[ii];
+        const double v = cb[ii + (size_t)jj * rc];
+        F[li + lj * ld] += v;
+        if (li != lj) F[lj + li * ld] += v;
+      }
+    }
+    __syncthreads();
+  }
+  double* __restrict__ P = N.L + S.L_off[s];
+  for (int jb = 0; jb < k; jb += 32) {
+    const int nb = min(32, k - jb), below = jb + nb;
+    // 1. column maxima below the diagonal block (threshold test sees the whole front column)
+    for (int c = warp; c < nb; c += nwarp) {
+      double m = 0.0;
+      for (int i = below + lane; i < f; i += 32) m = fmax(m, fabs(F[i + (jb + c) * ld]));
+      m = warp_max(m);
+      if (lane == 0) gmax[c] = m;
+    }
+    __syncthreads();
+    // 2. pivoted LDL^T of the diagonal block in registers (warp 0)
+    if (warp == 0) {
+      double a[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = (lane < nb && c < nb) ? F[(jb + lane) + (jb + c) * ld] : 0.0;
+      const double gext = (lane < nb) ? gmax[lane] : 0.0;
+      warp_ldlt32(a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colbuf, gext, N.counters);
+      if (lane < nb) {
+        N.lperm[c0 + jb + lane] = jb + order[lane];
+        N.dinv[c0 + jb + lane] = dinv_s[lane];
+        N.doff[c0 + jb + lane] = doff_s[lane];
+        N.ptype[c0 + jb + lane] = pt[lane];
+      }
+    }
+    __syncthreads();
+    // 3a. the block's row interchanges for the L columns already written (columns [0, jb), rows [jb, jb+nb))
+    for (int c = tid; c < jb; c += nt) {
+      double* col = P + (size_t)c * f + jb;
+      double tmp[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) tmp[t] = (t < nb) ? col[t] : 0.0;
+      // permute through this thread's private slice of Wp (free until step 3b)
+      double* sl = Wp + (size_t)c * 33;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) sl[t] = tmp[t];
+      for (int t = 0; t < nb; ++t) col[t] = sl[order[t]];
+    }
+    __syncthreads();
+    // 3b. panel rows below the block: x = A_perm L_bb^-T (= L D), l = x D^-1
+    for (int i = below + tid; i < f; i += nt) {
+      double x[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) x[t] = (t < nb) ? F[i + (jb + order[t]) * ld] : 0.0;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        if (t < nb) {
+          double acc = x[t];
+          const double* lrow = T + order[t] * 33;   // row of L_bb in pivot order: Lraw[order[t]][q], q < t
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (q < t) acc -= x[q] * lrow[q];
+          x[t] = acc;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        if (t < nb) {
+          double l;
+          const int ty = pt[t];
+          if (ty == 1) l = x[t] * dinv_s[t];
+          else if (ty == 2) l = x[t] * dinv_s[t] + x[(t + 1 < 32) ? t + 1 : t] * doff_s[t];
+          else l = x[(t > 0) ? t - 1 : 0] * doff_s[(t > 0) ? t - 1 : 0] + x[t] * dinv_s[t];
+          Lp[i * 33 + t] = l;
+          Wp[i * 33 + t] = x[t];
+          P[i + (size_t)(jb + t) * f] = l;
+        }
+      }
+    }
+    // L_bb (pivot order) and zeros above it
+    for (int e = tid; e < nb * (jb + nb); e += nt) {
+      const int t = e / (jb + nb), i = e % (jb + nb);
+      double v;
+      if (i < jb + t) v = 0.0;
+      else if (i == jb + t) v = 1.0;
+      else v = T[order[i - jb] * 33 + t];
+      P[i + (size_t)(jb + t) * f] = v;
+    }
+    __syncthreads();
+    // 4. trailing update (full square so the next diagonal block / column maxima read consistent values)
+    const int m = f - below;
+    for (int e = tid; e < ((m + 3) / 4) * ((m + 3) / 4); e += nt) {
+      const int bi = e % ((m + 3) / 4), bj = e / ((m + 3) / 4);
+      const int i0 = below + 4 * bi, j0 = below + 4 * bj;
+      double acc[4][4];
+#pragma unroll
+      for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) acc[a2][b2] = 0.0;
+      for (int t = 0; t < nb; ++t) {
+        double lv[4], wv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          lv[q] = (i0 + q < f) ? Lp[(i0 + q) * 33 + t] : 0.0;
+          wv[q] = (j0 + q < f) ? Wp[(j0 + q) * 33 + t] : 0.0;
+        }
+#pragma unroll
+        for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+          for (int b2 = 0; b2 < 4; ++b2) acc[a2][b2] = fma(lv[a2], wv[b2], acc[a2][b2]);
+      }
+#pragma unroll
+      for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2)
+          if (i0 + a2 < f && j0 + b2 < f) F[(i0 + a2) + (j0 + b2) * ld] -= acc[a2][b2];
+    }
+    __syncthreads();
+  }
+  double* __restrict__ cbo = N.CB + S.cb_off[s];
+  for (int mcol = warp; mcol < r; mcol += nwarp)
+    for (int i = mcol + lane; i < r; i += 32) cbo[i + (size_t)mcol * r] = F[(k + i) + (k + mcol) * ld];
+}
+
+// --------------------------------------------------------------------------------------------
 // Class L (big fronts), global-memory blocked path.
 // --------------------------------------------------------------------------------------------
 __global__ void k_big_zero(DevSym S, DevNum N, const int* __restrict__ front_list) {
