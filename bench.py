@@ -103,8 +103,8 @@ class ClockSampler(threading.Thread):
 
 
 def time_oracle(snaps, steps, warmup, threads):
-    from oracle_api import OracleLdlt
-    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from oracle_api import OracleLdlt, oracle_lib
+    oracle_lib().oracle_ldlt_set_threads(int(threads))
     s0 = snaps[0]
     o = OracleLdlt()
     o.InitializeStructure(s0["dim"], len(s0["irn"]), s0["irn"], s0["jcn"])
@@ -274,7 +274,15 @@ def main():
         tri_bytes = 2 * 8 * nnzL + 8 * 4 * dim   # L streamed twice + 2 reads/2 writes of the vector
         ach = tri_bytes / (tri_ms * 1e-3) / 1e9
         # CPU baseline, bounded sample on the host cores of this box
-        sec_cpu, ost = time_oracle(snaps, 3, 1, cpu_threads)
+        # the oracle's rank-1 updates are memory-bound: more threads are not always faster -> report the best of a few
+        cands = sorted({t for t in (8, 16, cpu_threads) if t <= cpu_threads})
+        trials = [(time_oracle(snaps, 1, 0, t)[0], t) for t in cands[:-1]] if len(cands) > 1 else []
+        best_t = min(trials)[1] if trials else cpu_threads
+        sec_last, ost = time_oracle(snaps, 3, 1, cpu_threads)
+        sec_cpu = sec_last
+        if trials and min(trials)[0] < sec_last:
+            sec_cpu, ost = time_oracle(snaps, 3, 1, best_t)
+            cpu_threads = best_t
         step_ms = ms_dev / K
         line = {
             "metric": "kkt_factor_solve_iters_per_sec", "value": world * K / (ms_dev * 1e-3), "unit": "iter/s",
@@ -285,7 +293,7 @@ def main():
             "gpu_launches": launches_timed,
             "kkt_factor_solve_ms_per_iter": {"device_resident": step_ms, "e2e_host_buffers": ms_e2e / K,
                                              "factor_ms": fac_ms, "solve_ms_per_rhs": tri_ms},
-            "roofline": {"kernel": "supernodal triangular solve sweep (k_fwd_front + k_bwd_front over all levels)",
+            "roofline": {"kernel": "supernodal triangular solve sweeps (k_solve_dataflow<fwd> + k_solve_dataflow<bwd>, persistent task-queue kernels)",
                          "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_solve": tri_bytes},

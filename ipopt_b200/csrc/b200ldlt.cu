@@ -436,7 +436,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
     }
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
-      k_big_colmax0<<<P.big_cnt, 256, 0, st>>>(D, N, bl); ++L;
+      k_big_colmax0<<<dim3(P.big_cnt, 8), 256, 0, st>>>(D, N, bl); ++L;
       // Panel pipeline on two streams (both inside the captured graph): the CHAIN  diag(p) -> trsm(p) -> diag(p+1)
       // is the critical path; the trailing update of panel p runs on the bulk stream concurrently with diag(p+1),
       // which applies panel p's rank-32 update to its own 32x32 block itself.

@@ -868,7 +868,7 @@ __global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_
   const int nb = min(2 * NB, k);   // panels 0 and 1 (panel 1's values lack panel 0's update: a one-panel-stale estimate)
   const double* __restrict__ P = N.L + S.L_off[s];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int j = warp; j < nb; j += nwarp) {
+  for (int j = blockIdx.y * nwarp + warp; j < nb; j += gridDim.y * nwarp) {   // one column per warp, 8 CTAs per front
     const int below = (j / NB + 1) * NB;
     double m = 0.0;
     for (int i = below + lane; i < f; i += 32) m = fmax(m, fabs(P[i + (size_t)j * f]));

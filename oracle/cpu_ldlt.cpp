@@ -25,6 +25,9 @@
 #include <cstring>
 #include <numeric>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 extern "C" int METIS_NodeND(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* options,
                             int64_t* perm, int64_t* iperm);
@@ -579,6 +582,13 @@ int oracle_ldlt_increase_quality(void* h) {
   if (O.pivtol >= O.pivtolmax) return 0;
   O.pivtol = std::min(O.pivtolmax, std::pow(O.pivtol, 0.5));  // IpMumpsSolverInterface.cpp:592-610
   return 1;
+}
+void oracle_ldlt_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 // out: [t_analyse, t_factor, t_solve, nnzL, flops, max_front, num_delayed, num_2x2]
 void oracle_ldlt_stats(void* h, double* out) {

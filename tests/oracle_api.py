@@ -27,6 +27,7 @@ def oracle_lib():
         L.oracle_ldlt_num_neg.argtypes = [C.c_void_p]
         L.oracle_ldlt_increase_quality.argtypes = [C.c_void_p]
         L.oracle_ldlt_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.oracle_ldlt_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
