@@ -468,7 +468,13 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaStreamWaitEvent(st, e, 0));
       }
       if (P.big_rmax > 0) {
-        k_big_schur<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
+        if (!getenv("B200_SCHUR_DMMA")) {
+          k_big_schur<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
+        } else {   // FP64 tensor-pipe (DMMA) contraction, 128x128 tiles: opt-in - measured 2-3 % SLOWER than the 64x64
+                   // DFMA tiles at these front sizes (r <= ~1500: too few 128x128 tiles to fill 148 SMs; B200's FP64
+                   // DMMA and DFMA peaks are equal), see profiles/r1_summary.md
+          k_big_schur_dmma<<<dim3(cdiv(P.big_rmax, DM_T), cdiv(P.big_rmax, DM_T), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
+        }
       }
     }
   }

@@ -1082,6 +1082,86 @@ __device__ __forceinline__ void tile_syrk(double* __restrict__ C, long long ldc,
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// FP64 tensor-pipe version of the Schur-complement contraction: C[i,j] -= sum_t A[i,t] * B[j,t], lower tiles only,
+// with mma.sync.m8n8k4.f64 (DMMA - the only FP64 path of the tensor pipe; tcgen05 has no f64 kind).
+// CTA tile 128x128, K step 16, 8 warps as 4(M) x 2(N), each warp 32x64 = 4 x 8 DMMA tiles (64 accumulators/thread).
+// Shared tiles As/Bs[16][132]: row stride 132 doubles (== 4 mod 16) makes the 64-bit fragment loads conflict-free.
+// --------------------------------------------------------------------------------------------
+#define DM_T 128
+#define DM_K 16
+#define DM_LD 132
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) k_big_schur_dmma(DevSym S, DevNum N, const int* __restrict__ front_list) {
+  __shared__ double As[DM_K * DM_LD];
+  __shared__ double Bs[DM_K * DM_LD];
+  const int s = front_list[blockIdx.z];
+  const int k = S.sn_start[s + 1] - S.sn_start[s];
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int f = k + r;
+  const int ti = blockIdx.x, tj = blockIdx.y;
+  if (tj > ti || ti * DM_T >= r) return;                 // lower tiles only
+  double* __restrict__ C = N.CB + S.cb_off[s];
+  const double* __restrict__ A = N.L + S.L_off[s] + k;    // rows k.. of L   (ld = f)
+  const double* __restrict__ B = N.W + S.L_off[s] + k;    // rows k.. of L*D (ld = f)
+  const int i0 = ti * DM_T, j0 = tj * DM_T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  double acc[4][8][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+  // global -> register prefetch: thread loads row (tid & 127), k columns (tid >> 7) + 2q
+  const int lrow = tid & 127, lk = tid >> 7;
+  double pa[8], pb[8];
+  auto prefetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int kk = k0 + lk + 2 * q;
+      pa[q] = (i0 + lrow < r && kk < k) ? A[(size_t)(i0 + lrow) + (size_t)kk * f] : 0.0;
+      pb[q] = (j0 + lrow < r && kk < k) ? B[(size_t)(j0 + lrow) + (size_t)kk * f] : 0.0;
+    }
+  };
+  prefetch(0);
+  for (int k0 = 0; k0 < k; k0 += DM_K) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      As[(lk + 2 * q) * DM_LD + lrow] = pa[q];
+      Bs[(lk + 2 * q) * DM_LD + lrow] = pb[q];
+    }
+    __syncthreads();
+    if (k0 + DM_K < k) prefetch(k0 + DM_K);
+#pragma unroll
+    for (int ks = 0; ks < DM_K; ks += 4) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = As[(ks + tig) * DM_LD + wm + a * 8 + gid];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) bf[b] = Bs[(ks + tig) * DM_LD + wn + b * 8 + gid];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) dmma_8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gi = i0 + wm + a * 8 + gid, gj = j0 + wn + b * 8 + 2 * tig + e;
+        if (gi < r && gj < r && gi >= gj) C[(size_t)gi + (size_t)gj * r] -= acc[a][b][e];
+      }
+}
+
 // trailing update of the remaining pivot columns after panel jb
 __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
   const int s = front_list[blockIdx.z];
