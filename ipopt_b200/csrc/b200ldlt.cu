@@ -92,6 +92,10 @@ struct Solver {
   DevBuf<long long> d_bigv_off;
   DevBuf<double> d_bigv, d_bigy;
   DevBuf<unsigned long long> d_ticket, d_tlog;
+  DevBuf<double> d_binv;
+  DevBuf<long long> d_binv_off;
+  DevBuf<int> d_binv_pairs;
+  int n_binv_pairs = 0;
   std::vector<SolveTask> h_tasks;   // fwd then bwd (debug timeline)
   DevSolve DV;
   int solve_epoch = 0, df_grid = 0;
@@ -320,6 +324,23 @@ static int run_analysis(Solver* sv, const double* vals) {
       std::vector<char> take(S.nsn, 1);
       build_solve_tasks(S, take, tf, tb, bundle);
     }
+    // inverse diagonal blocks of the big fronts (k_big_blockinv)
+    {
+      std::vector<long long> binv_off(S.nsn, -1);
+      std::vector<int> pairs;
+      long long tot = 0;
+      for (int s = 0; s < S.nsn; ++s) if (S.f(s) > MIDMAX) {
+        binv_off[s] = tot;
+        const int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK;
+        for (int b = 0; b < nkb; ++b) { pairs.push_back(s); pairs.push_back(b); }
+        tot += (long long)nkb * 8192;
+      }
+      sv->n_binv_pairs = (int)pairs.size() / 2;
+      if (pairs.empty()) pairs.push_back(0);
+      CU(sv->d_binv_off.upload(binv_off, st));
+      CU(sv->d_binv_pairs.upload(pairs, st));
+      CU(sv->d_binv.alloc(std::max<long long>(tot, 1)));
+    }
     CU(sv->d_tasks_f.upload(tf, st));
     CU(sv->d_tasks_b.upload(tb, st));
     if (bundle.empty()) bundle.push_back(0);
@@ -347,6 +368,8 @@ static int run_analysis(Solver* sv, const double* vals) {
     V.bflag_f = sv->d_bflag_f.p; V.bflag_b = sv->d_bflag_b.p; V.bcnt = sv->d_bcnt.p; V.bcnt_b = sv->d_bcnt_b.p;
     V.boff = sv->d_boff.p; V.bigv_off = sv->d_bigv_off.p; V.bigv = sv->d_bigv.p; V.bigy = sv->d_bigy.p;
     V.ticket = sv->d_ticket.p;
+    V.binv = getenv("B200_SOLVE_NOINV") ? nullptr : sv->d_binv.p;
+    V.binv_off = sv->d_binv_off.p;
     V.tlog = nullptr;
     if (getenv("B200_SOLVE_TIMELINE")) {
       CU(sv->d_tlog.alloc(2 * (tf.size() + tb.size())));
@@ -354,6 +377,7 @@ static int run_analysis(Solver* sv, const double* vals) {
       sv->h_tasks = tf; sv->h_tasks.insert(sv->h_tasks.end(), tb.begin(), tb.end());
     }
     const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
+    CU(cudaFuncSetAttribute(k_big_blockinv, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * (int)sizeof(double)));
     CU(cudaFuncSetAttribute(k_solve_dataflow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
     CU(cudaFuncSetAttribute(k_solve_dataflow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
     int occ = 1;
@@ -477,6 +501,10 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         }
       }
     }
+  }
+  if (sv->n_binv_pairs > 0 && sv->DV.binv != nullptr) {   // (in sharded runs: after each phase, for the fronts done so far)
+    // inverses of the 64x64 diagonal blocks of the big fronts for the triangular solves (all blocks in parallel)
+    k_big_blockinv<<<sv->n_binv_pairs, 64, 2 * 64 * 65 * sizeof(double), st>>>(D, N, sv->d_binv_pairs.p, sv->d_binv_off.p, sv->d_binv.p); ++L;
   }
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;

@@ -41,6 +41,8 @@ struct DevSolve {
   double* bigv;                // assembled+permuted rhs of big fronts
   double* bigy;                // y / x blocks of big fronts in pivoted order
   unsigned long long* ticket;  // [0] fwd, [1] bwd (monotonic)
+  const double* binv;          // per (big front, 64-block): Ext[64x64] (rows x pivot cols: [L_dd^-1 ; -L_cd L_dd^-1]) then L_dd^-T-friendly transpose
+  const long long* binv_off;   // nsn : offset of a big front's first block in binv (8192 doubles per block), -1 = none
   unsigned long long* tlog;    // optional (debug): 2 timestamps per task, fwd then bwd; nullptr = off
 };
 
@@ -417,6 +419,14 @@ __device__ void big_fwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
   __syncthreads();
   double wmine = 0.0;
   if (tid < nrow) wmine = __ldcg(V.bigv + V.bigv_off[s] + r0 + tid);
+  // precomputed inverse of the diagonal block (k_big_blockinv): the in-block substitution becomes a 64x64 GEMV
+  const bool use_inv = (V.binv != nullptr) && V.binv_off[s] >= 0 && ndiag > 0;
+  double ext[16];
+  if (use_inv) {
+    const double* __restrict__ E = V.binv + V.binv_off[s] + (size_t)b * 8192;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) ext[q] = E[tx + (ty + 4 * q) * 64];
+  }
   // software pipeline: the L tile of column block c+1 is in flight while block c is consumed
   double ltn[16];
   if (ncolblk_left > 0) {
@@ -448,7 +458,20 @@ __device__ void big_fwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
   __syncthreads();
   if (tid < 64) ys[tid] = (tid < nrow) ? wmine - (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]) : 0.0;
   __syncthreads();
-  if (warp == 0) {
+  if (use_inv) {
+    double p2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; if (t < ndiag) p2 = fma(ext[q], ys[t], p2); }
+    __syncthreads();                       // everyone has read ys
+    part[ty * 64 + tx] = p2;
+    __syncthreads();
+    if (tid < 64) {
+      const double g = part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid];
+      const double mine = ys[tid];
+      __syncwarp();
+      ys[tid] = (tid < ndiag) ? g : mine + g;   // pivot rows: y = L_dd^-1 v ; contribution rows of the block: v - L_cd y
+    }
+  } else if (warp == 0) {
     double v0 = ys[lane], v1 = ys[lane + 32];
 #pragma unroll 8
     for (int t = 0; t < ndiag; ++t) {
@@ -567,7 +590,22 @@ __device__ void big_bwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
     colacc[tid] = red[(2 * tyc) * 16 + q] + red[(2 * tyc + 1) * 16 + q];
   }
   __syncthreads();
-  if (warp == 0) {
+  const bool use_inv = (V.binv != nullptr) && V.binv_off[s] >= 0;
+  if (use_inv) {
+    // z_t = sum_{i >= t} Linv[i,t] * rhs_i  with the transposed copy (coalesced over t)
+    const double* __restrict__ ET = V.binv + V.binv_off[s] + (size_t)b * 8192 + 4096;
+    if (tid < 64) xs[tid] = (tid < ncol) ? x[c0 + t0 + tid] - colacc[tid] : 0.0;
+    __syncthreads();
+    double p2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int i = ty + 4 * q; if (i < ncol) p2 = fma(ET[tx + i * 64], xs[i], p2); }
+    __syncthreads();
+    red[0] = 0.0;   // (red is free again)
+    double* part2 = Lsq;   // 256 doubles of scratch
+    part2[ty * 64 + tx] = p2;
+    __syncthreads();
+    if (tid < 64) xs[tid] = part2[tid] + part2[64 + tid] + part2[128 + tid] + part2[192 + tid];
+  } else if (warp == 0) {
     double z0 = (lane < ncol) ? x[c0 + t0 + lane] - colacc[lane] : 0.0;
     double z1 = (lane + 32 < ncol) ? x[c0 + t0 + lane + 32] - colacc[lane + 32] : 0.0;
 #pragma unroll 8
@@ -590,6 +628,60 @@ __device__ void big_bwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
     if ((old + 1) % nkb == 0) { st_release(V.done_b + s, epoch); }
   }
   (void)t1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inverses of the 64x64 diagonal blocks of the big fronts' L11 (run once per factorisation, all blocks in parallel):
+//   Ext (64 x 64, ld 64): rows = rows of block b of the front, cols = its pivot columns:
+//        pivot rows      : L_dd^-1               (unit lower triangular)
+//        rows below k    : -L_cd * L_dd^-1       (contribution rows that share the block with the last pivots)
+//   ET  (64 x 64, ld 64): ET[t + i*64] = L_dd^-1[i][t]   (transposed copy for the backward sweep)
+// One CTA of 64 threads per (front, block); list = pairs (front, block).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_big_blockinv(DevSym S, DevNum N, const int* __restrict__ pairs,
+                                                     const long long* __restrict__ binv_off, double* __restrict__ binv) {
+  extern __shared__ double binv_sm[];
+  double* Ls = binv_sm;
+  double* Xs = binv_sm + 64 * 65;
+  const int s = pairs[2 * blockIdx.x], b = pairs[2 * blockIdx.x + 1];
+  const int k = S.sn_start[s + 1] - S.sn_start[s];
+  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int r0 = b * 64, nrow = min(64, f - r0), nd = min(64, k - r0);
+  const double* __restrict__ P = N.L + S.L_off[s];
+  double* __restrict__ E = binv + binv_off[s] + (size_t)b * 8192;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < 64 * 64; t += 64) {
+    const int i = t & 63, q = t >> 6;
+    Ls[i + q * 65] = (i < nrow && q < nd) ? P[(r0 + i) + (size_t)(r0 + q) * f] : 0.0;
+    Xs[i + q * 65] = 0.0;
+  }
+  __syncthreads();
+  // thread j computes column j of X = L_dd^-1 by forward substitution (unit diagonal)
+  if (tid < nd) {
+    const int j = tid;
+    Xs[j + j * 65] = 1.0;
+    for (int i = j + 1; i < nd; ++i) {
+      double acc = 0.0;
+      for (int t = j; t < i; ++t) acc = fma(Ls[i + t * 65], Xs[t + j * 65], acc);
+      Xs[i + j * 65] = -acc;
+    }
+  }
+  __syncthreads();
+  // rows of the block below the pivots: -L_cd * X
+  if (tid >= nd && tid < nrow) {
+    const int i = tid;
+    for (int j = 0; j < nd; ++j) {
+      double acc = 0.0;
+      for (int t = j; t < nd; ++t) acc = fma(Ls[i + t * 65], Xs[t + j * 65], acc);
+      Xs[i + j * 65] = -acc;
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < 64 * 64; t += 64) {
+    const int i = t & 63, q = t >> 6;
+    E[i + q * 64] = Xs[i + q * 65];
+    E[4096 + i + q * 64] = (i < nd && q < nd) ? Xs[q + i * 65] : 0.0;   // ET[t=i + row q*64] = X[q][i]
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
