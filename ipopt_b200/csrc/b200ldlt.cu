@@ -477,7 +477,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaStreamWaitEvent(sb, ec, 0));
         int rows_below = P.big_fmax - jb;  // upper bound
         int nrowblk = std::max(1u, cdiv(rows_below, 128));
-        k_big_trsm<<<dim3(nrowblk + cdiv(jb, 128), P.big_cnt), 128, 0, sb>>>(D, N, bl, jb, nrowblk); ++L;
+        k_big_trsm<<<dim3(nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), 128, 0, sb>>>(D, N, bl, jb, nrowblk); ++L;
         cudaEvent_t et = sv->next_event();
         CU(cudaEventRecord(et, sb));
         CU(cudaStreamWaitEvent(st, et, 0));      // diag(p+1) needs L/W of its own rows from trsm(p)

@@ -318,6 +318,14 @@ __device__ __forceinline__ void wred_max_idx(double& v, int& idx) {
   }
 }
 
+// warp-wide max of non-negative floats in ONE instruction (CREDUX.MAX.F32, sm_100a).  The pivot SEARCH runs on
+// float-rounded magnitudes (the tests are inequalities with slack >= 1e-8, the selected entries are then re-read exactly).
+__device__ __forceinline__ float wredux_max(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+
 __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const double u, const double tiny,
                             double* __restrict__ Lraw, int* __restrict__ order, int* __restrict__ pt,
                             double* __restrict__ dinv_s, double* __restrict__ doff_s,
@@ -334,6 +342,8 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
   int nc = k, npass = k, t = 0, progress = 0;
   bool forced = false;
   int c_neg = 0, c_forced = 0, c_tiny = 0, c_2x2 = 0;
+  int my_order = 0, my_pt = 1;
+  double my_dinv = 0.0, my_doff = 0.0;
   while (nc > 0) {
     if (npass == 0) {
       if (progress > 0) { npass = nc; progress = 0; }
@@ -344,12 +354,15 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
     int g0 = __ffs(__ballot_sync(0xffffffffu, me_alive && mypos == 0)) - 1;
     // ---- pivot search on column 0 ----
     const double v0 = fabs(a[0]);
-    double lam = (me_cand && lane != g0) ? v0 : -1.0;
-    int r = (me_cand && lane != g0) ? lane : 64;
-    wred_max_idx(lam, r);
-    double gam = (me_alive && !me_cand) ? v0 : 0.0;
-    gam = fmax(warp_max(gam), __shfl_sync(0xffffffffu, gext, g0));
-    if (lam < 0.0) { lam = 0.0; r = -1; }
+    const float v0f = __double2float_ru(v0);
+    const float lam_in = (me_cand && lane != g0) ? v0f : -1.0f;
+    const float lamf = wredux_max(lam_in);
+    const float gamf = wredux_max((me_alive && !me_cand) ? v0f : 0.0f);
+    int r = __ffs(__ballot_sync(0xffffffffu, lam_in == lamf)) - 1;   // lowest lane holding the maximum
+    double lam = 0.0;
+    if (lamf < 0.0f) r = -1;
+    else lam = __shfl_sync(0xffffffffu, v0, r);                       // exact magnitude of the selected entry
+    const double gam = fmax((double)gamf, __shfl_sync(0xffffffffu, gext, g0));
     const double ajj = fabs(__shfl_sync(0xffffffffu, a[0], g0));
     const bool ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
     int type = 0;
@@ -370,11 +383,11 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
         if (mypos == 1) mypos = p; else if (mypos == p) mypos = 1;
       }
       const double v1 = fabs(a[1]);
-      double sig = (me_cand && lane != r) ? v1 : 0.0;
-      double gamr = (me_alive && !me_cand) ? v1 : 0.0;
+      const float v1f = __double2float_ru(v1);
       const bool other = me_alive && lane != g0 && lane != r;
-      double cj = other ? v0 : 0.0, cr = other ? v1 : 0.0;
-      sig = warp_max(sig); gamr = warp_max(gamr); cj = warp_max(cj); cr = warp_max(cr);
+      double sig = (double)wredux_max((me_cand && lane != r) ? v1f : 0.0f);
+      double gamr = (double)wredux_max((me_alive && !me_cand) ? v1f : 0.0f);
+      double cj = (double)wredux_max(other ? v0f : 0.0f), cr = (double)wredux_max(other ? v1f : 0.0f);
       {
         const double ge_r = __shfl_sync(0xffffffffu, gext, r), ge_j = __shfl_sync(0xffffffffu, gext, g0);
         gamr = fmax(gamr, ge_r); cr = fmax(cr, ge_r); cj = fmax(cj, ge_j);
@@ -422,7 +435,8 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
         }
       }
       const double c0v = a[0];
-      const double l = (me_alive && lane != g0) ? c0v / dd : 0.0;
+      const double rinv = 1.0 / dd;
+      const double l = (me_alive && lane != g0) ? c0v * rinv : 0.0;
       // pivot row by position: F[g0][col at position c] = F[that col's row][g0] = that lane's a[0]
       if (me_alive) colbuf[mypos] = c0v;
       __syncwarp();
@@ -435,7 +449,7 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       }
       __syncwarp();
       Lraw[lane * 33 + t] = l;
-      if (lane == 0) { order[t] = g0; pt[t] = 1; dinv_s[t] = 1.0 / dd; doff_s[t] = 0.0; }
+      if (lane == t) { my_order = g0; my_pt = 1; my_dinv = rinv; my_doff = 0.0; }   // lane t keeps pivot t's record
       if (dd < 0.0) ++c_neg;
       alive &= ~(1u << g0); cand &= ~(1u << g0);
 #pragma unroll
@@ -449,8 +463,9 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       const double det = pa * pc2 - pb * pb;
       const double c1 = a[0], c2v = a[1];
       const bool other = me_alive && lane != g0 && lane != r;
-      const double l1 = other ? (pc2 * c1 - pb * c2v) / det : 0.0;
-      const double l2 = other ? (pa * c2v - pb * c1) / det : 0.0;
+      const double idet = 1.0 / det;
+      const double l1 = other ? (pc2 * c1 - pb * c2v) * idet : 0.0;
+      const double l2 = other ? (pa * c2v - pb * c1) * idet : 0.0;
       if (me_alive) { colbuf[mypos] = c1; colbuf[32 + mypos] = c2v; }
       __syncwarp();
       const double2* cb1 = reinterpret_cast<const double2*>(colbuf);
@@ -464,10 +479,8 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       __syncwarp();
       Lraw[lane * 33 + t] = l1;
       Lraw[lane * 33 + t + 1] = l2;
-      if (lane == 0) {
-        order[t] = g0; order[t + 1] = r; pt[t] = 2; pt[t + 1] = 3;
-        dinv_s[t] = pc2 / det; dinv_s[t + 1] = pa / det; doff_s[t] = -pb / det; doff_s[t + 1] = 0.0;
-      }
+      if (lane == t) { my_order = g0; my_pt = 2; my_dinv = pc2 * idet; my_doff = -pb * idet; }
+      if (lane == t + 1) { my_order = r; my_pt = 3; my_dinv = pa * idet; my_doff = 0.0; }
       ++c_2x2;
       if (det < 0.0) c_neg += 1; else if (pa < 0.0) c_neg += 2;
       alive &= ~((1u << g0) | (1u << r)); cand &= ~((1u << g0) | (1u << r));
@@ -479,6 +492,7 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
     }
     ++progress;
   }
+  if (lane < k) { order[lane] = my_order; pt[lane] = my_pt; dinv_s[lane] = my_dinv; doff_s[lane] = my_doff; }
   if (lane == 0) {
     if (c_neg) atomicAdd(counters + CNT_NEG, c_neg);
     if (c_forced) atomicAdd(counters + CNT_FORCED, c_forced);
@@ -927,14 +941,19 @@ __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* 
   }
 }
 
-// rows below the diagonal block: W = A_perm * L_bb^-T (= L*D), L = W * D^-1.
-// CTAs with blockIdx.x >= nrowblk apply the block's row interchanges to the L columns on the left.
+// rows below the diagonal block: W = A_perm * L_bb^-T (= L*D), L = W * D^-1.  One row per thread, the triangular
+// solve runs right-looking (x[q] -= x[t] L[q][t] for all q > t: independent FMAs, the block column read as double2).
+// CTAs with blockIdx.x >= nrowblk apply the block's row interchanges to the L columns on the left: one WARP per
+// column (the 32 rows of a column are one 256-byte segment; the permutation is a warp shuffle), TRSM_SWAP_COLS
+// columns per CTA.
+#define TRSM_LD 34          // even leading dimension: column t of the block starts 16-byte aligned
+#define TRSM_SWAP_COLS 32   // columns per row-swap CTA (4 warps x 8)
 __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
                                                   int nrowblk) {
-  __shared__ double Lb[33 * NB];
-  __shared__ double tiles[4][NB * 33];   // row-swap CTAs: one tile per warp; trsm CTA 0: L / W rows of the next diagonal block
-  __shared__ double di[NB], dof[NB];
-  __shared__ int pty[NB], bp[NB];
+  __shared__ __align__(16) double Lb[NB * TRSM_LD];
+  __shared__ double Ln[NB * 33], Wn[NB * 33];   // CTA 0: L / W rows of the next diagonal block
+  __shared__ double di[NB], dup[NB], dlo[NB];
+  __shared__ int bp[NB];
   const int s = front_list[blockIdx.y];
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   if (jb >= k) return;
@@ -945,83 +964,121 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
   const int tid = threadIdx.x;
   if ((int)blockIdx.x >= nrowblk) {
     // ---- left part: rows jb..jb+nb of columns [0, jb) get the block permutation ----
-    const int c = ((int)blockIdx.x - nrowblk) * blockDim.x + tid;
-    if (tid < nb) bp[tid] = N.bperm[c0 + jb + tid];
-    __syncthreads();
-    if (c >= jb) return;  // (whole trailing warps may leave; remaining lanes of a partial warp still sync below)
-    double* col = P + (size_t)c * f + jb;
-    // each warp permutes the rows of its 32 columns through its own 32x33 shared tile
-    double* tl = tiles[tid >> 5];
-    const int ln = tid & 31;
-#pragma unroll 8
-    for (int t = 0; t < nb; ++t) tl[ln * 33 + t] = col[t];
-    __syncwarp();
-#pragma unroll 8
-    for (int t = 0; t < nb; ++t) col[t] = tl[ln * 33 + bp[t]];
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cbeg = ((int)blockIdx.x - nrowblk) * TRSM_SWAP_COLS;
+    if (cbeg >= jb) return;
+    const int src = (lane < nb) ? N.bperm[c0 + jb + lane] : lane;
+    double v[TRSM_SWAP_COLS / 4];
+#pragma unroll
+    for (int q = 0; q < TRSM_SWAP_COLS / 4; ++q) {
+      const int c = cbeg + warp + 4 * q;
+      v[q] = (c < jb && lane < nb) ? P[(size_t)c * f + jb + lane] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < TRSM_SWAP_COLS / 4; ++q) {
+      const int c = cbeg + warp + 4 * q;
+      const double w = __shfl_sync(0xffffffffu, v[q], src);
+      if (c < jb && lane < nb) P[(size_t)c * f + jb + lane] = w;
+    }
     return;
   }
-  if ((long long)blockIdx.x * blockDim.x >= f - row0) return;
+  if ((long long)blockIdx.x * blockDim.x >= f - row0 && blockIdx.x != 0) return;
   double* Wp = N.W + S.L_off[s];
-  for (int t = tid; t < nb * nb; t += blockDim.x) {
-    int i = t % nb, j = t / nb;
-    Lb[i + j * 33] = P[(jb + i) + (size_t)(jb + j) * f];
-  }
-  if (tid < nb) {
-    di[tid] = N.dinv[c0 + jb + tid]; dof[tid] = N.doff[c0 + jb + tid];
-    pty[tid] = N.ptype[c0 + jb + tid]; bp[tid] = N.bperm[c0 + jb + tid];
-  }
-  __syncthreads();
   const int i = row0 + blockIdx.x * blockDim.x + tid;
   const bool active = i < f;
-  if (!active && blockIdx.x != 0) return;
+  // issue all global loads up front: the diagonal block, its D, and this thread's row (columns in pivot order)
+  {
+    double lb[NB * NB / 128];
+#pragma unroll
+    for (int q = 0; q < NB * NB / 128; ++q) {
+      const int t = tid + 128 * q, ii = t & (NB - 1), jj = t / NB;
+      lb[q] = (ii < nb && jj < nb && ii > jj) ? P[(jb + ii) + (size_t)(jb + jj) * f] : 0.0;
+    }
+    if (tid < NB) {
+      double d = 0.0, o = 0.0, om = 0.0;
+      int ty = 1, tym = 1, b = tid;
+      if (tid < nb) {
+        d = N.dinv[c0 + jb + tid]; o = N.doff[c0 + jb + tid]; ty = N.ptype[c0 + jb + tid]; b = N.bperm[c0 + jb + tid];
+        if (tid > 0) { om = N.doff[c0 + jb + tid - 1]; tym = N.ptype[c0 + jb + tid - 1]; }
+      }
+      di[tid] = d;
+      dup[tid] = (ty == 2) ? o : 0.0;                  // first column of a 2x2 pivot: + x[t+1] * offdiag
+      dlo[tid] = (ty == 3 && tym == 2) ? om : 0.0;      // second column:              + x[t-1] * offdiag
+      bp[tid] = b;
+    }
+#pragma unroll
+    for (int q = 0; q < NB * NB / 128; ++q) {
+      const int t = tid + 128 * q, ii = t & (NB - 1), jj = t / NB;
+      Lb[ii + jj * TRSM_LD] = lb[q];
+    }
+  }
+  __syncthreads();
   // CTA 0 owns the rows of the NEXT panel's diagonal block: it also applies this panel's rank-32 update to that
   // 32x32 block (the bulk trailing update skips it), so the next k_big_diag can start right after this kernel.
-  double* Ln = tiles[0];
-  double* Wn = tiles[1];
   const int nb2 = (blockIdx.x == 0) ? max(0, min(NB, k - row0)) : 0;
   double x[NB];
 #pragma unroll
   for (int t = 0; t < NB; ++t) x[t] = (active && t < nb) ? P[i + (size_t)(jb + bp[t]) * f] : 0.0;
 #pragma unroll
-  for (int t = 0; t < NB; ++t) {
-    if (t < nb) {
-      double acc = x[t];
+  for (int t = 0; t < NB - 1; ++t) {
+    const double xt = x[t];
+    const double* __restrict__ col = Lb + t * TRSM_LD;
+    if (((t + 1) & 1) != 0) x[t + 1] = fma(-xt, col[t + 1], x[t + 1]);
 #pragma unroll
-      for (int q = 0; q < NB; ++q)
-        if (q < t) acc -= x[q] * Lb[t + q * 33];
-      x[t] = acc;
+    for (int q = (t + 2) & ~1; q < NB; q += 2) {
+      const double2 l2 = *reinterpret_cast<const double2*>(col + q);
+      x[q] = fma(-xt, l2.x, x[q]);
+      x[q + 1] = fma(-xt, l2.y, x[q + 1]);
     }
   }
   const double lim = 1.0 / N.u;
-  int bad = 0;
+  double lmax = 0.0;
+  double l[NB];
 #pragma unroll
   for (int t = 0; t < NB; ++t) {
-    if (t < nb) {
-      double l;
-      const int ty = pty[t];
-      if (ty == 1) l = x[t] * di[t];
-      else if (ty == 2) l = x[t] * di[t] + x[(t + 1 < NB) ? t + 1 : t] * dof[t];
-      else l = x[(t > 0) ? t - 1 : 0] * dof[(t > 0) ? t - 1 : 0] + x[t] * di[t];
-      if (active) {
-        Wp[i + (size_t)(jb + t) * f] = x[t];
-        P[i + (size_t)(jb + t) * f] = l;
-        if (fabs(l) > lim) bad = 1;
-      }
-      if (tid < nb2) { Ln[tid * 33 + t] = l; Wn[tid * 33 + t] = x[t]; }
-    }
+    double v = x[t] * di[t];
+    if (t + 1 < NB) v = fma(x[t + 1], dup[t], v);
+    if (t > 0) v = fma(x[t - 1], dlo[t], v);
+    l[t] = v;
+    lmax = fmax(lmax, fabs(v));
+  }
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+      if (t < nb) { Wp[i + (size_t)(jb + t) * f] = x[t]; P[i + (size_t)(jb + t) * f] = l[t]; }
   }
   if (nb2 > 0) {
+    if (tid < nb2) {
+#pragma unroll
+      for (int t = 0; t < NB; ++t) { Ln[tid * 33 + t] = l[t]; Wn[tid * 33 + t] = x[t]; }
+    }
     __syncthreads();
-    for (int e = tid; e < nb2 * nb2; e += blockDim.x) {
-      const int ii = e % nb2, jj = e / nb2;
-      if (ii >= jj) {
-        double acc = 0.0;
-        for (int t = 0; t < nb; ++t) acc = fma(Ln[ii * 33 + t], Wn[jj * 33 + t], acc);
-        P[(row0 + ii) + (size_t)(row0 + jj) * f] -= acc;
+    // 32x32 block update, 2x4 entries per thread: rows a, a+16; columns b, b+8, b+16, b+24
+    const int a = tid & 15, b = tid >> 4;
+    double acc[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < NB; ++t) {
+      const double l0 = Ln[a * 33 + t], l1 = Ln[(a + 16) * 33 + t];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const double wv = Wn[(b + 8 * w) * 33 + t];
+        acc[0][w] = fma(l0, wv, acc[0][w]);
+        acc[1][w] = fma(l1, wv, acc[1][w]);
       }
     }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int ii = a + 16 * u, jj = b + 8 * w;
+        if (ii < nb2 && jj <= ii) P[(row0 + ii) + (size_t)(row0 + jj) * f] -= acc[u][w];
+      }
   }
-  if (bad) atomicAdd(N.counters + CNT_GROWTH, 1);
+  if (active && lmax > lim) atomicAdd(N.counters + CNT_GROWTH, 1);
 }
 
 // C[i,j] -= sum_t A[i,t] * B[j,t] on the lower trapezoid i >= j (global coordinates aligned:
