@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "factor_kernels.cu"
@@ -40,6 +41,15 @@ struct DevBuf {
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(st);  // tmp dies here
   }
+};
+
+// work lists of the explicit L11 inverses of the big fronts (k_linv_diag / k_linv_gemm, solve_dataflow.cu)
+struct LinvPlan {
+  DevBuf<int> d_diag;                      // (front, 64-block) pairs
+  int ndiag = 0;
+  std::vector<std::unique_ptr<DevBuf<LinvItem>>> d_g;   // per recursion level: the tile items (same list for both passes ...
+  std::vector<std::unique_ptr<DevBuf<LinvItem>>> d_g2;  // ... up to the k-range)
+  std::vector<int> ng;
 };
 
 struct LevelPlan {
@@ -92,10 +102,9 @@ struct Solver {
   DevBuf<long long> d_bigv_off;
   DevBuf<double> d_bigv, d_bigy;
   DevBuf<unsigned long long> d_ticket, d_tlog;
-  DevBuf<double> d_binv;
-  DevBuf<long long> d_binv_off;
-  DevBuf<int> d_binv_pairs;
-  int n_binv_pairs = 0;
+  DevBuf<double> d_linv;
+  DevBuf<long long> d_linv_off;
+  LinvPlan linv_plan;               // explicit inverses of the big fronts' pivot blocks (all fronts)
   std::vector<SolveTask> h_tasks;   // fwd then bwd (debug timeline)
   DevSolve DV;
   int solve_epoch = 0, df_grid = 0;
@@ -109,6 +118,7 @@ struct Solver {
     DevBuf<int> d_fl[2], d_bundle[2], d_mark_cut, d_mark_top;
     DevBuf<SolveTask> d_tf[2], d_tb[2];
     DevSolve DV[2];
+    LinvPlan linv_plan[2];
   } shard;
   cudaGraph_t fgraph = nullptr;
   cudaGraphExec_t fgraph_exec = nullptr;
@@ -169,18 +179,33 @@ static void build_level_plans(const Symbolic& S, int smax, const std::vector<cha
       }
     }
     // small fronts (level_sn is sorted by f descending inside a level)
-    const int lim[3] = {64, 32, 0};
-    const int thr[3] = {256, 128, 64};
-    int b = 0;
-    LevelPlan::Bucket cur{(int)fl.size(), 0, 0, 0, thr[0], 0};
+    // Size classes: (64, smax] 256 threads, (32, 64] 128 threads, <= 32 one warp per front.  Inside a class the
+    // fronts are split again at the soft limits below (shared memory per CTA follows the largest front of a launch,
+    // so finer buckets raise the number of resident CTAs per SM); a soft split only happens once the current bucket
+    // holds enough fronts to fill the GPU.
+    std::vector<int> soft;   // (measured at N=400: every extra launch costs more than the occupancy gains - no soft splits by default)
+    if (const char* e = getenv("B200_BUCKETS")) {
+      soft.clear();
+      for (const char* p = e; *p;) { soft.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
+    }
+    const int kMinBucket = 296;
+    auto threads_of = [](int f) { return f > 64 ? 256 : (f > 32 ? 128 : 64); };
+    LevelPlan::Bucket cur{(int)fl.size(), 0, 0, 0, 256, 0};
+    int cur_lo = 1 << 30;   // the current bucket accepts f > cur_lo ... (set when the bucket gets its first front)
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
       int s = S.level_sn[q];
       int f = S.f(s);
       if (!take[s] || f > smax) continue;
-      while (b < 2 && f <= lim[b]) {
-        if (cur.cnt) P.small.push_back(cur);
-        ++b;
-        cur = LevelPlan::Bucket{(int)fl.size(), 0, 0, 0, thr[b], 0};
+      bool split = false;
+      if (cur.cnt) {
+        if (threads_of(f) != cur.threads) split = true;
+        else if (cur.cnt >= kMinBucket && f <= cur_lo) split = true;
+      }
+      if (split) { P.small.push_back(cur); cur = LevelPlan::Bucket{(int)fl.size(), 0, 0, 0, 256, 0}; }
+      if (cur.cnt == 0) {
+        cur.threads = threads_of(f);
+        cur_lo = 0;
+        for (int v : soft) if (v < f) cur_lo = std::max(cur_lo, v);
       }
       fl.push_back(s);
       cur.cnt++;
@@ -196,6 +221,49 @@ static void build_level_plans(const Symbolic& S, int smax, const std::vector<cha
   }
 }
 
+static const int kSolveMidMax = 256;   // fronts above this order are "big" in the solve (block tasks + explicit L11 inverse)
+
+static int build_linv_plan(Solver* sv, const Symbolic& S, const std::vector<char>& take, LinvPlan& LP, cudaStream_t st) {
+  std::vector<int> pairs;
+  int maxkb = 0;
+  for (int s = 0; s < S.nsn; ++s) if (take[s] && S.f(s) > kSolveMidMax) {
+    const int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK;
+    maxkb = std::max(maxkb, nkb);
+    for (int b = 0; b < nkb; ++b) { pairs.push_back(s); pairs.push_back(b); }
+  }
+  LP.ndiag = (int)pairs.size() / 2;
+  if (pairs.empty()) pairs.push_back(0);
+  CU(LP.d_diag.upload(pairs, st));
+  LP.d_g.clear(); LP.d_g2.clear(); LP.ng.clear();
+  for (int Bt = 1; Bt < maxkb; Bt *= 2) {   // merge neighbouring blocks of Bt tiles
+    std::vector<LinvItem> g1, g2;
+    for (int s = 0; s < S.nsn; ++s) if (take[s] && S.f(s) > kSolveMidMax) {
+      const int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK;
+      for (int a0 = 0; a0 + Bt < nkb; a0 += 2 * Bt) {
+        const int a1 = a0 + Bt, b1 = std::min(a1 + Bt, nkb);   // first block [a0,a1), second [a1,b1)
+        for (int ib = a1; ib < b1; ++ib)
+          for (int jb = a0; jb < a1; ++jb) {
+            g1.push_back(LinvItem{s, ib, jb, jb, a1});        // T[ib,jb]    =  sum_{m=jb..a1-1} L[ib,m] Inv11[m,jb]
+            g2.push_back(LinvItem{s, ib, jb, a1, ib + 1});    // Linv[ib,jb] = -sum_{m=a1..ib}   Inv22[ib,m] T[m,jb]
+          }
+      }
+    }
+    // longest items first (the launch ends with its slowest tile)
+    auto longer = [](const LinvItem& x, const LinvItem& y) { return (x.m1 - x.m0) > (y.m1 - y.m0); };
+    std::stable_sort(g1.begin(), g1.end(), longer);
+    std::stable_sort(g2.begin(), g2.end(), longer);
+    LP.ng.push_back((int)g1.size());
+    if (g1.empty()) { g1.push_back(LinvItem{0, 0, 0, 0, 0}); g2.push_back(LinvItem{0, 0, 0, 0, 0}); }
+    LP.d_g.emplace_back(new DevBuf<LinvItem>());
+    LP.d_g2.emplace_back(new DevBuf<LinvItem>());
+    CU(LP.d_g.back()->upload(g1, st));
+    CU(LP.d_g2.back()->upload(g2, st));
+  }
+  return B200LDLT_SUCCESS;
+}
+
+static int enqueue_linv(Solver* sv, const LinvPlan& LP);
+
 // topologically sorted solve task lists (forward: levels ascending, backward: descending) for the fronts in take[]
 static void build_solve_tasks(const Symbolic& S, const std::vector<char>& take, std::vector<SolveTask>& tf,
                               std::vector<SolveTask>& tb, std::vector<int>& bundle) {
@@ -209,15 +277,20 @@ static void build_solve_tasks(const Symbolic& S, const std::vector<char>& take, 
       for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
         int s = S.level_sn[q];
         if (!take[s] || S.f(s) <= MIDMAX) continue;
-        if (pass == 0) {
-          T.push_back({ST_BIG_GATHER, s, 0, 0});
-          int nb = (S.f(s) + DF_BLK - 1) / DF_BLK;
-          for (int b = 0; b < nb; ++b) T.push_back({ST_BIG_BLOCK, s, b, 0});
-        } else {
-          int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK;
-          for (int b = nkb - 1; b >= 0; --b) T.push_back({ST_BIG_BLOCK, s, b, 0});
-        }
+        if (pass == 0) T.push_back({ST_BIG_GATHER, s, 0, 0});
       }
+      // the block tasks of a front are independent of each other inside a phase (explicit L11 inverse):
+      // phase 0 = pivot blocks (forward) / t blocks (backward), phase 1 = contribution rows / x blocks; long tasks first
+      for (int phase = 0; phase < 2; ++phase)
+        for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+          int s = S.level_sn[q];
+          if (!take[s] || S.f(s) <= MIDMAX) continue;
+          const int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK, ncb = (S.r(s) + DF_BLK - 1) / DF_BLK;
+          if (pass == 0 && phase == 0) for (int b = nkb - 1; b >= 0; --b) T.push_back({ST_BIG_BLOCK, s, b, 0});
+          if (pass == 0 && phase == 1) for (int j = 0; j < ncb; ++j) T.push_back({ST_BIG_BLOCK, s, j, 1});
+          if (pass == 1 && phase == 0) for (int b = 0; b < nkb; ++b) T.push_back({ST_BIG_BLOCK, s, b, 0});
+          if (pass == 1 && phase == 1) for (int b = 0; b < nkb; ++b) T.push_back({ST_BIG_BLOCK, s, b, 1});
+        }
       for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
         int s = S.level_sn[q];
         if (!take[s] || S.f(s) > MIDMAX) continue;
@@ -324,22 +397,21 @@ static int run_analysis(Solver* sv, const double* vals) {
       std::vector<char> take(S.nsn, 1);
       build_solve_tasks(S, take, tf, tb, bundle);
     }
-    // inverse diagonal blocks of the big fronts (k_big_blockinv)
+    // explicit inverses of the big fronts' pivot blocks (k_linv_*): K64 x K64 doubles per big front
     {
-      std::vector<long long> binv_off(S.nsn, -1);
-      std::vector<int> pairs;
+      std::vector<long long> linv_off(S.nsn, -1);
       long long tot = 0;
       for (int s = 0; s < S.nsn; ++s) if (S.f(s) > MIDMAX) {
-        binv_off[s] = tot;
-        const int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK;
-        for (int b = 0; b < nkb; ++b) { pairs.push_back(s); pairs.push_back(b); }
-        tot += (long long)nkb * 8192;
+        linv_off[s] = tot;
+        const long long K64 = (long long)((S.k(s) + DF_BLK - 1) / DF_BLK) * DF_BLK;
+        tot += K64 * K64;
       }
-      sv->n_binv_pairs = (int)pairs.size() / 2;
-      if (pairs.empty()) pairs.push_back(0);
-      CU(sv->d_binv_off.upload(binv_off, st));
-      CU(sv->d_binv_pairs.upload(pairs, st));
-      CU(sv->d_binv.alloc(std::max<long long>(tot, 1)));
+      CU(sv->d_linv_off.upload(linv_off, st));
+      CU(sv->d_linv.alloc(std::max<long long>(tot, 1)));
+      CU(cudaMemsetAsync(sv->d_linv.p, 0, sv->d_linv.n * sizeof(double), st));
+      std::vector<char> take(S.nsn, 1);
+      int rc2 = build_linv_plan(sv, S, take, sv->linv_plan, st);
+      if (rc2 != B200LDLT_SUCCESS) return rc2;
     }
     CU(sv->d_tasks_f.upload(tf, st));
     CU(sv->d_tasks_b.upload(tb, st));
@@ -368,8 +440,8 @@ static int run_analysis(Solver* sv, const double* vals) {
     V.bflag_f = sv->d_bflag_f.p; V.bflag_b = sv->d_bflag_b.p; V.bcnt = sv->d_bcnt.p; V.bcnt_b = sv->d_bcnt_b.p;
     V.boff = sv->d_boff.p; V.bigv_off = sv->d_bigv_off.p; V.bigv = sv->d_bigv.p; V.bigy = sv->d_bigy.p;
     V.ticket = sv->d_ticket.p;
-    V.binv = getenv("B200_SOLVE_NOINV") ? nullptr : sv->d_binv.p;
-    V.binv_off = sv->d_binv_off.p;
+    V.linv = sv->d_linv.p;
+    V.linv_off = sv->d_linv_off.p;
     V.tlog = nullptr;
     if (getenv("B200_SOLVE_TIMELINE")) {
       CU(sv->d_tlog.alloc(2 * (tf.size() + tb.size())));
@@ -377,7 +449,6 @@ static int run_analysis(Solver* sv, const double* vals) {
       sv->h_tasks = tf; sv->h_tasks.insert(sv->h_tasks.end(), tb.begin(), tb.end());
     }
     const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
-    CU(cudaFuncSetAttribute(k_big_blockinv, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * (int)sizeof(double)));
     CU(cudaFuncSetAttribute(k_solve_dataflow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
     CU(cudaFuncSetAttribute(k_solve_dataflow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
     int occ = 1;
@@ -412,7 +483,7 @@ static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b
 
 // enqueue the whole numeric factorisation of the values in d_vals
 static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nullptr, const int* fl_p = nullptr,
-                          bool prologue = true) {
+                          bool prologue = true, const LinvPlan* linv_p = nullptr) {
   Symbolic& S = sv->S;
   cudaStream_t st = sv->stream;
   DevSym& D = sv->DS;
@@ -502,9 +573,25 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       }
     }
   }
-  if (sv->n_binv_pairs > 0 && sv->DV.binv != nullptr) {   // (in sharded runs: after each phase, for the fronts done so far)
-    // inverses of the 64x64 diagonal blocks of the big fronts for the triangular solves (all blocks in parallel)
-    k_big_blockinv<<<sv->n_binv_pairs, 64, 2 * 64 * 65 * sizeof(double), st>>>(D, N, sv->d_binv_pairs.p, sv->d_binv_off.p, sv->d_binv.p); ++L;
+  {
+    int rc = enqueue_linv(sv, linv_p ? *linv_p : sv->linv_plan);
+    if (rc != B200LDLT_SUCCESS) return rc;
+  }
+  CU(cudaGetLastError());
+  return B200LDLT_SUCCESS;
+}
+
+// explicit inverses of the pivot blocks of the big fronts in LP (after their numeric factorisation): level 0 for all
+// 64x64 diagonal blocks in one launch, then two tile-GEMM launches per doubling level (all fronts and pairs batched)
+static int enqueue_linv(Solver* sv, const LinvPlan& LP) {
+  if (LP.ndiag <= 0) return B200LDLT_SUCCESS;
+  cudaStream_t st = sv->stream;
+  int& L = sv->launches;
+  k_linv_diag<<<LP.ndiag, 64, 0, st>>>(sv->DS, sv->DN, LP.d_diag.p, sv->d_linv_off.p, sv->d_linv.p); ++L;
+  for (size_t l = 0; l < LP.ng.size(); ++l) {
+    if (LP.ng[l] <= 0) continue;
+    k_linv_gemm<1><<<LP.ng[l], 256, 0, st>>>(sv->DS, sv->DN, LP.d_g[l]->p, sv->d_linv_off.p, sv->d_linv.p); ++L;
+    k_linv_gemm<2><<<LP.ng[l], 256, 0, st>>>(sv->DS, sv->DN, LP.d_g2[l]->p, sv->d_linv_off.p, sv->d_linv.p); ++L;
   }
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;
@@ -667,6 +754,7 @@ static int shard_setup(Solver* sv, int rank, int world) {
     std::vector<SolveTask> tf, tb;
     build_level_plans(S, sv->opt.smem_front_max, take[ph], fl, H.plan[ph]);
     build_solve_tasks(S, take[ph], tf, tb, bundle);
+    { int rc2 = build_linv_plan(sv, S, take[ph], H.linv_plan[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
     if (fl.empty()) fl.push_back(0);
     if (bundle.empty()) bundle.push_back(0);
     if (tf.empty()) tf.push_back({ST_SMALL, 0, 0, 0});
@@ -929,7 +1017,7 @@ int b200ldlt_shard_factor(b200ldlt_handle h, int phase, int from_host) {
     if (from_host) CU(cudaMemcpyAsync(sv->d_vals.p, sv->h_vals, sv->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
     sv->have_dev_vals = true;
   }
-  return enqueue_factor(sv, &sv->shard.plan[phase], sv->shard.d_fl[phase].p, phase == 0);
+  return enqueue_factor(sv, &sv->shard.plan[phase], sv->shard.d_fl[phase].p, phase == 0, &sv->shard.linv_plan[phase]);
 }
 
 /* counters_total: CNT_N ints already summed over the ranks (all-reduce of device_ptr("counters")) */

@@ -75,7 +75,7 @@ __global__ void k_fill(int n, double* x, double v) {
 
 // --------------------------------------------------------------------------------------------
 // pivoted LDL^T of a dense symmetric front held in shared memory (full square storage).
-//   F   : f x f, leading dimension ld, both triangles valid on entry
+//   F   : f x f, leading dimension ld, LOWER triangle valid on entry (the strictly upper part is never read)
 //   k   : number of fully-summed (pivot) columns, candidates are rows/cols [0,k)
 //   lp  : k ints, out: pivot position t holds original local column lp[t]
 //   pt  : k ints, out: pivot type (1, 2, 3)
@@ -99,6 +99,14 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// warp-wide max of non-negative floats in ONE instruction (CREDUX.MAX.F32, sm_100a).  The pivot SEARCH runs on
+// float-rounded magnitudes (the tests are inequalities with slack >= 1e-8, the selected entries are then re-read exactly).
+__device__ __forceinline__ float wredux_max(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+
 // The pivoted front factorisation runs either on a whole CTA (WARP=false, __syncthreads) or on a single
 // warp (WARP=true, __syncwarp; several fronts per CTA).
 template <bool WARP>
@@ -106,16 +114,19 @@ __device__ __forceinline__ void gsync() { if (WARP) __syncwarp(); else __syncthr
 
 template <bool WARP>
 __device__ void swap_sym(double* F, int ld, int f, int p, int q) {
-  // symmetric interchange of rows/cols p and q of the full square; caller syncs before.
+  // symmetric interchange of rows/cols p < q of a matrix whose LOWER triangle is stored (the strictly upper part
+  // of F is never read); one pass, index t handled by one thread; caller syncs before.
   const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nt = WARP ? 32 : blockDim.x;
+  if (p > q) { const int x = p; p = q; q = x; }
   for (int t = tid; t < f; t += nt) {
-    double a = F[p + t * ld], b = F[q + t * ld];
-    F[p + t * ld] = b; F[q + t * ld] = a;
-  }
-  gsync<WARP>();
-  for (int t = tid; t < f; t += nt) {
-    double a = F[t + p * ld], b = F[t + q * ld];
-    F[t + p * ld] = b; F[t + q * ld] = a;
+    double* u; double* v;
+    if (t < p) { u = F + p + t * ld; v = F + q + t * ld; }             // row segments left of p
+    else if (t == p) { u = F + p + p * ld; v = F + q + q * ld; }       // the two diagonal entries
+    else if (t < q) { u = F + t + p * ld; v = F + q + t * ld; }        // column p below p  <->  row q between p and q
+    else if (t == q) continue;                                         // F[q][p] stays
+    else { u = F + t + p * ld; v = F + t + q * ld; }                   // column segments below q
+    const double a = *u, b = *v;
+    *u = b; *v = a;
   }
   gsync<WARP>();
 }
@@ -145,7 +156,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         // column is rounding noise (scaled matrix, entries O(1)) the matrix is numerically singular.
         double cm = 0.0;
         for (int i = j + lane; i < f; i += 32) cm = fmax(cm, fabs(F[i + j * ld]));
-        cm = warp_max(cm);
+        cm = (double)wredux_max(__double2float_ru(cm));
         type = 1; r = j;
         if (lane == 0) sh[2] = !(cm > 1e-12);
       } else {
@@ -156,8 +167,18 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
           if (i < kend) { if (v > lam) { lam = v; ridx = i; } }
           else gam = fmax(gam, v);
         }
-        warp_argmax(lam, ridx);
-        gam = warp_max(gam);
+        {
+          // one-instruction float reductions; the winning lane's exact (lam, ridx) pair is then broadcast
+          const float lamf = (ridx >= 0) ? __double2float_ru(lam) : -1.0f;
+          const float lmax = wredux_max(lamf);
+          gam = (double)wredux_max(__double2float_ru(gam));
+          const unsigned bal = __ballot_sync(0xffffffffu, ridx >= 0 && lamf == lmax);
+          if (bal) {
+            const int src = __ffs(bal) - 1;
+            lam = __shfl_sync(0xffffffffu, lam, src);
+            ridx = __shfl_sync(0xffffffffu, ridx, src);
+          } else { lam = 0.0; ridx = -1; }
+        }
         double ajj = fabs(F[j + j * ld]);
         bool ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
         if (lam == 0.0 || ridx < 0) { if (ok1) { type = 1; r = j; } }
@@ -171,7 +192,8 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
             if (m < kend) sig = fmax(sig, v); else gamr = fmax(gamr, v);
             if (m != j) { cr = fmax(cr, v); cj = fmax(cj, fabs(F[m + j * ld])); }
           }
-          sig = warp_max(sig); gamr = warp_max(gamr); cj = warp_max(cj); cr = warp_max(cr);
+          sig = (double)wredux_max(__double2float_ru(sig)); gamr = (double)wredux_max(__double2float_ru(gamr));
+          cj = (double)wredux_max(__double2float_ru(cj)); cr = (double)wredux_max(__double2float_ru(cr));
           double arr = fabs(F[r + r * ld]);
           if (ok1 && ajj * sig >= BK_ALPHA * lam * lam) { type = 1; r = j; }
           else if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, gamr)) { type = 2; }
@@ -221,14 +243,15 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         }
       }
       const double dv = d;
+      const double rdv = 1.0 / dv;
       gsync<WARP>();
       for (int i = j + 1 + tid; i < f; i += nt) {
         double c = F[i + j * ld];
         cv1[i] = c;
-        F[i + j * ld] = c / dv;
+        F[i + j * ld] = c * rdv;
       }
       if (tid == 0) {
-        pt[j] = 1; dinv[j] = 1.0 / dv; doff[j] = 0.0; ptype_g[j] = 1;
+        pt[j] = 1; dinv[j] = rdv; doff[j] = 0.0; ptype_g[j] = 1;
         if (dv < 0.0) ++c_neg;
       }
       gsync<WARP>();
@@ -236,7 +259,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       for (int i = j + 1 + lane; i < f; i += 32) {
         const double li = F[i + j * ld];
         int m = j + 1 + warp;
-        for (; m + 3 * nwarp < f; m += 4 * nwarp) {
+        for (; m + 3 * nwarp <= i; m += 4 * nwarp) {   // lower triangle only: columns m <= i
           const double c0 = cv1[m], c1 = cv1[m + nwarp], c2 = cv1[m + 2 * nwarp], c3 = cv1[m + 3 * nwarp];
           double* q0 = F + i + m * ld;
           double* q1 = q0 + nwarp * ld;
@@ -245,7 +268,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
           const double f0 = *q0, f1 = *q1, f2 = *q2, f3 = *q3;
           *q0 = fma(-li, c0, f0); *q1 = fma(-li, c1, f1); *q2 = fma(-li, c2, f2); *q3 = fma(-li, c3, f3);
         }
-        for (; m < f; m += nwarp) F[i + m * ld] = fma(-li, cv1[m], F[i + m * ld]);
+        for (; m <= i; m += nwarp) F[i + m * ld] = fma(-li, cv1[m], F[i + m * ld]);
       }
       gsync<WARP>();
       j += 1;
@@ -253,16 +276,17 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       // ---------------- 2x2 pivot at (j, j+1) ----------------
       const double a = F[j + j * ld], b = F[j + 1 + j * ld], c = F[j + 1 + (j + 1) * ld];
       const double det = a * c - b * b;
+      const double idet = 1.0 / det;
       gsync<WARP>();
       for (int i = j + 2 + tid; i < f; i += nt) {
         double c1 = F[i + j * ld], c2 = F[i + (j + 1) * ld];
         cv1[i] = c1; cv2[i] = c2;
-        F[i + j * ld] = (c * c1 - b * c2) / det;
-        F[i + (j + 1) * ld] = (a * c2 - b * c1) / det;
+        F[i + j * ld] = (c * c1 - b * c2) * idet;
+        F[i + (j + 1) * ld] = (a * c2 - b * c1) * idet;
       }
       if (tid == 0) {
         pt[j] = 2; pt[j + 1] = 3; ptype_g[j] = 2; ptype_g[j + 1] = 3;
-        dinv[j] = c / det; dinv[j + 1] = a / det; doff[j] = -b / det; doff[j + 1] = 0.0;
+        dinv[j] = c * idet; dinv[j + 1] = a * idet; doff[j] = -b * idet; doff[j + 1] = 0.0;
         ++c_2x2;
         if (det < 0.0) c_neg += 1; else if (a < 0.0) c_neg += 2;
       }
@@ -270,7 +294,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       for (int i = j + 2 + lane; i < f; i += 32) {
         const double l1 = F[i + j * ld], l2 = F[i + (j + 1) * ld];
         int m = j + 2 + warp;
-        for (; m + 3 * nwarp < f; m += 4 * nwarp) {
+        for (; m + 3 * nwarp <= i; m += 4 * nwarp) {
           const double a0 = cv1[m], a1 = cv1[m + nwarp], a2 = cv1[m + 2 * nwarp], a3 = cv1[m + 3 * nwarp];
           const double b0 = cv2[m], b1 = cv2[m + nwarp], b2 = cv2[m + 2 * nwarp], b3 = cv2[m + 3 * nwarp];
           double* q0 = F + i + m * ld;
@@ -281,7 +305,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
           *q0 = fma(-l2, b0, fma(-l1, a0, f0)); *q1 = fma(-l2, b1, fma(-l1, a1, f1));
           *q2 = fma(-l2, b2, fma(-l1, a2, f2)); *q3 = fma(-l2, b3, fma(-l1, a3, f3));
         }
-        for (; m < f; m += nwarp) F[i + m * ld] = fma(-l2, cv2[m], fma(-l1, cv1[m], F[i + m * ld]));
+        for (; m <= i; m += nwarp) F[i + m * ld] = fma(-l2, cv2[m], fma(-l1, cv1[m], F[i + m * ld]));
       }
       gsync<WARP>();
       j += 2;
@@ -316,14 +340,6 @@ __device__ __forceinline__ void wred_max_idx(double& v, int& idx) {
     int oi = __shfl_xor_sync(0xffffffffu, idx, o);
     if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
   }
-}
-
-// warp-wide max of non-negative floats in ONE instruction (CREDUX.MAX.F32, sm_100a).  The pivot SEARCH runs on
-// float-rounded magnitudes (the tests are inequalities with slack >= 1e-8, the selected entries are then re-read exactly).
-__device__ __forceinline__ float wredux_max(float v) {
-  float m;
-  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
-  return m;
 }
 
 __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const double u, const double tiny,
@@ -530,9 +546,7 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
   for (long long uu = S.uent_ptr[s] + tid; uu < S.uent_ptr[s + 1]; uu += nt) {
     unsigned d = S.u_dst[uu];
     int lr = d & 0xffffu, lc = d >> 16;
-    double v = N.uval[uu];
-    F[lr + lc * ld] = v;
-    F[lc + lr * ld] = v;
+    F[lr + lc * ld] = N.uval[uu];   // lower triangle only (lr >= lc)
   }
   gsync<WARP>();
   // extend-add of the children contribution blocks, one child at a time (deterministic)
@@ -545,9 +559,7 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
       const int lj = rl[jj];
       for (int ii = jj + (tid & 31); ii < rc; ii += 32) {
         const int li = rl[ii];
-        const double v = cb[ii + (size_t)jj * rc];
-        F[li + lj * ld] += v;
-        if (li != lj) F[lj + li * ld] += v;
+        F[li + lj * ld] += cb[ii + (size_t)jj * rc];   // rel is increasing: li >= lj
       }
     }
     gsync<WARP>();
@@ -1219,19 +1231,86 @@ __global__ void __launch_bounds__(256) k_big_schur_dmma(DevSym S, DevNum N, cons
       }
 }
 
-// trailing update of the remaining pivot columns after panel jb
+// trailing update of the remaining pivot columns after panel jb: C -= L_panel * W_panel^T (rank NB), 64x64 tiles.
+// One k-step (the whole rank-32 slab of both operands in shared memory); the C tile is prefetched before the
+// contraction so its latency overlaps the FMAs.  Skips the next diagonal block (k_big_trsm's CTA 0 updates it) and
+// records the column maxima of the panel AFTER next below its diagonal block (reduced per warp: one atomic per
+// column and warp instead of one per entry).
 __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
+  __shared__ double As[NB][TM + 1];
+  __shared__ double Bs[NB][TM + 1];
   const int s = front_list[blockIdx.z];
-  const int k = S.sn_start[s + 1] - S.sn_start[s];
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   if (jb + NB >= k) return;
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const int o = jb + NB;
   const int M = f - o, Nn = k - o;
-  if ((int)blockIdx.x * TM >= M || (int)blockIdx.y * TM >= Nn) return;
-  double* P = N.L + S.L_off[s];
-  const double* Wp = N.W + S.L_off[s];
-  tile_syrk(P + o + (long long)o * f, f, P + o + (long long)jb * f, Wp + o + (long long)jb * f, f, M, Nn,
-            NB, blockIdx.x, blockIdx.y, N.colmax + S.sn_start[s] + o);
+  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TM;
+  if (i0 >= M || j0 >= Nn || i0 + TM - 1 < j0) return;
+  const long long ld = f;
+  double* __restrict__ C = N.L + S.L_off[s] + o + (long long)o * ld;
+  const double* __restrict__ A = N.L + S.L_off[s] + o + (long long)jb * ld;
+  const double* __restrict__ Bm = N.W + S.L_off[s] + o + (long long)jb * ld;
+  double* colmax_next = N.colmax + c0 + o;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  {
+    double av[8], bv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tid + 256 * q, ii = t & (TM - 1), kk = t / TM;
+      av[q] = (i0 + ii < M) ? A[i0 + ii + (long long)kk * ld] : 0.0;
+      bv[q] = (j0 + ii < Nn) ? Bm[j0 + ii + (long long)kk * ld] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tid + 256 * q, ii = t & (TM - 1), kk = t / TM;
+      As[kk][ii] = av[q]; Bs[kk][ii] = bv[q];
+    }
+  }
+  double c[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int gi = i0 + tx + 16 * q, gj = j0 + ty + 16 * p;
+      c[q][p] = (gi < M && gj < Nn && gi >= gj) ? C[gi + (long long)gj * ld] : 0.0;
+    }
+  __syncthreads();
+#pragma unroll 8
+  for (int kk = 0; kk < NB; ++kk) {
+    double a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { a[q] = As[kk][tx + 16 * q]; b[q] = Bs[kk][ty + 16 * q]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) c[q][p] = fma(-a[q], b[p], c[q][p]);
+  }
+  const int lane = tid & 31;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int gj = j0 + ty + 16 * p;
+    float m = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int gi = i0 + tx + 16 * q;
+      if (gi < M && gj < Nn && gi >= gj) {
+        if (gi < min(NB, Nn) && gj < NB) continue;   // next diagonal block: updated by k_big_trsm (a partial last panel has < 32 columns)
+        C[gi + (long long)gj * ld] = c[q][p];
+        if (gi >= 2 * NB) m = fmaxf(m, __double2float_ru(fabs(c[q][p])));
+      }
+    }
+    // columns [NB, 2NB) of the trailing matrix are the panel AFTER next: the next panel's chain kernels run
+    // concurrently with this update, so they use the maxima recorded one panel earlier.
+    if (j0 == 0 && p >= 2) {   // (warp-uniform) columns 32..63 of the first tile column
+      const float m_lo = wredux_max((lane < 16) ? m : 0.0f), m_hi = wredux_max((lane >= 16) ? m : 0.0f);
+      if ((lane == 0 || lane == 16) && gj < Nn) {
+        const float mm = (lane == 0) ? m_lo : m_hi;
+        if (mm > 0.0f)
+          atomicMax(reinterpret_cast<unsigned long long*>(colmax_next + gj), (unsigned long long)__double_as_longlong((double)mm));
+      }
+    }
+  }
 }
 
 // Schur complement: CB -= L21 * (L21 D)^T  (the dense contraction of the front)

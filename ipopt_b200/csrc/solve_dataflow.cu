@@ -41,8 +41,8 @@ struct DevSolve {
   double* bigv;                // assembled+permuted rhs of big fronts
   double* bigy;                // y / x blocks of big fronts in pivoted order
   unsigned long long* ticket;  // [0] fwd, [1] bwd (monotonic)
-  const double* binv;          // per (big front, 64-block): Ext[64x64] (rows x pivot cols: [L_dd^-1 ; -L_cd L_dd^-1]) then L_dd^-T-friendly transpose
-  const long long* binv_off;   // nsn : offset of a big front's first block in binv (8192 doubles per block), -1 = none
+  const double* linv;          // explicit inverses of the big fronts' pivot blocks L11 (K64 x K64 each, see k_linv_*)
+  const long long* linv_off;   // nsn : offset of a big front's inverse in linv, -1 = none
   unsigned long long* tlog;    // optional (debug): 2 timestamps per task, fwd then bwd; nullptr = off
 };
 
@@ -389,193 +389,140 @@ __device__ void big_gather(const DevSym& S, const DevNum& N, const DevSolve& V, 
   if (tid == 0) { st_release(V.gflag + s, epoch); }
 }
 
-// forward block row b of big front s: rows [64b, min(f, 64b+64))
-// smem: ys[64] | part[4*64] | Lsq[64*65]
-__device__ void big_fwd_block(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
-                              double* sm, double* __restrict__ x, double* __restrict__ cbv) {
+// Big fronts use the EXPLICIT inverse of their unit-lower-triangular pivot block L11 (k_linv_* below, computed once
+// per factorisation): the in-front recurrences  y = L11^-1 w  and  x = L11^-T t  become block GEMVs whose 64-row /
+// 64-column blocks are independent tasks -- no chain of nkb dependent steps per front.  Linv is stored K64 x K64
+// (K64 = 64*ceil(k/64), column-major, zero-padded, upper block triangle never read).
+#define DF_STAGE 8192      // doubles of the shared staging area (vectors are staged in chunks of this many rows)
+
+__device__ __forceinline__ void wait_flags(const int* flags, int first, int last, int epoch) {
+  // flags[first..last) all equal to epoch (one flag per thread, in parallel), then a CTA barrier
+  for (int c = first + (int)threadIdx.x; c < last; c += blockDim.x) wait_eq(flags + c, epoch);
+  __syncthreads();
+}
+
+// forward, pivot block b (rows [64b, 64b+64) of the pivoted front): y_b = sum_{c<=b} Linv[b,c] w_c
+// smem: stage[DF_STAGE] | part[256] | ys[64]
+__device__ void big_fwd_piv(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
+                            double* sm, double* __restrict__ x) {
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]), f = k + r;
-  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31, warp = tid >> 5;
-  double* ys = sm;
-  double* part = sm + 64;
-  double* Lsq = sm + 64 + 256;
-  const int r0 = b * DF_BLK, nrow = min(DF_BLK, f - r0);
-  const int ncolblk_left = min(b, (k + DF_BLK - 1) / DF_BLK);   // column blocks strictly left of the diagonal block
-  const double* __restrict__ P = N.L + S.L_off[s];
-  const int* bf = V.bflag_f + V.boff[s];
-  const double* yb = V.bigy + V.bigv_off[s];
-  double acc = 0.0;
-  const int row = r0 + tx;
-  // everything that does not depend on the y blocks is fetched first: the diagonal block and (after the gather
-  // flag, which is long set by the time the left blocks arrive) this block's slice of the assembled rhs
-  const int ndiag = max(0, min(k - r0, DF_BLK));
-  if (ndiag > 0) {
-    for (int t = tid; t < nrow * ndiag; t += blockDim.x) {
-      int i = t % nrow, q = t / nrow;
-      Lsq[i + q * 65] = P[(r0 + i) + (size_t)(r0 + q) * f];
-    }
-  }
+  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int nkb = (k + DF_BLK - 1) / DF_BLK;
+  const long long K64 = (long long)nkb * DF_BLK;
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  double* stage = sm;
+  double* part = sm + DF_STAGE;
+  double* ys = part + 256;
+  const int t0 = b * DF_BLK, nrow = min(DF_BLK, k - t0);
+  const double* __restrict__ Li = V.linv + V.linv_off[s] + (t0 + tx);
+  const double* __restrict__ w = V.bigv + V.bigv_off[s];
+  // first tile in flight before the gather flag is seen (Linv does not depend on the right-hand side)
+  double ltn[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)(ty + 4 * q) * K64];
   if (tid == 0) wait_eq(V.gflag + s, epoch);
   __syncthreads();
-  double wmine = 0.0;
-  if (tid < nrow) wmine = __ldcg(V.bigv + V.bigv_off[s] + r0 + tid);
-  // precomputed inverse of the diagonal block (k_big_blockinv): the in-block substitution becomes a 64x64 GEMV
-  const bool use_inv = (V.binv != nullptr) && V.binv_off[s] >= 0 && ndiag > 0;
-  double ext[16];
-  if (use_inv) {
-    const double* __restrict__ E = V.binv + V.binv_off[s] + (size_t)b * 8192;
+  double acc = 0.0;
+  const int ntile = b + 1;
+  for (int base = 0; base < ntile; base += DF_STAGE / DF_BLK) {
+    const int lim = min(ntile, base + DF_STAGE / DF_BLK);
+    __syncthreads();
+    for (int i = base * DF_BLK + tid; i < lim * DF_BLK; i += blockDim.x) stage[i - base * DF_BLK] = (i < k) ? __ldcg(w + i) : 0.0;
+    __syncthreads();
+    for (int c = base; c < lim; ++c) {
+      double lt[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) ext[q] = E[tx + (ty + 4 * q) * 64];
-  }
-  // software pipeline: the L tile of column block c+1 is in flight while block c is consumed
-  double ltn[16];
-  if (ncolblk_left > 0) {
-    const int nc0 = min(DF_BLK, k);
-    const double* base = P + row;
+      for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+      if (c + 1 < ntile) {
+        const double* nx = Li + (long long)(c + 1) * DF_BLK * K64;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nrow && t < nc0) ? base[(size_t)t * f] : 0.0; }
-  }
-  for (int c = 0; c < ncolblk_left; ++c) {
-    const int t0 = c * DF_BLK, ncol = min(DF_BLK, k - t0);
-    double lt[16];
+        for (int q = 0; q < 16; ++q) ltn[q] = nx[(long long)(ty + 4 * q) * K64];
+      }
+      const double* wc = stage + (c - base) * DF_BLK + ty;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-    if (c + 1 < ncolblk_left) {
-      const int t0n = t0 + DF_BLK, ncn = min(DF_BLK, k - t0n);
-      const double* base = P + row + (size_t)t0n * f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nrow && t < ncn) ? base[(size_t)t * f] : 0.0; }
+      for (int q = 0; q < 16; ++q) acc = fma(lt[q], wc[4 * q], acc);
     }
-    if (tid == 0) wait_eq(bf + c, epoch);
-    __syncthreads();
-    if (tid < ncol) ys[tid] = __ldcg(yb + t0 + tid);
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; if (t < ncol) acc = fma(lt[q], ys[t], acc); }
-    __syncthreads();
   }
   part[ty * 64 + tx] = acc;
   __syncthreads();
-  if (tid < 64) ys[tid] = (tid < nrow) ? wmine - (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]) : 0.0;
-  __syncthreads();
-  if (use_inv) {
-    double p2 = 0.0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; if (t < ndiag) p2 = fma(ext[q], ys[t], p2); }
-    __syncthreads();                       // everyone has read ys
-    part[ty * 64 + tx] = p2;
-    __syncthreads();
-    if (tid < 64) {
-      const double g = part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid];
-      const double mine = ys[tid];
-      __syncwarp();
-      ys[tid] = (tid < ndiag) ? g : mine + g;   // pivot rows: y = L_dd^-1 v ; contribution rows of the block: v - L_cd y
-    }
-  } else if (warp == 0) {
-    double v0 = ys[lane], v1 = ys[lane + 32];
-#pragma unroll 8
-    for (int t = 0; t < ndiag; ++t) {
-      const double yt = (t < 32) ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
-      if (lane > t) v0 = fma(-Lsq[lane + t * 65], yt, v0);
-      if (lane + 32 > t) v1 = fma(-Lsq[lane + 32 + t * 65], yt, v1);
-    }
-    ys[lane] = v0; ys[lane + 32] = v1;
-  }
+  if (tid < 64) ys[tid] = (tid < nrow) ? part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid] : 0.0;
   __syncthreads();
   if (tid < nrow) {
-    const int i = r0 + tid;
-    if (i < k) {
-      V.bigy[V.bigv_off[s] + i] = ys[tid];   // y block for the rows below (pivoted order)
-      const int ty2 = N.ptype[c0 + i];
-      double y;
-      if (ty2 == 1) y = ys[tid] * N.dinv[c0 + i];
-      else if (ty2 == 2) y = ys[tid] * N.dinv[c0 + i] + ys[tid + 1] * N.doff[c0 + i];
-      else y = ys[tid - 1] * N.doff[c0 + i - 1] + ys[tid] * N.dinv[c0 + i];
-      x[c0 + i] = y;
-    } else cbv[S.rows_ptr[s] + (i - k)] = ys[tid];
+    const int i = t0 + tid;
+    V.bigy[V.bigv_off[s] + i] = ys[tid];   // y block for the contribution rows (pivoted order)
+    const int ty2 = N.ptype[c0 + i];
+    double y;
+    if (ty2 == 1) y = ys[tid] * N.dinv[c0 + i];
+    else if (ty2 == 2) y = ys[tid] * N.dinv[c0 + i] + ys[tid + 1] * N.doff[c0 + i];
+    else y = ys[tid - 1] * N.doff[c0 + i - 1] + ys[tid] * N.dinv[c0 + i];
+    x[c0 + i] = y;
   }
   __syncthreads();
   if (tid == 0) {
-    if (r0 < k) st_release((int*)bf + b, epoch);
-    const int nblk = (f + DF_BLK - 1) / DF_BLK;
+    st_release(V.bflag_f + V.boff[s] + b, epoch);
+    const int nblk = nkb + (f - k + DF_BLK - 1) / DF_BLK;
     const int old = atomicAdd(V.bcnt + s, 1);
     if ((old + 1) % nblk == 0) { st_release(V.done_f + s, epoch); }
   }
 }
 
-// backward block column b of big front s: columns [64b, min(k, 64b+64))
-// smem: xs[64] | red[DF_THREADS*16 -> done with shuffles] ...
-__device__ void big_bwd_block(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
-                              double* sm, double* __restrict__ x) {
+// forward, contribution rows [k + 64j, ...): update vector = w - L21[rows, :] y
+__device__ void big_fwd_cb(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int j, int epoch,
+                           double* sm, double* __restrict__ cbv) {
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const long long ro = S.rows_ptr[s];
-  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
-  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31, warp = tid >> 5;
-  double* xs = sm;                 // 64
-  double* colacc = sm + 64;        // 64
-  double* red = sm + 128;          // 8 warps x 16
-  double* Lsq = sm + 128 + 128;    // 64 x 65
-  const int t0 = b * DF_BLK, ncol = min(DF_BLK, k - t0), t1 = t0 + ncol;
+  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const int nkb = (k + DF_BLK - 1) / DF_BLK;
-  const double* __restrict__ P = N.L + S.L_off[s];
-  const int* bf = V.bflag_b + V.boff[s];
-  double pacc[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
-  // stage the diagonal block first (independent of everything we wait for)
-  for (int t = tid; t < ncol * ncol; t += blockDim.x) {
-    int i = t % ncol, q = t / ncol;
-    Lsq[i + q * 65] = P[(t0 + i) + (size_t)(t0 + q) * f];
-  }
-  const int par = S.sn_parent[s];
-  if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
-  __syncthreads();
-  // rows below the block are processed in chunks of 64: first the contribution-block rows (ancestors'
-  // final values), then this front's later pivot blocks from the last one down as they get published.
-  const int nchunk_cb = (r + DF_BLK - 1) / DF_BLK;
-  const int nchunk = nchunk_cb + (nkb - 1 - b);
-  // chunk geometry: first the contribution-block rows, then the later pivot blocks from the last one down
-  auto chunk_geom = [&](int ch, int& rbase, int& nr, int& c) {
-    if (ch < nchunk_cb) { c = -1; rbase = k + ch * DF_BLK; nr = min(DF_BLK, f - rbase); }
-    else { c = nkb - 1 - (ch - nchunk_cb); rbase = c * DF_BLK; nr = min(DF_BLK, k - rbase); }
-  };
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  double* stage = sm;
+  double* part = sm + DF_STAGE;
+  const int rbase = k + j * DF_BLK, nr = min(DF_BLK, f - rbase);
+  const double* __restrict__ P = N.L + S.L_off[s] + (rbase + tx);
+  const double* __restrict__ yb = V.bigy + V.bigv_off[s];
   double ltn[16];
-  if (nchunk > 0) {
-    int rbase, nr, c;
-    chunk_geom(0, rbase, nr, c);
-    const double* base = P + (rbase + tx) + (size_t)t0 * f;
+  {
+    const int nc0 = min(DF_BLK, k);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncol) ? base[(size_t)t * f] : 0.0; }
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < nc0) ? P[(size_t)t * f] : 0.0; }
   }
-  for (int ch = 0; ch < nchunk; ++ch) {
-    int rbase, nr, c;
-    chunk_geom(ch, rbase, nr, c);
-    double lt[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-    if (ch + 1 < nchunk) {   // next tile in flight while this chunk is consumed (it does not depend on x)
-      int rb2, nr2, c2;
-      chunk_geom(ch + 1, rb2, nr2, c2);
-      const double* base = P + (rb2 + tx) + (size_t)t0 * f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
-    }
-    if (c < 0) {
-      if (tid < nr) xs[tid] = __ldcg(x + S.rows[ro + (rbase - k) + tid]);
-    } else {
-      if (tid == 0) wait_eq(bf + c, epoch);
-      __syncthreads();
-      if (tid < nr) xs[tid] = __ldcg(V.bigy + V.bigv_off[s] + rbase + tid);
-    }
+  if (tid == 0) wait_eq(V.gflag + s, epoch);
+  __syncthreads();
+  const double wmine = (tid < nr) ? __ldcg(V.bigv + V.bigv_off[s] + rbase + tid) : 0.0;
+  wait_flags(V.bflag_f + V.boff[s], 0, nkb, epoch);
+  double acc = 0.0;
+  for (int base = 0; base < nkb; base += DF_STAGE / DF_BLK) {
+    const int lim = min(nkb, base + DF_STAGE / DF_BLK);
     __syncthreads();
-    if (tx < nr) {
-      const double xi = xs[tx];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], xi, pacc[q]);
-    }
+    for (int i = base * DF_BLK + tid; i < lim * DF_BLK; i += blockDim.x) stage[i - base * DF_BLK] = (i < k) ? __ldcg(yb + i) : 0.0;
     __syncthreads();
+    for (int c = base; c < lim; ++c) {
+      double lt[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+      if (c + 1 < nkb) {
+        const int t0n = (c + 1) * DF_BLK, ncn = min(DF_BLK, k - t0n);
+        const double* nx = P + (size_t)t0n * f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncn) ? nx[(size_t)t * f] : 0.0; }
+      }
+      const double* yc = stage + (c - base) * DF_BLK + ty;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc = fma(lt[q], yc[4 * q], acc);
+    }
   }
-  // reduce pacc over the 64 row-threads of each ty group: warp shuffle then across the two half-warps
+  part[ty * 64 + tx] = acc;
+  __syncthreads();
+  if (tid < nr) cbv[S.rows_ptr[s] + (rbase - k) + tid] = wmine - (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]);
+  __syncthreads();
+  if (tid == 0) {
+    const int nblk = nkb + (f - k + DF_BLK - 1) / DF_BLK;
+    const int old = atomicAdd(V.bcnt + s, 1);
+    if ((old + 1) % nblk == 0) { st_release(V.done_f + s, epoch); }
+  }
+}
+
+// sum the per-thread partials pacc[q] (column t = ty + 4q, row lane tx) over the 64 row lanes -> colacc[64] (smem)
+__device__ __forceinline__ void reduce_cols(double (&pacc)[16], double* red, double* colacc) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     double a = pacc[q];
@@ -590,98 +537,231 @@ __device__ void big_bwd_block(const DevSym& S, const DevNum& N, const DevSolve& 
     colacc[tid] = red[(2 * tyc) * 16 + q] + red[(2 * tyc + 1) * 16 + q];
   }
   __syncthreads();
-  const bool use_inv = (V.binv != nullptr) && V.binv_off[s] >= 0;
-  if (use_inv) {
-    // z_t = sum_{i >= t} Linv[i,t] * rhs_i  with the transposed copy (coalesced over t)
-    const double* __restrict__ ET = V.binv + V.binv_off[s] + (size_t)b * 8192 + 4096;
-    if (tid < 64) xs[tid] = (tid < ncol) ? x[c0 + t0 + tid] - colacc[tid] : 0.0;
-    __syncthreads();
-    double p2 = 0.0;
+}
+
+// backward phase 1, column block b: t_b = z_b - L21[:, b]^T x(contribution rows)   (no dependence on other blocks)
+// smem: stage[DF_STAGE] | red[128] | colacc[64]
+__device__ void big_bwd_t(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
+                          double* sm, const double* __restrict__ x) {
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const long long ro = S.rows_ptr[s];
+  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  double* stage = sm;
+  double* red = sm + DF_STAGE;
+  double* colacc = red + 128;
+  const int t0 = b * DF_BLK, ncol = min(DF_BLK, k - t0);
+  const double* __restrict__ P = N.L + S.L_off[s] + (size_t)t0 * f;
+  const int nchunk = (r + DF_BLK - 1) / DF_BLK;
+  double pacc[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) { const int i = ty + 4 * q; if (i < ncol) p2 = fma(ET[tx + i * 64], xs[i], p2); }
-    __syncthreads();
-    red[0] = 0.0;   // (red is free again)
-    double* part2 = Lsq;   // 256 doubles of scratch
-    part2[ty * 64 + tx] = p2;
-    __syncthreads();
-    if (tid < 64) xs[tid] = part2[tid] + part2[64 + tid] + part2[128 + tid] + part2[192 + tid];
-  } else if (warp == 0) {
-    double z0 = (lane < ncol) ? x[c0 + t0 + lane] - colacc[lane] : 0.0;
-    double z1 = (lane + 32 < ncol) ? x[c0 + t0 + lane + 32] - colacc[lane + 32] : 0.0;
-#pragma unroll 8
-    for (int q = ncol - 1; q >= 0; --q) {
-      const double zq = (q < 32) ? __shfl_sync(0xffffffffu, z0, q) : __shfl_sync(0xffffffffu, z1, q - 32);
-      if (lane < q) z0 = fma(-Lsq[q + lane * 65], zq, z0);
-      if (lane + 32 < q) z1 = fma(-Lsq[q + (lane + 32) * 65], zq, z1);
-    }
-    xs[lane] = z0; xs[lane + 32] = z1;
+  for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
+  double ltn[16];
+  if (nchunk > 0) {
+    const int nr = min(DF_BLK, r);
+    const double* base = P + (k + tx);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncol) ? base[(size_t)t * f] : 0.0; }
   }
+  const int par = S.sn_parent[s];
+  if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
   __syncthreads();
-  if (tid < ncol) {
-    V.bigy[V.bigv_off[s] + t0 + tid] = xs[tid];                 // pivoted order, for the blocks to the left
-    x[c0 + N.lperm[c0 + t0 + tid]] = xs[tid];                   // final value (permutation is panel-local)
+  for (int cb = 0; cb < nchunk; cb += DF_STAGE / DF_BLK) {
+    const int lim = min(nchunk, cb + DF_STAGE / DF_BLK);
+    __syncthreads();
+    for (int i = cb * DF_BLK + tid; i < lim * DF_BLK; i += blockDim.x) stage[i - cb * DF_BLK] = (i < r) ? __ldcg(x + S.rows[ro + i]) : 0.0;
+    __syncthreads();
+    for (int ch = cb; ch < lim; ++ch) {
+      double lt[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+      if (ch + 1 < nchunk) {
+        const int rb2 = k + (ch + 1) * DF_BLK, nr2 = min(DF_BLK, f - rb2);
+        const double* base = P + (rb2 + tx);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
+      }
+      const double xi = stage[(ch - cb) * DF_BLK + tx];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], xi, pacc[q]);
+    }
   }
+  reduce_cols(pacc, red, colacc);
+  if (tid < ncol) V.bigv[V.bigv_off[s] + t0 + tid] = x[c0 + t0 + tid] - colacc[tid];
+  __syncthreads();
+  if (tid == 0) st_release(V.bflag_b + V.boff[s] + b, epoch);
+}
+
+// backward phase 2, column block b: x_b = sum_{c>=b} Linv[c,b]^T t_c
+__device__ void big_bwd_x(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
+                          double* sm, double* __restrict__ x) {
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int nkb = (k + DF_BLK - 1) / DF_BLK;
+  const long long K64 = (long long)nkb * DF_BLK;
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  double* stage = sm;
+  double* red = sm + DF_STAGE;
+  double* colacc = red + 128;
+  const int t0 = b * DF_BLK, ncol = min(DF_BLK, k - t0);
+  const double* __restrict__ Li = V.linv + V.linv_off[s] + (long long)t0 * K64 + tx;
+  const double* __restrict__ tv = V.bigv + V.bigv_off[s];
+  double pacc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
+  double ltn[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)b * DF_BLK + (long long)(ty + 4 * q) * K64];
+  wait_flags(V.bflag_b + V.boff[s], b, nkb, epoch);
+  for (int cb = b; cb < nkb; cb += DF_STAGE / DF_BLK) {
+    const int lim = min(nkb, cb + DF_STAGE / DF_BLK);
+    __syncthreads();
+    for (int i = cb * DF_BLK + tid; i < lim * DF_BLK; i += blockDim.x) stage[i - cb * DF_BLK] = (i < k) ? __ldcg(tv + i) : 0.0;
+    __syncthreads();
+    for (int c = cb; c < lim; ++c) {
+      double lt[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+      if (c + 1 < nkb) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)(c + 1) * DF_BLK + (long long)(ty + 4 * q) * K64];
+      }
+      const double ti = stage[(c - cb) * DF_BLK + tx];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], ti, pacc[q]);
+    }
+  }
+  reduce_cols(pacc, red, colacc);
+  if (tid < ncol) x[c0 + N.lperm[c0 + t0 + tid]] = colacc[tid];   // final value (the permutation is panel-local)
   __syncthreads();
   if (tid == 0) {
-    st_release((int*)bf + b, epoch);
     const int old = atomicAdd(V.bcnt_b + s, 1);
     if ((old + 1) % nkb == 0) { st_release(V.done_b + s, epoch); }
   }
-  (void)t1;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Inverses of the 64x64 diagonal blocks of the big fronts' L11 (run once per factorisation, all blocks in parallel):
-//   Ext (64 x 64, ld 64): rows = rows of block b of the front, cols = its pivot columns:
-//        pivot rows      : L_dd^-1               (unit lower triangular)
-//        rows below k    : -L_cd * L_dd^-1       (contribution rows that share the block with the last pivots)
-//   ET  (64 x 64, ld 64): ET[t + i*64] = L_dd^-1[i][t]   (transposed copy for the backward sweep)
-// One CTA of 64 threads per (front, block); list = pairs (front, block).
+// Explicit inverse of the pivot block L11 of the big fronts, once per factorisation, by recursive doubling:
+//   level 0 : the 64x64 diagonal blocks (k_linv_diag: one thread per column, the column in registers);
+//   level l : [A 0; B C]^-1 = [A^-1 0; -C^-1 B A^-1  C^-1] for all pairs of neighbouring blocks of 64*2^(l-1)
+//             columns, as two batched 64x64-tile GEMM passes (k_linv_gemm<1>: T = B A^-1 into the W scratch of the
+//             factorisation, k_linv_gemm<2>: -C^-1 T into Linv).  Work items are enumerated on the host at analysis.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_big_blockinv(DevSym S, DevNum N, const int* __restrict__ pairs,
-                                                     const long long* __restrict__ binv_off, double* __restrict__ binv) {
-  extern __shared__ double binv_sm[];
-  double* Ls = binv_sm;
-  double* Xs = binv_sm + 64 * 65;
+struct LinvItem { int s, ib, jb, m0, m1; };   // front, tile row / column (64-blocks), k-range of tiles [m0, m1)
+
+#define LI_LD 66
+__global__ void __launch_bounds__(64) k_linv_diag(DevSym S, DevNum N, const int* __restrict__ pairs,
+                                                  const long long* __restrict__ linv_off, double* __restrict__ linv) {
+  __shared__ __align__(16) double Ls[64 * LI_LD];
   const int s = pairs[2 * blockIdx.x], b = pairs[2 * blockIdx.x + 1];
   const int k = S.sn_start[s + 1] - S.sn_start[s];
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-  const int r0 = b * 64, nrow = min(64, f - r0), nd = min(64, k - r0);
+  const long long K64 = (long long)((k + 63) / 64) * 64;
+  const int r0 = b * 64, nd = min(64, k - r0);
   const double* __restrict__ P = N.L + S.L_off[s];
-  double* __restrict__ E = binv + binv_off[s] + (size_t)b * 8192;
   const int tid = threadIdx.x;
   for (int t = tid; t < 64 * 64; t += 64) {
     const int i = t & 63, q = t >> 6;
-    Ls[i + q * 65] = (i < nrow && q < nd) ? P[(r0 + i) + (size_t)(r0 + q) * f] : 0.0;
-    Xs[i + q * 65] = 0.0;
+    Ls[i + q * LI_LD] = (i < nd && q < nd && i > q) ? P[(r0 + i) + (size_t)(r0 + q) * f] : 0.0;
   }
   __syncthreads();
-  // thread j computes column j of X = L_dd^-1 by forward substitution (unit diagonal)
-  if (tid < nd) {
-    const int j = tid;
-    Xs[j + j * 65] = 1.0;
-    for (int i = j + 1; i < nd; ++i) {
-      double acc = 0.0;
-      for (int t = j; t < i; ++t) acc = fma(Ls[i + t * 65], Xs[t + j * 65], acc);
-      Xs[i + j * 65] = -acc;
+  // thread j: column j of X = L_dd^-1 by forward substitution on e_j, right-looking (independent FMAs per step)
+  double xc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) xc[i] = (i == tid) ? 1.0 : 0.0;
+#pragma unroll
+  for (int t = 0; t < 63; ++t) {
+    const double xt = xc[t];
+    const double* __restrict__ col = Ls + t * LI_LD;
+    if (((t + 1) & 1) != 0) xc[t + 1] = fma(-xt, col[t + 1], xc[t + 1]);
+#pragma unroll
+    for (int q = (t + 2) & ~1; q < 64; q += 2) {
+      const double2 l2 = *reinterpret_cast<const double2*>(col + q);
+      xc[q] = fma(-xt, l2.x, xc[q]);
+      xc[q + 1] = fma(-xt, l2.y, xc[q + 1]);
     }
   }
   __syncthreads();
-  // rows of the block below the pivots: -L_cd * X
-  if (tid >= nd && tid < nrow) {
-    const int i = tid;
-    for (int j = 0; j < nd; ++j) {
-      double acc = 0.0;
-      for (int t = j; t < nd; ++t) acc = fma(Ls[i + t * 65], Xs[t + j * 65], acc);
-      Xs[i + j * 65] = -acc;
-    }
-  }
+#pragma unroll
+  for (int i = 0; i < 64; ++i) Ls[i + tid * LI_LD] = (i < nd && tid < nd) ? xc[i] : 0.0;
   __syncthreads();
+  double* __restrict__ E = linv + linv_off[s] + r0 + (long long)r0 * K64;
   for (int t = tid; t < 64 * 64; t += 64) {
     const int i = t & 63, q = t >> 6;
-    E[i + q * 64] = Xs[i + q * 65];
-    E[4096 + i + q * 64] = (i < nd && q < nd) ? Xs[q + i * 65] : 0.0;   // ET[t=i + row q*64] = X[q][i]
+    E[i + (long long)q * K64] = Ls[i + q * LI_LD];
   }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(256) k_linv_gemm(DevSym S, DevNum N, const LinvItem* __restrict__ items,
+                                                   const long long* __restrict__ linv_off, double* __restrict__ linv) {
+  __shared__ double As[16][65];
+  __shared__ double Bs[16][65];
+  const LinvItem it = items[blockIdx.x];
+  const int s = it.s;
+  const int k = S.sn_start[s + 1] - S.sn_start[s];
+  const long long f = k + (S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const long long K64 = (long long)((k + 63) / 64) * 64;
+  double* __restrict__ Li = linv + linv_off[s];
+  const double* __restrict__ Lp = N.L + S.L_off[s];
+  double* __restrict__ Wp = N.W + S.L_off[s];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = it.ib * 64, j0 = it.jb * 64;
+  // loaders: A element (row i0+ai, col kk0+ak) with ai = t & 63, ak = t >> 6 (+4 per step); B element (row kk0+bk,
+  // col j0+bj) with bk = t & 15, bj = t >> 4 (+16 per step)
+  auto ldA = [&](int kk0, double (&v)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ai = tid & 63, ak = (tid >> 6) + 4 * q;
+      const long long row = i0 + ai, col = kk0 + ak;
+      if (PHASE == 1) v[q] = (row < k && col < k) ? Lp[row + col * f] : 0.0;
+      else v[q] = Li[row + col * K64];
+    }
+  };
+  auto ldB = [&](int kk0, double (&v)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int bk = tid & 15, bj = (tid >> 4) + 16 * q;
+      const long long row = kk0 + bk, col = j0 + bj;
+      if (PHASE == 1) v[q] = Li[row + col * K64];
+      else v[q] = (row < k && col < k) ? Wp[row + col * f] : 0.0;
+    }
+  };
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+  const int kbeg = it.m0 * 64, kend = it.m1 * 64;
+  double av[4], bv[4];
+  ldA(kbeg, av); ldB(kbeg, bv);
+  for (int kk0 = kbeg; kk0 < kend; kk0 += 16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      As[(tid >> 6) + 4 * q][tid & 63] = av[q];
+      Bs[tid & 15][(tid >> 4) + 16 * q] = bv[q];
+    }
+    __syncthreads();
+    if (kk0 + 16 < kend) { ldA(kk0 + 16, av); ldB(kk0 + 16, bv); }
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double a[4], c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = As[kk][tx + 16 * q]; c[q] = Bs[kk][ty + 16 * q]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[q][p] = fma(a[q], c[p], acc[q][p]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const long long row = i0 + tx + 16 * q, col = j0 + ty + 16 * p;
+      if (PHASE == 1) { if (row < k && col < k) Wp[row + col * f] = acc[q][p]; }
+      else Li[row + col * K64] = -acc[q][p];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -716,7 +796,8 @@ __global__ void __launch_bounds__(DF_THREADS) k_solve_dataflow(DevSym S, DevNum 
     } else if (T.type == ST_BIG_GATHER) {
       big_gather(S, N, V, T.a, epoch, x, cbv);
     } else {
-      if (FWD) big_fwd_block(S, N, V, T.a, T.b, epoch, sm, x, cbv); else big_bwd_block(S, N, V, T.a, T.b, epoch, sm, x);
+      if (FWD) { if (T.c == 0) big_fwd_piv(S, N, V, T.a, T.b, epoch, sm, x); else big_fwd_cb(S, N, V, T.a, T.b, epoch, sm, cbv); }
+      else { if (T.c == 0) big_bwd_t(S, N, V, T.a, T.b, epoch, sm, x); else big_bwd_x(S, N, V, T.a, T.b, epoch, sm, x); }
     }
     __syncthreads();
     if (V.tlog && threadIdx.x == 0) {
