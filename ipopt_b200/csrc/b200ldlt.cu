@@ -67,10 +67,11 @@ struct Solver {
   int dev = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;      // bulk (trsm / trailing update) stream of the big-front pipeline
+  cudaStream_t stream3 = nullptr;      // contribution-block updates of the big fronts (trail behind the chain)
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   bool own_stream = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_zero = nullptr;
 
   int n = 0, nnz = 0;
   std::vector<int> irn, jcn;
@@ -91,7 +92,8 @@ struct Solver {
   DevBuf<long long> d_rows_ptr, d_uent_ptr, d_u_dst64, d_L_off, d_cb_off, d_useg_ptr;
   DevBuf<unsigned> d_u_dst;
   DevBuf<double> d_vals, d_uval, d_L, d_W, d_CB, d_dinv, d_doff, d_scale, d_x, d_cbv, d_rhs, d_res, d_colmax;
-  DevBuf<int> d_ptype, d_lperm, d_bperm, d_counters;
+  DevBuf<int> d_ptype, d_lperm, d_bperm, d_counters, d_einv;
+  DevBuf<long long> d_einv_off;
   DevBuf<unsigned long long> d_rmax;
   DevSym DS;
   DevNum DN;
@@ -135,7 +137,24 @@ struct Solver {
     if (fgraph) cudaGraphDestroy(fgraph);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (stream2) cudaStreamDestroy(stream2);
+    if (stream3) cudaStreamDestroy(stream3);
     if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+  // debug (B200_FACTOR_SECTIONS=1 with use_graph=0): timed section marks of the last factorisation
+  std::vector<std::pair<std::string, cudaEvent_t>> sect;
+  void mark(const char* label, int level) {
+    if (!getenv("B200_FACTOR_SECTIONS") || opt.use_graph != 0) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream);
+    sect.emplace_back(std::string(label) + " L" + std::to_string(level), e);
+  }
+  void dump_sections() {
+    if (sect.empty()) return;
+    for (size_t i = 1; i < sect.size(); ++i) {
+      float ms = 0; cudaEventElapsedTime(&ms, sect[i - 1].second, sect[i].second);
+      fprintf(stderr, "[sections] %-18s %8.1f us\n", sect[i].first.c_str(), ms * 1e3);
+    }
+    for (auto& pr : sect) cudaEventDestroy(pr.second);
+    sect.clear();
   }
   cudaEvent_t next_event() {
     if (ev_next == ev_pool.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ev_pool.push_back(e); }
@@ -366,6 +385,25 @@ static int run_analysis(Solver* sv, const double* vals) {
   N.dinv = sv->d_dinv.p; N.doff = sv->d_doff.p; N.ptype = sv->d_ptype.p;
   N.lperm = sv->d_lperm.p; N.bperm = sv->d_bperm.p; N.counters = sv->d_counters.p; N.colmax = sv->d_colmax.p;
 
+  // inverse row maps of the children of the (factorisation-)big fronts, for the one-launch extend-add
+  {
+    std::vector<long long> eoff(S.nsn, -1);
+    long long tot = 0;
+    for (int c = 0; c < S.nsn; ++c) {
+      const int p = S.sn_parent[c];
+      if (p >= 0 && S.f(p) > sv->opt.smem_front_max) { eoff[c] = tot; tot += S.f(p); }
+    }
+    std::vector<int> einv((size_t)std::max<long long>(tot, 1), -1);
+    for (int c = 0; c < S.nsn; ++c) if (eoff[c] >= 0) {
+      const long long ro = S.rows_ptr[c];
+      const int rc = S.r(c);
+      for (int j = 0; j < rc; ++j) einv[(size_t)(eoff[c] + S.rel[ro + j])] = j;
+    }
+    CU(sv->d_einv_off.upload(eoff, st));
+    CU(sv->d_einv.upload(einv, st));
+    D.einv_off = sv->d_einv_off.p; D.einv = sv->d_einv.p;
+  }
+
   // ---- launch plan: per level, big fronts first then small ones by descending order --------
   std::vector<int> fl;
   {
@@ -510,16 +548,39 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
     k_apply_scale<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_u_row.p, sv->d_u_col.p, sv->d_scale.p, sv->d_uval.p); ++L;
   }
   }  // prologue
+  // storage of all big fronts of this plan is cleared up front on the bulk stream (overlaps the leaf levels)
+  bool any_big = false;
+  for (int l = 0; l < S.nlevels; ++l) any_big = any_big || plan[l].big_cnt > 0;
+  if (any_big) {
+    cudaStream_t sz = getenv("B200_ONE_STREAM") ? st : sv->stream2;
+    cudaEvent_t e0 = sv->next_event();
+    CU(cudaEventRecord(e0, st));
+    CU(cudaStreamWaitEvent(sz, e0, 0));
+    for (int l = 0; l < S.nlevels; ++l) {
+      const LevelPlan& P = plan[l];
+      if (!P.big_cnt) continue;
+      k_big_zero<<<dim3(std::min<unsigned>(cdiv(P.big_zero_max, 1024), 592), P.big_cnt), 256, 0, sz>>>(D, N, fl + P.big_off); ++L;
+    }
+    sv->ev_zero = sv->next_event();
+    CU(cudaEventRecord(sv->ev_zero, sz));
+  }
+  bool zero_waited = false;
+  sv->mark("prologue", -1);
   for (int l = 0; l < S.nlevels; ++l) {
     const LevelPlan& P = plan[l];
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
-      k_big_zero<<<dim3(std::min<unsigned>(cdiv(P.big_zero_max, 1024), 592), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
+      if (!zero_waited) { CU(cudaStreamWaitEvent(st, sv->ev_zero, 0)); zero_waited = true; }
       k_big_assemble<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_entmax, 256), 64)), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
-      for (int q = 0; q < P.big_chmax; ++q) {
-        k_big_extend_add<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_fmax, 8), 128)), P.big_cnt), 256, 0, st>>>(D, N, bl, q); ++L;
+      if (getenv("B200_EXTEND_PER_CHILD")) {
+        for (int q = 0; q < P.big_chmax; ++q) {
+          k_big_extend_add<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_fmax, 8), 128)), P.big_cnt), 256, 0, st>>>(D, N, bl, q); ++L;
+        }
+      } else if (P.big_chmax > 0) {
+        k_big_extend_all<<<dim3(cdiv(P.big_fmax, 8), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
       }
     }
+    if (P.big_cnt) sv->mark("big-assemble", l);
     for (const auto& bk : P.small) {
       if (bk.fmax <= 32) {  // one warp per front (registers), 4 fronts per CTA
         k_front_warp<<<cdiv(bk.cnt, 4), 128, 4 * XS_SMEM_PER_WARP, st>>>(D, N, fl + bk.off, bk.cnt); ++L;
@@ -529,6 +590,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, st>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
       }
     }
+    sv->mark("small-fronts", l);
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
       k_big_colmax0<<<dim3(P.big_cnt, 8), 256, 0, st>>>(D, N, bl); ++L;
@@ -536,6 +598,15 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       // is the critical path; the trailing update of panel p runs on the bulk stream concurrently with diag(p+1),
       // which applies panel p's rank-32 update to its own 32x32 block itself.
       cudaStream_t sb = getenv("B200_ONE_STREAM") ? st : sv->stream2;
+      // opt-in (B200_SCHUR_FUSED=1): per-panel rank-32 updates of the contribution block on a third stream instead of
+      // one Schur GEMM per level; measured equal within noise at N=400 (7.61 vs 7.57 ms), so the single GEMM stays default
+      const bool fused_cb = getenv("B200_SCHUR_FUSED") && atoi(getenv("B200_SCHUR_FUSED")) != 0;
+      cudaStream_t sc = getenv("B200_ONE_STREAM") ? st : sv->stream3;
+      if (fused_cb) {
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, st));
+        CU(cudaStreamWaitEvent(sc, e, 0));
+      }
       {
         cudaEvent_t e = sv->next_event();
         CU(cudaEventRecord(e, st));
@@ -553,8 +624,14 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaEventRecord(et, sb));
         CU(cudaStreamWaitEvent(st, et, 0));      // diag(p+1) needs L/W of its own rows from trsm(p)
         int rem_k = P.big_kmax - jb - NB;
+        if (fused_cb && P.big_rmax > 0) {
+          // the panel's rank-nb update of the contribution block runs on a third stream: it only needs trsm(p) and
+          // the previous CB update, so it trails behind the chain instead of a Schur GEMM at the end of the level
+          CU(cudaStreamWaitEvent(sc, et, 0));
+          k_big_update<<<dim3(cdiv(P.big_rmax, TM) + 1, cdiv(P.big_rmax, TM) + 1, P.big_cnt), 256, 0, sc>>>(D, N, bl, jb, 2); ++L;
+        }
         if (rem_k > 0) {
-          k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, sb>>>(D, N, bl, jb); ++L;
+          k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, sb>>>(D, N, bl, jb, 0); ++L;
         }
       }
       {
@@ -562,7 +639,13 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaEventRecord(e, sb));
         CU(cudaStreamWaitEvent(st, e, 0));
       }
-      if (P.big_rmax > 0) {
+      if (fused_cb) {
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, sc));
+        CU(cudaStreamWaitEvent(st, e, 0));
+      }
+      sv->mark("big-chain", l);
+      if (P.big_rmax > 0 && !fused_cb) {
         if (!getenv("B200_SCHUR_DMMA")) {
           k_big_schur<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
         } else {   // FP64 tensor-pipe (DMMA) contraction, 128x128 tiles: opt-in - measured 2-3 % SLOWER than the 64x64
@@ -573,10 +656,12 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       }
     }
   }
+  sv->mark("big-schur(last)", S.nlevels);
   {
     int rc = enqueue_linv(sv, linv_p ? *linv_p : sv->linv_plan);
     if (rc != B200LDLT_SUCCESS) return rc;
   }
+  sv->mark("linv", S.nlevels);
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;
 }
@@ -604,6 +689,7 @@ static int finish_factor(Solver* sv, int check_inertia, int expected_neg, int* n
   CU(cudaStreamSynchronize(st));
   float ms = 0;
   cudaEventElapsedTime(&ms, sv->ev0, sv->ev1);
+  sv->dump_sections();
   b200ldlt_info& I = sv->info;
   I.ms_factor_gpu = ms;
   I.launches_factor = sv->launches;
@@ -836,6 +922,7 @@ b200ldlt_handle b200ldlt_create(const b200ldlt_options* opt) {
   if (sv->opt.stream) sv->stream = (cudaStream_t)sv->opt.stream;
   else { cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking); sv->own_stream = true; }
   cudaStreamCreateWithFlags(&sv->stream2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&sv->stream3, cudaStreamNonBlocking);
   cudaEventCreate(&sv->ev0);
   cudaEventCreate(&sv->ev1);
   cudaHostAlloc((void**)&sv->h_counters, CNT_N * sizeof(int), cudaHostAllocDefault);

@@ -138,7 +138,8 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
   const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nt = WARP ? 32 : blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   for (int t = tid; t < k; t += nt) lp[t] = t;
-  if (tid == 0) sh[2] = 0;
+  if (tid == 0) { sh[2] = 0; sh[6] = 0; }
+  int par = 0;   // decisions alternate between sh[0..2] and sh[4..6]: no barrier needed before the next one is written
   int c_neg = 0, c_forced = 0, c_tiny = 0, c_2x2 = 0;  // only meaningful on thread 0
   int j = 0, kend = k, progress = 0;
   bool forced = false;
@@ -158,7 +159,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
         for (int i = j + lane; i < f; i += 32) cm = fmax(cm, fabs(F[i + j * ld]));
         cm = (double)wredux_max(__double2float_ru(cm));
         type = 1; r = j;
-        if (lane == 0) sh[2] = !(cm > 1e-12);
+        if (lane == 0) sh[4 * par + 2] = !(cm > 1e-12);
       } else {
         double lam = 0.0, gam = 0.0;
         int ridx = -1;
@@ -206,11 +207,11 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
           }
         }
       }
-      if (lane == 0) { sh[0] = type; sh[1] = r; }
+      if (lane == 0) { sh[4 * par] = type; sh[4 * par + 1] = r; }
     }
     gsync<WARP>();
-    const int type = sh[0], r = sh[1], noise = sh[2];
-    gsync<WARP>();  // everyone has read sh before it is rewritten
+    const int type = sh[4 * par], r = sh[4 * par + 1], noise = sh[4 * par + 2];
+    par ^= 1;
     if (type == 0) {  // reject for now: park column j at the end of the candidate range
       if (j != kend - 1) {
         swap_sym<WARP>(F, ld, f, j, kend - 1);
@@ -244,7 +245,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       }
       const double dv = d;
       const double rdv = 1.0 / dv;
-      gsync<WARP>();
+      if (forced) gsync<WARP>();   // (the static-pivot branch above read the column that is rescaled below)
       for (int i = j + 1 + tid; i < f; i += nt) {
         double c = F[i + j * ld];
         cv1[i] = c;
@@ -276,8 +277,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       // ---------------- 2x2 pivot at (j, j+1) ----------------
       const double a = F[j + j * ld], b = F[j + 1 + j * ld], c = F[j + 1 + (j + 1) * ld];
       const double det = a * c - b * b;
-      const double idet = 1.0 / det;
-      gsync<WARP>();
+      const double idet = 1.0 / det;   // (a, b, c are not touched by the loop below: no barrier needed)
       for (int i = j + 2 + tid; i < f; i += nt) {
         double c1 = F[i + j * ld], c2 = F[i + (j + 1) * ld];
         cv1[i] = c1; cv2[i] = c2;
@@ -886,6 +886,45 @@ __global__ void k_big_extend_add(DevSym S, DevNum N, const int* __restrict__ fro
   }
 }
 
+// extend-add of ALL children of every big front in the list in one launch: each WARP owns one column of the parent
+// front and applies the children one after the other (fixed order => deterministic, no atomics; no two warps touch
+// the same parent entry).  The child column that lands in the warp's parent column comes from the inverse row map
+// einv built at analysis; per-child metadata is fetched lane-parallel (one child per lane) and broadcast.
+__global__ void __launch_bounds__(256) k_big_extend_all(DevSym S, DevNum N, const int* __restrict__ front_list) {
+  const int p = front_list[blockIdx.y];
+  const int kp = S.sn_start[p + 1] - S.sn_start[p];
+  const int rp = (int)(S.rows_ptr[p + 1] - S.rows_ptr[p]);
+  const int fp = kp + rp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lj = blockIdx.x * 8 + warp;
+  if (lj >= fp) return;
+  // destination column indexed by the parent row li >= lj
+  double* __restrict__ dst = (lj < kp) ? N.L + S.L_off[p] + (size_t)lj * fp
+                                       : N.CB + S.cb_off[p] + (size_t)(lj - kp) * rp - kp;
+  const int ch0 = S.child_ptr[p], nch = S.child_ptr[p + 1] - ch0;
+  for (int q0 = 0; q0 < nch; q0 += 32) {
+    int jj = -1, rc = 0;
+    long long ro = 0, co = 0;
+    if (q0 + lane < nch) {
+      const int c = S.child_idx[ch0 + q0 + lane];
+      ro = S.rows_ptr[c];
+      rc = (int)(S.rows_ptr[c + 1] - ro);
+      co = S.cb_off[c];
+      jj = S.einv[S.einv_off[c] + lj];
+    }
+    unsigned has = __ballot_sync(0xffffffffu, jj >= 0);
+    while (has) {
+      const int src = __ffs(has) - 1;
+      has &= has - 1;
+      const int jq = __shfl_sync(0xffffffffu, jj, src), rq = __shfl_sync(0xffffffffu, rc, src);
+      const long long roq = __shfl_sync(0xffffffffu, ro, src), coq = __shfl_sync(0xffffffffu, co, src);
+      const double* __restrict__ cbcol = N.CB + coq + (size_t)jq * rq;
+      const int* __restrict__ rl = S.rel + roq;
+      for (int ii = jq + lane; ii < rq; ii += 32) dst[rl[ii]] += cbcol[ii];
+    }
+  }
+}
+
 // column maxima of the first panel below its diagonal block (later panels get theirs from k_big_update)
 __global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_list) {
   const int s = front_list[blockIdx.x];
@@ -1236,19 +1275,30 @@ __global__ void __launch_bounds__(256) k_big_schur_dmma(DevSym S, DevNum N, cons
 // contraction so its latency overlaps the FMAs.  Skips the next diagonal block (k_big_trsm's CTA 0 updates it) and
 // records the column maxima of the panel AFTER next below its diagonal block (reduced per warp: one atomic per
 // column and warp instead of one per entry).
-__global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
+// with_cb != 0: the same launch also applies the panel's rank-nb update to the contribution block (columns >= k of the
+// trailing matrix live in N.CB), so the Schur complement is complete when the last panel is done and rides in the
+// shadow of the diag/trsm chain instead of a separate GEMM at the end of the level.
+__global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
+                                                    int with_cb) {
   __shared__ double As[NB][TM + 1];
   __shared__ double Bs[NB][TM + 1];
   const int s = front_list[blockIdx.z];
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  if (jb + NB >= k) return;
-  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-  const int o = jb + NB;
-  const int M = f - o, Nn = k - o;
-  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TM;
+  if (jb >= k) return;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int f = k + r;
+  const int nb = min(NB, k - jb);
+  const int o = jb + nb;
+  const int M = f - o, Nk = k - o;            // trailing rows; remaining pivot columns (0 after the last panel)
+  const int Nn = with_cb ? M : Nk;            // columns covered by this launch
+  // with_cb == 2: contribution-block columns only (tile grid anchored at the 64-aligned column below k)
+  const int jbase = (with_cb == 2) ? (Nk / TM) * TM : 0;
+  const int i0 = jbase + blockIdx.x * TM, j0 = jbase + blockIdx.y * TM;
   if (i0 >= M || j0 >= Nn || i0 + TM - 1 < j0) return;
+  const int jlo = (with_cb == 2) ? Nk : 0;    // first column this launch owns
   const long long ld = f;
   double* __restrict__ C = N.L + S.L_off[s] + o + (long long)o * ld;
+  double* __restrict__ CBp = N.CB + S.cb_off[s];
   const double* __restrict__ A = N.L + S.L_off[s] + o + (long long)jb * ld;
   const double* __restrict__ Bm = N.W + S.L_off[s] + o + (long long)jb * ld;
   double* colmax_next = N.colmax + c0 + o;
@@ -1258,8 +1308,8 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int t = tid + 256 * q, ii = t & (TM - 1), kk = t / TM;
-      av[q] = (i0 + ii < M) ? A[i0 + ii + (long long)kk * ld] : 0.0;
-      bv[q] = (j0 + ii < Nn) ? Bm[j0 + ii + (long long)kk * ld] : 0.0;
+      av[q] = (i0 + ii < M && kk < nb) ? A[i0 + ii + (long long)kk * ld] : 0.0;
+      bv[q] = (j0 + ii < Nn && kk < nb) ? Bm[j0 + ii + (long long)kk * ld] : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -1273,7 +1323,9 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int gi = i0 + tx + 16 * q, gj = j0 + ty + 16 * p;
-      c[q][p] = (gi < M && gj < Nn && gi >= gj) ? C[gi + (long long)gj * ld] : 0.0;
+      double v = 0.0;
+      if (gi < M && gj < Nn && gi >= gj && gj >= jlo) v = (gj < Nk) ? C[gi + (long long)gj * ld] : CBp[(gi - Nk) + (long long)(gj - Nk) * r];
+      c[q][p] = v;
     }
   __syncthreads();
 #pragma unroll 8
@@ -1294,17 +1346,18 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int gi = i0 + tx + 16 * q;
-      if (gi < M && gj < Nn && gi >= gj) {
-        if (gi < min(NB, Nn) && gj < NB) continue;   // next diagonal block: updated by k_big_trsm (a partial last panel has < 32 columns)
-        C[gi + (long long)gj * ld] = c[q][p];
+      if (gi < M && gj < Nn && gi >= gj && gj >= jlo) {
+        if (gi < min(NB, Nk) && gj < NB) continue;   // next diagonal block: updated by k_big_trsm (a partial last panel has < 32 columns)
+        if (gj < Nk) C[gi + (long long)gj * ld] = c[q][p];
+        else CBp[(gi - Nk) + (long long)(gj - Nk) * r] = c[q][p];
         if (gi >= 2 * NB) m = fmaxf(m, __double2float_ru(fabs(c[q][p])));
       }
     }
     // columns [NB, 2NB) of the trailing matrix are the panel AFTER next: the next panel's chain kernels run
     // concurrently with this update, so they use the maxima recorded one panel earlier.
-    if (j0 == 0 && p >= 2) {   // (warp-uniform) columns 32..63 of the first tile column
+    if (j0 == 0 && p >= 2 && with_cb != 2) {   // (warp-uniform) columns 32..63 of the first tile column
       const float m_lo = wredux_max((lane < 16) ? m : 0.0f), m_hi = wredux_max((lane >= 16) ? m : 0.0f);
-      if ((lane == 0 || lane == 16) && gj < Nn) {
+      if ((lane == 0 || lane == 16) && gj < Nk) {
         const float mm = (lane == 0) ? m_lo : m_hi;
         if (mm > 0.0f)
           atomicMax(reinterpret_cast<unsigned long long*>(colmax_next + gj), (unsigned long long)__double_as_longlong((double)mm));

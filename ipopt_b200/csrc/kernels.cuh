@@ -21,6 +21,10 @@ struct DevSym {
   const long long* u_dst64;    // lrow + lcol*f
   const long long* L_off;      // nsn+1
   const long long* cb_off;     // nsn+1
+  // children of the big fronts: inverse of rel -- einv[einv_off[c] + j] = index of parent-front row j in child c's
+  // row list, or -1 (einv_off[c] = -1 if c's parent is not a big front)
+  const long long* einv_off;   // nsn
+  const int* einv;
 };
 
 struct DevNum {
