@@ -481,6 +481,7 @@ static int run_analysis(Solver* sv, const double* vals) {
     V.linv = sv->d_linv.p;
     V.linv_off = sv->d_linv_off.p;
     V.tlog = nullptr;
+    V.opts = getenv("B200_GATHER_GLOBAL") ? 1 : 0;
     if (getenv("B200_SOLVE_TIMELINE")) {
       CU(sv->d_tlog.alloc(2 * (tf.size() + tb.size())));
       V.tlog = sv->d_tlog.p;
@@ -646,7 +647,9 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       }
       sv->mark("big-chain", l);
       if (P.big_rmax > 0 && !fused_cb) {
-        if (!getenv("B200_SCHUR_DMMA")) {
+        if (!getenv("B200_SCHUR_44") && !getenv("B200_SCHUR_DMMA")) {   // default: 8x4 register-blocked DFMA tiles
+          k_big_schur84<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 128, 0, st>>>(D, N, bl); ++L;
+        } else if (!getenv("B200_SCHUR_DMMA")) {
           k_big_schur<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
         } else {   // FP64 tensor-pipe (DMMA) contraction, 128x128 tiles: opt-in - measured 2-3 % SLOWER than the 64x64
                    // DFMA tiles at these front sizes (r <= ~1500: too few 128x128 tiles to fill 148 SMs; B200's FP64
@@ -675,8 +678,8 @@ static int enqueue_linv(Solver* sv, const LinvPlan& LP) {
   k_linv_diag<<<LP.ndiag, 64, 0, st>>>(sv->DS, sv->DN, LP.d_diag.p, sv->d_linv_off.p, sv->d_linv.p); ++L;
   for (size_t l = 0; l < LP.ng.size(); ++l) {
     if (LP.ng[l] <= 0) continue;
-    k_linv_gemm<1><<<LP.ng[l], 256, 0, st>>>(sv->DS, sv->DN, LP.d_g[l]->p, sv->d_linv_off.p, sv->d_linv.p); ++L;
-    k_linv_gemm<2><<<LP.ng[l], 256, 0, st>>>(sv->DS, sv->DN, LP.d_g2[l]->p, sv->d_linv_off.p, sv->d_linv.p); ++L;
+    k_linv_gemm<1><<<LP.ng[l], 128, 0, st>>>(sv->DS, sv->DN, LP.d_g[l]->p, sv->d_linv_off.p, sv->d_linv.p); ++L;
+    k_linv_gemm<2><<<LP.ng[l], 128, 0, st>>>(sv->DS, sv->DN, LP.d_g2[l]->p, sv->d_linv_off.p, sv->d_linv.p); ++L;
   }
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;

@@ -1379,4 +1379,66 @@ __global__ void __launch_bounds__(256) k_big_schur(DevSym S, DevNum N, const int
   tile_syrk(C, r, P + k, Wp + k, f, r, r, k, blockIdx.x, blockIdx.y);
 }
 
+// --------------------------------------------------------------------------------------------
+// Schur complement with 8x4 register blocking: 64x64 tile per CTA of 128 threads (thread = rows tx+8q, columns
+// ty+16p), 12 shared-memory loads per 32 FMAs (the 4x4 version needs 8 per 16 and is shared-memory bound),
+// next k-slab prefetched into registers while the current one is consumed.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_big_schur84(DevSym S, DevNum N, const int* __restrict__ front_list) {
+  __shared__ double As[TK][TM + 1];
+  __shared__ double Bs[TK][TM + 1];
+  const int s = front_list[blockIdx.z];
+  const int k = S.sn_start[s + 1] - S.sn_start[s];
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const long long f = k + r;
+  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TM;
+  if (i0 >= r || j0 >= r || i0 + TM - 1 < j0) return;
+  double* __restrict__ C = N.CB + S.cb_off[s];
+  const double* __restrict__ A = N.L + S.L_off[s] + k;
+  const double* __restrict__ Bm = N.W + S.L_off[s] + k;
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int li = tid & 63, lk = tid >> 6;   // loader: element (row li, k-index lk + 2q)
+  double acc[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  double av[8], bv[8];
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const long long gk = k0 + lk + 2 * q;
+      av[q] = (i0 + li < r && gk < k) ? A[i0 + li + gk * f] : 0.0;
+      bv[q] = (j0 + li < r && gk < k) ? Bm[j0 + li + gk * f] : 0.0;
+    }
+  };
+  load(0);
+  for (int k0 = 0; k0 < k; k0 += TK) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { As[lk + 2 * q][li] = av[q]; Bs[lk + 2 * q][li] = bv[q]; }
+    __syncthreads();
+    if (k0 + TK < k) load(k0 + TK);
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      double a[8], b[4];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = As[kk][tx + 8 * q];
+#pragma unroll
+      for (int p2 = 0; p2 < 4; ++p2) b[p2] = Bs[kk][ty + 16 * p2];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) acc[q][p2] = fma(a[q], b[p2], acc[q][p2]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int p2 = 0; p2 < 4; ++p2) {
+      const int gi = i0 + tx + 8 * q, gj = j0 + ty + 16 * p2;
+      if (gi < r && gj < r && gi >= gj) C[gi + (long long)gj * r] -= acc[q][p2];
+    }
+}
+
 }  // namespace b200

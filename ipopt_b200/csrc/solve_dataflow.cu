@@ -44,6 +44,7 @@ struct DevSolve {
   const double* linv;          // explicit inverses of the big fronts' pivot blocks L11 (K64 x K64 each, see k_linv_*)
   const long long* linv_off;   // nsn : offset of a big front's inverse in linv, -1 = none
   unsigned long long* tlog;    // optional (debug): 2 timestamps per task, fwd then bwd; nullptr = off
+  int opts;                    // bit 0: gather through global memory (debug / comparison)
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -362,8 +363,8 @@ __device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
 // ------------------------------------------------------------------------------------------------
 // big fronts: gather task + one task per 64-row block (forward) / 64-column block (backward)
 // ------------------------------------------------------------------------------------------------
-__device__ void big_gather(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch,
-                           const double* __restrict__ x, const double* __restrict__ cbv) {
+__device__ void big_gather_global(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch,
+                                  const double* __restrict__ x, const double* __restrict__ cbv) {
   // w = [x(cols) ; 0] + scatter(children update vectors), then the in-front pivot permutation; result in bigv.
   // Children write disjoint... no: two children may hit the same parent row, so children are applied one
   // after the other (deterministic), each child fully parallel.
@@ -389,12 +390,66 @@ __device__ void big_gather(const DevSym& S, const DevNum& N, const DevSolve& V, 
   if (tid == 0) { st_release(V.gflag + s, epoch); }
 }
 
+#define DF_STAGE 8192      // doubles of the shared staging area (vectors are staged in chunks of this many rows)
+#define DF_GATHER_MAXCH 256
+
+// Same result as big_gather_global with the assembled vector held in shared memory and the children's update
+// vectors software-pipelined (the (rel, value) pair of the next chunk is in flight while the current one is added;
+// a barrier only between children, whose targets may overlap).  Falls back to the global version for fronts that do
+// not fit (order > DF_STAGE or more than DF_GATHER_MAXCH children).
+// smem: tmp[DF_STAGE] | meta_o[DF_GATHER_MAXCH] (long long) | meta_rc[DF_GATHER_MAXCH] (int)
+__device__ void big_gather(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+                           const double* __restrict__ x, const double* __restrict__ cbv) {
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]), f = k + r;
+  const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
+  if (f > DF_STAGE || nch > DF_GATHER_MAXCH || (V.opts & 1)) { big_gather_global(S, N, V, s, epoch, x, cbv); return; }
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* tmp = sm;
+  long long* meta_o = reinterpret_cast<long long*>(sm + DF_STAGE);
+  int* meta_rc = reinterpret_cast<int*>(meta_o + DF_GATHER_MAXCH);
+  for (int q = tid; q < nch; q += nt) {
+    const int c = S.child_idx[ch0 + q];
+    const long long o = S.rows_ptr[c];
+    meta_o[q] = o;
+    meta_rc[q] = (int)(S.rows_ptr[c + 1] - o);
+    wait_eq(V.done_f + c, epoch);
+  }
+  for (int i = tid; i < f; i += nt) tmp[i] = (i < k) ? x[c0 + i] : 0.0;
+  __syncthreads();
+  {
+    int q = 0, t = tid;
+    int idx = 0; double val = 0.0; bool ok = false;
+    if (nch > 0) {
+      ok = t < meta_rc[0];
+      if (ok) { idx = S.rel[meta_o[0] + t]; val = __ldcg(cbv + meta_o[0] + t); }
+    }
+    while (q < nch) {
+      const int cidx = idx; const double cval = val; const bool cok = ok;
+      int nq = q, ntt = t + nt;
+      if (ntt - tid >= meta_rc[q]) { nq = q + 1; ntt = tid; }   // (uniform: depends on the chunk base only)
+      ok = false;
+      if (nq < nch) {
+        const long long o = meta_o[nq];
+        ok = ntt < meta_rc[nq];
+        if (ok) { idx = S.rel[o + ntt]; val = __ldcg(cbv + o + ntt); }
+      }
+      if (cok) tmp[cidx] += cval;
+      if (nq != q) __syncthreads();
+      q = nq; t = ntt;
+    }
+  }
+  double* w = V.bigv + V.bigv_off[s];
+  const int* __restrict__ lp = N.lperm + c0;
+  for (int i = tid; i < f; i += nt) w[i] = (i < k) ? tmp[lp[i]] : tmp[i];
+  __syncthreads();
+  if (tid == 0) { st_release(V.gflag + s, epoch); }
+}
+
 // Big fronts use the EXPLICIT inverse of their unit-lower-triangular pivot block L11 (k_linv_* below, computed once
 // per factorisation): the in-front recurrences  y = L11^-1 w  and  x = L11^-T t  become block GEMVs whose 64-row /
 // 64-column blocks are independent tasks -- no chain of nkb dependent steps per front.  Linv is stored K64 x K64
 // (K64 = 64*ceil(k/64), column-major, zero-padded, upper block triangle never read).
-#define DF_STAGE 8192      // doubles of the shared staging area (vectors are staged in chunks of this many rows)
-
 __device__ __forceinline__ void wait_flags(const int* flags, int first, int last, int epoch) {
   // flags[first..last) all equal to epoch (one flag per thread, in parallel), then a CTA barrier
   for (int c = first + (int)threadIdx.x; c < last; c += blockDim.x) wait_eq(flags + c, epoch);
@@ -691,8 +746,10 @@ __global__ void __launch_bounds__(64) k_linv_diag(DevSym S, DevNum N, const int*
   }
 }
 
+// 64x64 tile per CTA of 128 threads, 8x4 register blocking (rows tx+8q, columns ty+16p), k-slabs of 16 prefetched
+// into registers while the current slab is consumed.
 template <int PHASE>
-__global__ void __launch_bounds__(256) k_linv_gemm(DevSym S, DevNum N, const LinvItem* __restrict__ items,
+__global__ void __launch_bounds__(128) k_linv_gemm(DevSym S, DevNum N, const LinvItem* __restrict__ items,
                                                    const long long* __restrict__ linv_off, double* __restrict__ linv) {
   __shared__ double As[16][65];
   __shared__ double Bs[16][65];
@@ -704,61 +761,58 @@ __global__ void __launch_bounds__(256) k_linv_gemm(DevSym S, DevNum N, const Lin
   double* __restrict__ Li = linv + linv_off[s];
   const double* __restrict__ Lp = N.L + S.L_off[s];
   double* __restrict__ Wp = N.W + S.L_off[s];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
   const int i0 = it.ib * 64, j0 = it.jb * 64;
-  // loaders: A element (row i0+ai, col kk0+ak) with ai = t & 63, ak = t >> 6 (+4 per step); B element (row kk0+bk,
-  // col j0+bj) with bk = t & 15, bj = t >> 4 (+16 per step)
-  auto ldA = [&](int kk0, double (&v)[4]) {
+  // loaders: A element (row i0 + (tid & 63), col kk0 + (tid >> 6) + 2q); B element (row kk0 + (tid & 15), col j0 + (tid >> 4) + 8q)
+  double av[8], bv[8];
+  auto load = [&](int kk0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ai = tid & 63, ak = (tid >> 6) + 4 * q;
-      const long long row = i0 + ai, col = kk0 + ak;
-      if (PHASE == 1) v[q] = (row < k && col < k) ? Lp[row + col * f] : 0.0;
-      else v[q] = Li[row + col * K64];
+    for (int q = 0; q < 8; ++q) {
+      const long long arow = i0 + (tid & 63), acol = kk0 + (tid >> 6) + 2 * q;
+      const long long brow = kk0 + (tid & 15), bcol = j0 + (tid >> 4) + 8 * q;
+      if (PHASE == 1) {
+        av[q] = (arow < k && acol < k) ? Lp[arow + acol * f] : 0.0;
+        bv[q] = Li[brow + bcol * K64];
+      } else {
+        av[q] = Li[arow + acol * K64];
+        bv[q] = (brow < k && bcol < k) ? Wp[brow + bcol * f] : 0.0;
+      }
     }
   };
-  auto ldB = [&](int kk0, double (&v)[4]) {
+  double acc[8][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int bk = tid & 15, bj = (tid >> 4) + 16 * q;
-      const long long row = kk0 + bk, col = j0 + bj;
-      if (PHASE == 1) v[q] = Li[row + col * K64];
-      else v[q] = (row < k && col < k) ? Wp[row + col * f] : 0.0;
-    }
-  };
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
   const int kbeg = it.m0 * 64, kend = it.m1 * 64;
-  double av[4], bv[4];
-  ldA(kbeg, av); ldB(kbeg, bv);
+  load(kbeg);
   for (int kk0 = kbeg; kk0 < kend; kk0 += 16) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      As[(tid >> 6) + 4 * q][tid & 63] = av[q];
-      Bs[tid & 15][(tid >> 4) + 16 * q] = bv[q];
+    for (int q = 0; q < 8; ++q) {
+      As[(tid >> 6) + 2 * q][tid & 63] = av[q];
+      Bs[tid & 15][(tid >> 4) + 8 * q] = bv[q];
     }
     __syncthreads();
-    if (kk0 + 16 < kend) { ldA(kk0 + 16, av); ldB(kk0 + 16, bv); }
+    if (kk0 + 16 < kend) load(kk0 + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      double a[4], c[4];
+      double a[8], c[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { a[q] = As[kk][tx + 16 * q]; c[q] = Bs[kk][ty + 16 * q]; }
+      for (int q = 0; q < 8; ++q) a[q] = As[kk][tx + 8 * q];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int p = 0; p < 4; ++p) c[p] = Bs[kk][ty + 16 * p];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[q][p] = fma(a[q], c[p], acc[q][p]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 8; ++q)
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const long long row = i0 + tx + 16 * q, col = j0 + ty + 16 * p;
+      const long long row = i0 + tx + 8 * q, col = j0 + ty + 16 * p;
       if (PHASE == 1) { if (row < k && col < k) Wp[row + col * f] = acc[q][p]; }
       else Li[row + col * K64] = -acc[q][p];
     }
@@ -794,7 +848,7 @@ __global__ void __launch_bounds__(DF_THREADS) k_solve_dataflow(DevSym S, DevNum 
     } else if (T.type == ST_MID) {
       if (FWD) mid_fwd(S, N, V, T.a, epoch, sm, x, cbv); else mid_bwd(S, N, V, T.a, epoch, sm, x);
     } else if (T.type == ST_BIG_GATHER) {
-      big_gather(S, N, V, T.a, epoch, x, cbv);
+      big_gather(S, N, V, T.a, epoch, sm, x, cbv);
     } else {
       if (FWD) { if (T.c == 0) big_fwd_piv(S, N, V, T.a, T.b, epoch, sm, x); else big_fwd_cb(S, N, V, T.a, T.b, epoch, sm, cbv); }
       else { if (T.c == 0) big_bwd_t(S, N, V, T.a, T.b, epoch, sm, x); else big_bwd_x(S, N, V, T.a, T.b, epoch, sm, x); }
