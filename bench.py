@@ -295,8 +295,8 @@ def main():
                                              "factor_ms": fac_ms, "solve_ms_per_rhs": tri_ms},
             "roofline": {"kernel": "supernodal triangular solve sweeps (k_solve_dataflow<fwd> + k_solve_dataflow<bwd>, persistent task-queue kernels)",
                          "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": 471.4e6 if dim == 321600 else None,
-                         "traffic_source": "ncu --set full of k_solve_dataflow fwd+bwd (dram__bytes_read+write: 231.3+11.3+224.9+3.8 MB), profiles/r1_summary.md",
+                         "traffic": 488.2e6 if dim == 321600 else None,
+                         "traffic_source": "ncu --set full of k_solve_dataflow fwd+bwd (dram__bytes_read+write: 239.5+11.7+233.1+3.8 MB), profiles/r1_summary.md",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_solve": tri_bytes},
             "factor": {"flops_panel": info["flops_panel"], "flops_schur": info["flops_schur"],

@@ -245,23 +245,21 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       }
       const double dv = d;
       const double rdv = 1.0 / dv;
-      if (forced) gsync<WARP>();   // (the static-pivot branch above read the column that is rescaled below)
-      for (int i = j + 1 + tid; i < f; i += nt) {
-        double c = F[i + j * ld];
-        cv1[i] = c;
-        F[i + j * ld] = c * rdv;
-      }
+      // Deferred scaling: column j keeps the UNSCALED values c = l * d (only the final write-out applies D^-1, kept in
+      // cv1 = dinv / cv2 = doff), so the update below reads column j that nobody writes -- no barrier before it and no
+      // separate scaling pass.
       if (tid == 0) {
         pt[j] = 1; dinv[j] = rdv; doff[j] = 0.0; ptype_g[j] = 1;
+        cv1[j] = rdv; cv2[j] = 0.0;
         if (dv < 0.0) ++c_neg;
       }
-      gsync<WARP>();
       // trailing update, 4 columns per trip so the shared-memory loads overlap (latency-bound otherwise)
+      const double* __restrict__ cj = F + j * ld;
       for (int i = j + 1 + lane; i < f; i += 32) {
-        const double li = F[i + j * ld];
+        const double li = cj[i] * rdv;
         int m = j + 1 + warp;
         for (; m + 3 * nwarp <= i; m += 4 * nwarp) {   // lower triangle only: columns m <= i
-          const double c0 = cv1[m], c1 = cv1[m + nwarp], c2 = cv1[m + 2 * nwarp], c3 = cv1[m + 3 * nwarp];
+          const double c0 = cj[m], c1 = cj[m + nwarp], c2 = cj[m + 2 * nwarp], c3 = cj[m + 3 * nwarp];
           double* q0 = F + i + m * ld;
           double* q1 = q0 + nwarp * ld;
           double* q2 = q1 + nwarp * ld;
@@ -269,7 +267,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
           const double f0 = *q0, f1 = *q1, f2 = *q2, f3 = *q3;
           *q0 = fma(-li, c0, f0); *q1 = fma(-li, c1, f1); *q2 = fma(-li, c2, f2); *q3 = fma(-li, c3, f3);
         }
-        for (; m <= i; m += nwarp) F[i + m * ld] = fma(-li, cv1[m], F[i + m * ld]);
+        for (; m <= i; m += nwarp) F[i + m * ld] = fma(-li, cj[m], F[i + m * ld]);
       }
       gsync<WARP>();
       j += 1;
@@ -277,26 +275,25 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       // ---------------- 2x2 pivot at (j, j+1) ----------------
       const double a = F[j + j * ld], b = F[j + 1 + j * ld], c = F[j + 1 + (j + 1) * ld];
       const double det = a * c - b * b;
-      const double idet = 1.0 / det;   // (a, b, c are not touched by the loop below: no barrier needed)
-      for (int i = j + 2 + tid; i < f; i += nt) {
-        double c1 = F[i + j * ld], c2 = F[i + (j + 1) * ld];
-        cv1[i] = c1; cv2[i] = c2;
-        F[i + j * ld] = (c * c1 - b * c2) * idet;
-        F[i + (j + 1) * ld] = (a * c2 - b * c1) * idet;
-      }
+      const double idet = 1.0 / det;
+      const double da = c * idet, db = a * idet, dof = -b * idet;   // D^-1 of the 2x2 block
       if (tid == 0) {
         pt[j] = 2; pt[j + 1] = 3; ptype_g[j] = 2; ptype_g[j + 1] = 3;
-        dinv[j] = c * idet; dinv[j + 1] = a * idet; doff[j] = -b * idet; doff[j + 1] = 0.0;
+        dinv[j] = da; dinv[j + 1] = db; doff[j] = dof; doff[j + 1] = 0.0;
+        cv1[j] = da; cv1[j + 1] = db; cv2[j] = dof; cv2[j + 1] = 0.0;
         ++c_2x2;
         if (det < 0.0) c_neg += 1; else if (a < 0.0) c_neg += 2;
       }
-      gsync<WARP>();
+      // columns j, j+1 stay unscaled (see the 1x1 case): l = [c1 c2] D^-1 is formed on the fly
+      const double* __restrict__ cj = F + j * ld;
+      const double* __restrict__ cj1 = F + (j + 1) * ld;
       for (int i = j + 2 + lane; i < f; i += 32) {
-        const double l1 = F[i + j * ld], l2 = F[i + (j + 1) * ld];
+        const double r1 = cj[i], r2 = cj1[i];
+        const double l1 = fma(r1, da, r2 * dof), l2 = fma(r1, dof, r2 * db);
         int m = j + 2 + warp;
         for (; m + 3 * nwarp <= i; m += 4 * nwarp) {
-          const double a0 = cv1[m], a1 = cv1[m + nwarp], a2 = cv1[m + 2 * nwarp], a3 = cv1[m + 3 * nwarp];
-          const double b0 = cv2[m], b1 = cv2[m + nwarp], b2 = cv2[m + 2 * nwarp], b3 = cv2[m + 3 * nwarp];
+          const double a0 = cj[m], a1 = cj[m + nwarp], a2 = cj[m + 2 * nwarp], a3 = cj[m + 3 * nwarp];
+          const double b0 = cj1[m], b1 = cj1[m + nwarp], b2 = cj1[m + 2 * nwarp], b3 = cj1[m + 3 * nwarp];
           double* q0 = F + i + m * ld;
           double* q1 = q0 + nwarp * ld;
           double* q2 = q1 + nwarp * ld;
@@ -305,7 +302,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
           *q0 = fma(-l2, b0, fma(-l1, a0, f0)); *q1 = fma(-l2, b1, fma(-l1, a1, f1));
           *q2 = fma(-l2, b2, fma(-l1, a2, f2)); *q3 = fma(-l2, b3, fma(-l1, a3, f3));
         }
-        for (; m <= i; m += nwarp) F[i + m * ld] = fma(-l2, cv2[m], fma(-l1, cv1[m], F[i + m * ld]));
+        for (; m <= i; m += nwarp) F[i + m * ld] = fma(-l2, cj1[m], fma(-l1, cj[m], F[i + m * ld]));
       }
       gsync<WARP>();
       j += 2;
@@ -570,14 +567,17 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
 
   // write L panel (f x k, ld = f), unit diagonal, zero strictly-upper part of the pivot block
   double* __restrict__ P = N.L + S.L_off[s];
+  // (the pivot columns of F hold the unscaled values L*D: apply D^-1 = {cv1 = dinv, cv2 = doff} here)
   for (int t = tid >> 5; t < k; t += (nt >> 5)) {
-    const int is2 = (pt[t] == 2);
+    const int ty = pt[t];
     for (int i = tid & 31; i < f; i += 32) {
       double v;
       if (i < t) v = 0.0;
       else if (i == t) v = 1.0;
-      else if (is2 && i == t + 1) v = 0.0;
-      else v = F[i + t * ld];
+      else if (ty == 2 && i == t + 1) v = 0.0;
+      else if (ty == 1) v = F[i + t * ld] * cv1[t];
+      else if (ty == 2) v = fma(F[i + t * ld], cv1[t], F[i + (t + 1) * ld] * cv2[t]);
+      else v = fma(F[i + (t - 1) * ld], cv2[t - 1], F[i + t * ld] * cv1[t]);
       P[i + (size_t)t * f] = v;
     }
   }
