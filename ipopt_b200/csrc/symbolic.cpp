@@ -67,6 +67,23 @@ void postorder(int n, const std::vector<int>& parent, std::vector<int>& post) {
   }
 }
 
+// Entries (column c, row r, id) sorted by (c, r, id): two stable counting passes (by r, then by c) over entries given
+// in ascending id order -- same result as std::sort on ((c*n + r), id) pairs at a fraction of the time.
+struct Ent { int c, r, id; };
+void sort_entries(int n, std::vector<Ent>& a) {
+  const size_t m = a.size();
+  std::vector<Ent> b(m);
+  std::vector<int64_t> cnt((size_t)n + 1);
+  std::fill(cnt.begin(), cnt.end(), 0);
+  for (const Ent& x : a) cnt[x.r + 1]++;
+  for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+  for (const Ent& x : a) b[cnt[x.r]++] = x;
+  std::fill(cnt.begin(), cnt.end(), 0);
+  for (const Ent& x : b) cnt[x.c + 1]++;
+  for (int i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+  for (const Ent& x : b) a[cnt[x.c]++] = x;
+}
+
 }  // namespace
 
 int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* vals,
@@ -89,27 +106,26 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
   }
 
   // ---- 1. unique lower pattern in ORIGINAL labels -------------------------------------------
-  std::vector<std::pair<int64_t, int>> keyed((size_t)nnz);
+  std::vector<Ent> keyed((size_t)nnz);
   for (int64_t e = 0; e < nnz; ++e) {
     int i = irn[e] - 1, j = jcn[e] - 1;
-    int r = std::max(i, j), c = std::min(i, j);
-    keyed[e] = {(int64_t)c * n + r, (int)e};
+    keyed[e] = Ent{std::min(i, j), std::max(i, j), (int)e};
   }
-  std::sort(keyed.begin(), keyed.end());
+  sort_entries(n, keyed);
   std::vector<int> ur, uc;        // original unique entries
   std::vector<double> uv;         // summed values (only if vals)
   std::vector<int> t2u0((size_t)nnz);
   ur.reserve(nnz); uc.reserve(nnz);
   for (int64_t q = 0; q < nnz; ++q) {
-    if (q == 0 || keyed[q].first != keyed[q - 1].first) {
-      uc.push_back((int)(keyed[q].first / n));
-      ur.push_back((int)(keyed[q].first % n));
+    if (q == 0 || keyed[q].c != keyed[q - 1].c || keyed[q].r != keyed[q - 1].r) {
+      uc.push_back(keyed[q].c);
+      ur.push_back(keyed[q].r);
       if (vals) uv.push_back(0.0);
     }
-    t2u0[keyed[q].second] = (int)ur.size() - 1;
-    if (vals) uv.back() += vals[keyed[q].second];
+    t2u0[keyed[q].id] = (int)ur.size() - 1;
+    if (vals) uv.back() += vals[keyed[q].id];
   }
-  { std::vector<std::pair<int64_t, int>>().swap(keyed); }
+  { std::vector<Ent>().swap(keyed); }
   const int64_t nu = (int64_t)ur.size();
   S.nnz_u = nu;
 
@@ -481,20 +497,19 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
   lap("8 row structures");
   // ---- 9. unique entries in final order, assembly maps ----------------------------------------
   {
-    std::vector<std::pair<int64_t, int>> k2((size_t)nu);
+    std::vector<Ent> k2((size_t)nu);
     for (int64_t u = 0; u < nu; ++u) {
       int a = iperm[ur[u]], b2 = iperm[uc[u]];
-      int r = std::max(a, b2), c = std::min(a, b2);
-      k2[u] = {(int64_t)c * n + r, (int)u};
+      k2[u] = Ent{std::min(a, b2), std::max(a, b2), (int)u};
     }
-    std::sort(k2.begin(), k2.end());
+    sort_entries(n, k2);
     std::vector<int> rank((size_t)nu);
     S.u_row.resize(nu); S.u_col.resize(nu); S.u_dst.resize(nu); S.u_dst64.resize(nu);
     S.uent_ptr.assign(nsn + 1, 0);
     for (int64_t q = 0; q < nu; ++q) {
-      int u = k2[q].second;
+      int u = k2[q].id;
       rank[u] = (int)q;
-      int c = (int)(k2[q].first / n), r = (int)(k2[q].first % n);
+      int c = k2[q].c, r = k2[q].r;
       int s = sn_of[c];
       int a = S.sn_start[s], e = S.sn_start[s + 1], k = e - a;
       int fr = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
