@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -303,6 +304,12 @@ int factor_front(std::vector<double>& F, int f, int p, double u, std::vector<int
   int npiv = 0, pend = p, progress = 0;
   std::vector<double> c1(f), c2(f);
   bool force = false;
+  // The pivot search only ever reads the first p columns (all rows), so the rank-1/rank-2 updates are applied eagerly to
+  // those columns only; the contribution block (rows/columns >= p) receives the same updates, in the same pivot order and
+  // with the same operands (=> bit-identical result), in one cache-friendly pass at the end.  Wcb keeps the unscaled
+  // pivot columns (= L*D) of the contribution rows for that pass.
+  const int q = f - p;
+  std::vector<double> Wcb((size_t)q * p);
   while (npiv < p) {
     if (npiv == pend) {
       if (progress > 0) { pend = p; progress = 0; }
@@ -350,9 +357,10 @@ int factor_front(std::vector<double>& F, int f, int p, double u, std::vector<int
       d1[j] = d; d2[j] = 0.0; two[j] = 0;
       if (d < 0) ++neg;
       for (int i = j + 1; i < f; ++i) { c1[i] = AT(F, f, i, j); AT(F, f, i, j) = c1[i] / d; }
+      for (int i = p; i < f; ++i) Wcb[(size_t)j * q + (i - p)] = c1[i];
       const int m0 = j + 1;
-#pragma omp parallel for schedule(static) if ((int64_t)(f - m0) * (f - m0) > 40000)
-      for (int m = m0; m < f; ++m) {
+#pragma omp parallel for schedule(static) if ((int64_t)(p - m0) * (f - m0) > 40000)
+      for (int m = m0; m < p; ++m) {
         double cm = c1[m];
         if (cm == 0.0) continue;
         double* col = &F[(size_t)m * f];
@@ -374,9 +382,10 @@ int factor_front(std::vector<double>& F, int f, int p, double u, std::vector<int
         AT(F, f, i, j + 1) = (a * c2[i] - b * c1[i]) / det;
       }
       AT(F, f, j + 1, j) = 0.0;
+      for (int i = p; i < f; ++i) { Wcb[(size_t)j * q + (i - p)] = c1[i]; Wcb[(size_t)(j + 1) * q + (i - p)] = c2[i]; }
       const int m0 = j + 2;
-#pragma omp parallel for schedule(static) if ((int64_t)(f - m0) * (f - m0) > 40000)
-      for (int m = m0; m < f; ++m) {
+#pragma omp parallel for schedule(static) if ((int64_t)(p - m0) * (f - m0) > 40000)
+      for (int m = m0; m < p; ++m) {
         double a1 = c1[m], a2 = c2[m];
         if (a1 == 0.0 && a2 == 0.0) continue;
         double* col = &F[(size_t)m * f];
@@ -388,6 +397,28 @@ int factor_front(std::vector<double>& F, int f, int p, double u, std::vector<int
       npiv += 2;
     }
     ++progress;
+  }
+  // deferred update of the contribution block: column m, pivots in elimination order
+  if (q > 0 && npiv > 0) {
+#pragma omp parallel for schedule(dynamic, 4) if ((int64_t)q * q * npiv > 2000000)
+    for (int m = p; m < f; ++m) {
+      double* col = &F[(size_t)m * f];
+      for (int t = 0; t < npiv; ++t) {
+        if (two[t]) {
+          const double a1 = Wcb[(size_t)t * q + (m - p)], a2 = Wcb[(size_t)(t + 1) * q + (m - p)];
+          const double* l1 = &F[(size_t)t * f];
+          const double* l2 = &F[(size_t)(t + 1) * f];
+          ++t;
+          if (a1 == 0.0 && a2 == 0.0) continue;
+          for (int i = m; i < f; ++i) col[i] -= l1[i] * a1 + l2[i] * a2;
+        } else {
+          const double cm = Wcb[(size_t)t * q + (m - p)];
+          if (cm == 0.0) continue;
+          const double* lj = &F[(size_t)t * f];
+          for (int i = m; i < f; ++i) col[i] -= lj[i] * cm;
+        }
+      }
+    }
   }
   return npiv;
 }
@@ -414,12 +445,28 @@ int factor(Oracle& O) {
   }
   O.fronts.assign(nsn, Front());
   std::vector<CB> cbs(nsn);
-  std::vector<int> pos(n, -1);
   O.num_neg = O.num_delayed = O.num_2x2 = 0; O.max_front = 0; O.nnzL = 0; O.flops = 0;
   int nforced = 0;
-  std::vector<double> F;
-  std::vector<int> ind, order;
-  for (int s = 0; s < nsn; ++s) {
+  // Fronts of one tree level (height above the leaves) are independent: levels with many fronts are processed by
+  // concurrent threads (one front per thread, private work space), levels with few fronts one after the other with the
+  // parallel loops inside factor_front.  The arithmetic of a front does not depend on the schedule.
+  std::vector<int> level(nsn, 0);
+  int nlev = 0;
+  for (int s = 0; s < nsn; ++s) {   // children precede parents
+    for (int c : O.sn_children[s]) level[s] = std::max(level[s], level[c] + 1);
+    nlev = std::max(nlev, level[s] + 1);
+  }
+  std::vector<std::vector<int>> by_level(nlev);
+  for (int s = 0; s < nsn; ++s) by_level[level[s]].push_back(s);
+  struct Work { std::vector<double> F; std::vector<int> ind, order, pos; };
+  struct Tally { int neg = 0, n2 = 0, delayed = 0, forced = 0, max_front = 0; int64_t nnzL = 0; };
+  std::vector<double> front_flops(nsn, 0.0);
+  auto process_front = [&](int s, Work& W, Tally& T) {
+    std::vector<double>& F = W.F;
+    std::vector<int>& ind = W.ind;
+    std::vector<int>& order = W.order;
+    std::vector<int>& pos = W.pos;
+    if ((int)pos.size() != n) pos.assign(n, -1);
     const int a = O.sn_start[s], e = O.sn_start[s + 1];
     ind.clear();
     for (int j = a; j < e; ++j) ind.push_back(j);
@@ -428,7 +475,7 @@ int factor(Oracle& O) {
     const int p = ind.size();
     for (int i : O.sn_rows[s]) ind.push_back(i);
     const int f = ind.size();
-    O.max_front = std::max(O.max_front, f);
+    T.max_front = std::max(T.max_front, f);
     for (int t = 0; t < f; ++t) pos[ind[t]] = t;
     F.assign((size_t)f * f, 0.0);
     for (int j = a; j < e; ++j)
@@ -454,7 +501,7 @@ int factor(Oracle& O) {
     Front& fr = O.fronts[s];
     fr.d1.assign(p, 0.0); fr.d2.assign(p, 0.0); fr.two.assign(p, 0);
     const bool is_root = O.parent_sn[s] < 0;
-    int npiv = factor_front(F, f, p, O.pivtol, order, fr.d1, fr.d2, fr.two, O.num_neg, O.num_2x2, O.flops, is_root, nforced);
+    int npiv = factor_front(F, f, p, O.pivtol, order, fr.d1, fr.d2, fr.two, T.neg, T.n2, front_flops[s], is_root, T.forced);
     fr.npiv = npiv;
     fr.d1.resize(npiv); fr.d2.resize(npiv); fr.two.resize(npiv);
     fr.ind.resize(f);
@@ -464,19 +511,47 @@ int factor(Oracle& O) {
       fr.L[(size_t)j * f + j] = 1.0;
       for (int i = j + 1; i < f; ++i) fr.L[(size_t)j * f + i] = AT(F, f, i, j);
     }
-    O.nnzL += (int64_t)npiv * f - (int64_t)npiv * (npiv - 1) / 2;
+    T.nnzL += (int64_t)npiv * f - (int64_t)npiv * (npiv - 1) / 2;
     const int m = f - npiv;
     if (!is_root) {
       CB& cb = cbs[s];
       cb.ndelay = p - npiv;
-      O.num_delayed += cb.ndelay;
+      T.delayed += cb.ndelay;
       cb.ind.assign(fr.ind.begin() + npiv, fr.ind.end());
       cb.a.assign((size_t)m * m, 0.0);
       for (int jj = 0; jj < m; ++jj)
         for (int ii = jj; ii < m; ++ii) cb.a[(size_t)jj * m + ii] = AT(F, f, npiv + ii, npiv + jj);
     }
     for (int t = 0; t < f; ++t) pos[ind[t]] = -1;
+  };
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = omp_get_max_threads();
+#endif
+  std::vector<Work> work(nthreads);
+  std::vector<Tally> tally(nthreads);
+  for (int l = 0; l < nlev; ++l) {
+    const double tl0 = wall();
+    const std::vector<int>& fl = by_level[l];
+    if (nthreads > 1 && (int)fl.size() >= std::max(2, nthreads / 4)) {
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int q = 0; q < (int)fl.size(); ++q) {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        process_front(fl[q], work[tid], tally[tid]);
+      }
+    } else {
+      for (int s : fl) process_front(s, work[0], tally[0]);
+    }
+    if (getenv("ORACLE_PROFILE")) fprintf(stderr, "[oracle] level %d: %zu fronts %.1f ms\n", l, fl.size(), (wall() - tl0) * 1e3);
   }
+  for (const Tally& T : tally) {
+    O.num_neg += T.neg; O.num_2x2 += T.n2; O.num_delayed += T.delayed; nforced += T.forced;
+    O.max_front = std::max(O.max_front, T.max_front); O.nnzL += T.nnzL;
+  }
+  for (int s = 0; s < nsn; ++s) O.flops += front_flops[s];
   O.factored = true;
   O.t_factor = wall() - t0;
   if (O.verbose)
