@@ -97,12 +97,20 @@ int b200ldlt_solve_device(b200ldlt_handle h, int nrhs, double* d_rhs);
 /* <-> NumberOfNegEVals() (hpp:207) */
 int b200ldlt_num_neg(b200ldlt_handle h);
 /* <-> IncreaseQuality() (hpp:220): pivtol <- min(pivtolmax, pivtol^0.75); returns 0 if already at max.
+ * If the last factorisation had to LIFT pivots (info.num_forced) or saw growth beyond 1/u (info.num_growth), the
+ * first request instead schedules a re-analysis (saddle pairing + ordering) on the values of the next factor call.
+ * With num_forced > 0 the factors and the inertia are those of a matrix perturbed by <= 1e-8 |column| in the lifted pivots.
  * The values of the last matrix are kept on the device, so the next factor call may pass new or old values. */
 int b200ldlt_increase_quality(b200ldlt_handle h);
 /* Re-run the numeric factorisation on the values kept on the device from the last factor call
  * (used after increase_quality instead of the reference's CALL_AGAIN round trip,
  *  IpMumpsSolverInterface.cpp:265-278). */
 int b200ldlt_refactor(b200ldlt_handle h, int check_inertia, int expected_neg, int* num_neg);
+
+/* (Re)set the pivot threshold and its cap, e.g. when a kept handle starts a new optimisation
+ * (warm_start_same_structure: the reference adapters re-read pivtol in every InitializeImpl,
+ *  IpMumpsSolverInterface.cpp:191-245). */
+int b200ldlt_set_pivtol(b200ldlt_handle h, double pivtol, double pivtolmax);
 
 int b200ldlt_get_info(b200ldlt_handle h, b200ldlt_info* info);
 /* Copy a named array of the symbolic analysis ("perm","sn_start","sn_parent","rows_ptr","rows","rel",

@@ -52,6 +52,16 @@ struct LinvPlan {
   std::vector<int> ng;
 };
 
+// triangular-solve work of a set of fronts (solve_dataflow.cu): subtrees for k_solve_sub + task lists for k_solve_top
+struct SolvePlan {
+  DevBuf<SolveTask> d_tf, d_tb;
+  DevBuf<int> d_bundle, d_sub_ptr, d_lvl_ptr, d_lvl_nsmall, d_sub_fronts, d_sub_root, d_ccnt;
+  DevBuf<double> d_part;
+  DevSolve V;
+  int nsub = 0, ntf = 0, ntb = 0;
+  long long sub_bytes = 0;
+};
+
 struct LevelPlan {
   // big fronts of the level: [big_off, big_off+big_cnt) in front_list
   int big_off = 0, big_cnt = 0, big_kmax = 0, big_fmax = 0, big_rmax = 0, big_chmax = 0;
@@ -61,8 +71,24 @@ struct LevelPlan {
   int all_off = 0, all_cnt = 0, fmax = 0;  // whole level (solve)
 };
 
+// environment switches for profiling / A-B runs, read ONCE at b200ldlt_create (never on the enqueue path)
+struct DebugSwitches {
+  bool factor_sections = false;   // B200_FACTOR_SECTIONS=1 (with use_graph=0): timed section marks
+  bool one_stream = false;        // B200_ONE_STREAM=1: big-front pipeline on a single stream
+  bool solve_timeline = false;    // B200_SOLVE_TIMELINE=1: per-task %globaltimer log of the top solve kernel
+  std::vector<int> buckets;       // B200_BUCKETS=a,b,c: soft split points of the shared-memory front classes
+  void read() {
+    factor_sections = getenv("B200_FACTOR_SECTIONS") != nullptr;
+    one_stream = getenv("B200_ONE_STREAM") != nullptr;
+    solve_timeline = getenv("B200_SOLVE_TIMELINE") != nullptr;
+    if (const char* e = getenv("B200_BUCKETS"))
+      for (const char* p = e; *p;) { buckets.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
+  }
+};
+
 struct Solver {
   b200ldlt_options opt;
+  DebugSwitches dbg;
   std::string err;
   int dev = 0;
   cudaStream_t stream = nullptr;
@@ -80,6 +106,10 @@ struct Solver {
   int rhs_cap = 0;
   int* h_counters = nullptr;     // pinned
   bool analysed = false, factored = false, have_dev_vals = false;
+  bool reanalyse = false;          // set by increase_quality after forced pivots: next factor re-runs the analysis on its values
+  int n_reanalysed = 0;
+  long long n_factor = 0;
+  bool reanalysed_since_raise = false;
   Symbolic S;
   std::vector<LevelPlan> plan;
   b200ldlt_info info;
@@ -98,9 +128,8 @@ struct Solver {
   DevSym DS;
   DevNum DN;
   int launches = 0;
-  // dataflow solve
-  DevBuf<SolveTask> d_tasks_f, d_tasks_b;
-  DevBuf<int> d_bundle, d_done_f, d_done_b, d_gflag, d_bflag_f, d_bflag_b, d_bcnt, d_bcnt_b, d_boff;
+  // solve (solve_dataflow.cu): shared flag / scratch arrays + one plan per front set
+  DevBuf<int> d_done_f, d_done_b, d_bflag_f, d_bflag_b, d_bcnt, d_bcnt_b, d_boff;
   DevBuf<long long> d_bigv_off;
   DevBuf<double> d_bigv, d_bigy;
   DevBuf<unsigned long long> d_ticket, d_tlog;
@@ -108,7 +137,7 @@ struct Solver {
   DevBuf<long long> d_linv_off;
   LinvPlan linv_plan;               // explicit inverses of the big fronts' pivot blocks (all fronts)
   std::vector<SolveTask> h_tasks;   // fwd then bwd (debug timeline)
-  DevSolve DV;
+  SolvePlan splan;                  // all fronts
   int solve_epoch = 0, df_grid = 0;
   unsigned long long ticket_f = 0, ticket_b = 0;
   int num_sms = 148;
@@ -117,9 +146,8 @@ struct Solver {
     int rank = 0, world = 1, nsub = 0;
     std::vector<int> owner, cut_roots, top_fronts;
     std::vector<LevelPlan> plan[2];          // [0] my subtrees, [1] top part
-    DevBuf<int> d_fl[2], d_bundle[2], d_mark_cut, d_mark_top;
-    DevBuf<SolveTask> d_tf[2], d_tb[2];
-    DevSolve DV[2];
+    DevBuf<int> d_fl[2], d_mark_cut, d_mark_top;
+    SolvePlan splan[2];
     LinvPlan linv_plan[2];
   } shard;
   cudaGraph_t fgraph = nullptr;
@@ -143,7 +171,7 @@ struct Solver {
   // debug (B200_FACTOR_SECTIONS=1 with use_graph=0): timed section marks of the last factorisation
   std::vector<std::pair<std::string, cudaEvent_t>> sect;
   void mark(const char* label, int level) {
-    if (!getenv("B200_FACTOR_SECTIONS") || opt.use_graph != 0) return;
+    if (!dbg.factor_sections || opt.use_graph != 0) return;
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream);
     sect.emplace_back(std::string(label) + " L" + std::to_string(level), e);
   }
@@ -174,7 +202,7 @@ struct Solver {
 
 // per level: big fronts first, then the shared-memory classes by descending front order; only fronts with take[s]
 static void build_level_plans(const Symbolic& S, int smax, const std::vector<char>& take, std::vector<int>& fl,
-                              std::vector<LevelPlan>& plan) {
+                              std::vector<LevelPlan>& plan, const std::vector<int>& soft) {
   fl.clear();
   fl.reserve(S.nsn);
   plan.assign(S.nlevels, LevelPlan());
@@ -202,11 +230,7 @@ static void build_level_plans(const Symbolic& S, int smax, const std::vector<cha
     // fronts are split again at the soft limits below (shared memory per CTA follows the largest front of a launch,
     // so finer buckets raise the number of resident CTAs per SM); a soft split only happens once the current bucket
     // holds enough fronts to fill the GPU.
-    std::vector<int> soft;   // (measured at N=400: every extra launch costs more than the occupancy gains - no soft splits by default)
-    if (const char* e = getenv("B200_BUCKETS")) {
-      soft.clear();
-      for (const char* p = e; *p;) { soft.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
-    }
+    // (soft: measured at N=400 every extra launch costs more than the occupancy gains - no soft splits by default)
     const int kMinBucket = 296;
     auto threads_of = [](int f) { return f > 64 ? 256 : (f > 32 ? 128 : 64); };
     LevelPlan::Bucket cur{(int)fl.size(), 0, 0, 0, 256, 0};
@@ -283,49 +307,142 @@ static int build_linv_plan(Solver* sv, const Symbolic& S, const std::vector<char
 
 static int enqueue_linv(Solver* sv, const LinvPlan& LP);
 
-// topologically sorted solve task lists (forward: levels ascending, backward: descending) for the fronts in take[]
-static void build_solve_tasks(const Symbolic& S, const std::vector<char>& take, std::vector<SolveTask>& tf,
-                              std::vector<SolveTask>& tb, std::vector<int>& bundle) {
-  const int MIDMAX = 256;
+// Triangular-solve plan of the fronts in take[] (see solve_dataflow.cu).
+//  * Subtrees: maximal subtrees (of the forest induced by take[]) whose fronts are all of order <= DF_MIDMAX and whose
+//    L panels stay below a byte / front-count cap -> one CTA each in k_solve_sub, largest first.
+//  * Everything else -> topologically sorted task lists for k_solve_top (forward: levels ascending; backward: descending).
+static const long long kSubBytesCap = 256 * 1024;
+static const int kSubFrontsCap = 96;
+
+static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<char>& take, SolvePlan& SP, cudaStream_t st) {
+  const int nsn = S.nsn;
+  std::vector<long long> subB(nsn, 0);
+  std::vector<int> subN(nsn, 0), subF(nsn, 0);
+  for (int s = 0; s < nsn; ++s) if (take[s]) {   // children precede parents
+    subB[s] += (long long)S.f(s) * S.k(s) * 8; subN[s] += 1; subF[s] = std::max(subF[s], S.f(s));
+    const int p = S.sn_parent[s];
+    if (p >= 0 && take[p]) { subB[p] += subB[s]; subN[p] += subN[s]; subF[p] = std::max(subF[p], subF[s]); }
+  }
+  auto ok = [&](int s) { return take[s] && subF[s] <= DF_MIDMAX && subB[s] <= kSubBytesCap && subN[s] <= kSubFrontsCap; };
+  std::vector<int> sub_of(nsn, -1), roots;
+  for (int s = nsn - 1; s >= 0; --s) {
+    if (!ok(s)) continue;
+    const int p = S.sn_parent[s];
+    if (p >= 0 && take[p] && ok(p)) sub_of[s] = sub_of[p];
+    else { sub_of[s] = (int)roots.size(); roots.push_back(s); }
+  }
+  // largest subtree first
+  std::vector<int> order(roots.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subB[roots[a]] > subB[roots[b]]; });
+  std::vector<int> rank_of(roots.size());
+  for (size_t i = 0; i < order.size(); ++i) rank_of[order[i]] = (int)i;
+  const int nsub = (int)roots.size();
+  std::vector<std::vector<int>> members(nsub);
+  SP.sub_bytes = 0;
+  for (int s = 0; s < nsn; ++s) if (sub_of[s] >= 0) { members[rank_of[sub_of[s]]].push_back(s); SP.sub_bytes += (long long)S.f(s) * S.k(s) * 8; }
+  std::vector<int> sub_ptr(1, 0), lvl_ptr(1, 0), lvl_nsmall, sub_fronts, sub_root(std::max(nsub, 1), 0);
+  for (int u = 0; u < nsub; ++u) {
+    std::vector<int>& M = members[u];
+    sub_root[u] = roots[order[u]];
+    // by (level, small first, larger first)
+    std::stable_sort(M.begin(), M.end(), [&](int a, int b) {
+      if (S.sn_level[a] != S.sn_level[b]) return S.sn_level[a] < S.sn_level[b];
+      const bool sa = S.f(a) <= 64, sb = S.f(b) <= 64;
+      if (sa != sb) return sa;
+      return S.f(a) > S.f(b);
+    });
+    for (size_t q = 0; q < M.size();) {
+      size_t e = q; int ns = 0;
+      while (e < M.size() && S.sn_level[M[e]] == S.sn_level[M[q]]) { if (S.f(M[e]) <= 64) ++ns; ++e; }
+      for (size_t t = q; t < e; ++t) sub_fronts.push_back(M[t]);
+      lvl_ptr.push_back((int)sub_fronts.size());
+      lvl_nsmall.push_back(ns);
+      q = e;
+    }
+    sub_ptr.push_back((int)lvl_nsmall.size());
+  }
+  // top task lists
+  std::vector<SolveTask> tf, tb;
+  std::vector<int> bundle;
+  int ncidx = 0;
+  long long npart = 0;
+  auto chunked = [&](std::vector<SolveTask>& T, int type, int s, int blk, int t0, int t1) {
+    const int ntile = t1 - t0;
+    const int nq = std::max(1, (ntile + DF_CH - 1) / DF_CH);
+    for (int q = 0; q < nq; ++q) {
+      SolveTask k{type, s, blk, t0 + q * DF_CH, std::min(t1, t0 + (q + 1) * DF_CH), q, nq, (int)npart, ncidx, 0};
+      if (ntile <= 0) { k.t0 = t0; k.t1 = t0; }
+      T.push_back(k);
+    }
+    npart += nq; ncidx += 1;
+  };
   for (int pass = 0; pass < 2; ++pass) {
     std::vector<SolveTask>& T = pass == 0 ? tf : tb;
     for (int li = 0; li < S.nlevels; ++li) {
       const int l = pass == 0 ? li : S.nlevels - 1 - li;
       std::vector<int> smalls;
-      // big first (longest), then mid, then small bundles
-      for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
-        int s = S.level_sn[q];
-        if (!take[s] || S.f(s) <= MIDMAX) continue;
-        if (pass == 0) T.push_back({ST_BIG_GATHER, s, 0, 0});
-      }
-      // the block tasks of a front are independent of each other inside a phase (explicit L11 inverse):
-      // phase 0 = pivot blocks (forward) / t blocks (backward), phase 1 = contribution rows / x blocks; long tasks first
       for (int phase = 0; phase < 2; ++phase)
         for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
-          int s = S.level_sn[q];
-          if (!take[s] || S.f(s) <= MIDMAX) continue;
+          const int s = S.level_sn[q];
+          if (!take[s] || sub_of[s] >= 0 || S.f(s) <= DF_MIDMAX) continue;
           const int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK, ncb = (S.r(s) + DF_BLK - 1) / DF_BLK;
-          if (pass == 0 && phase == 0) for (int b = nkb - 1; b >= 0; --b) T.push_back({ST_BIG_BLOCK, s, b, 0});
-          if (pass == 0 && phase == 1) for (int j = 0; j < ncb; ++j) T.push_back({ST_BIG_BLOCK, s, j, 1});
-          if (pass == 1 && phase == 0) for (int b = 0; b < nkb; ++b) T.push_back({ST_BIG_BLOCK, s, b, 0});
-          if (pass == 1 && phase == 1) for (int b = 0; b < nkb; ++b) T.push_back({ST_BIG_BLOCK, s, b, 1});
+          if (pass == 0 && phase == 0) for (int b = nkb - 1; b >= 0; --b) chunked(T, ST_FP, s, b, 0, b + 1);
+          if (pass == 0 && phase == 1) for (int j = 0; j < ncb; ++j) chunked(T, ST_FC, s, j, 0, nkb);
+          if (pass == 1 && phase == 0) for (int b = 0; b < nkb; ++b) chunked(T, ST_BT, s, b, 0, ncb);
+          if (pass == 1 && phase == 1) for (int b = 0; b < nkb; ++b) chunked(T, ST_BX, s, b, b, nkb);
         }
       for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
-        int s = S.level_sn[q];
-        if (!take[s] || S.f(s) > MIDMAX) continue;
-        if (S.f(s) > 64) T.push_back({ST_MID, s, 0, 0});
-        else smalls.push_back(s);   // warp-per-front classes (<= 32 staged in smem, 33..64 streamed)
+        const int s = S.level_sn[q];
+        if (!take[s] || sub_of[s] >= 0 || S.f(s) > DF_MIDMAX) continue;
+        if (S.f(s) > 64) T.push_back(SolveTask{ST_MID, s, 0, 0, 0, 0, 1, 0, 0, 0});
+        else smalls.push_back(s);
       }
       for (size_t q = 0; q < smalls.size(); q += 8) {
-        int cnt = (int)std::min<size_t>(8, smalls.size() - q);
-        T.push_back({ST_SMALL, (int)bundle.size(), cnt, 0});
+        const int cnt = (int)std::min<size_t>(8, smalls.size() - q);
+        T.push_back(SolveTask{ST_SMALL, (int)bundle.size(), cnt, 0, 0, 0, 1, 0, 0, 0});
         for (int w = 0; w < cnt; ++w) bundle.push_back(smalls[q + w]);
       }
     }
   }
+  SP.nsub = nsub; SP.ntf = (int)tf.size(); SP.ntb = (int)tb.size();
+  if (sv->opt.verbose)
+    fprintf(stderr, "[b200ldlt] solve plan: %d subtrees (%.1f MB of L, largest %.0f KB), top: %d fwd / %d bwd tasks, %lld partial slots\n",
+            nsub, SP.sub_bytes / 1e6, nsub ? subB[roots[order[0]]] / 1e3 : 0.0, SP.ntf, SP.ntb, npart);
+  if (sv->dbg.solve_timeline) { sv->h_tasks = tf; sv->h_tasks.insert(sv->h_tasks.end(), tb.begin(), tb.end()); }
+  if (tf.empty()) tf.push_back(SolveTask{ST_SMALL, 0, 0, 0, 0, 0, 1, 0, 0, 0});
+  if (tb.empty()) tb.push_back(SolveTask{ST_SMALL, 0, 0, 0, 0, 0, 1, 0, 0, 0});
+  if (bundle.empty()) bundle.push_back(0);
+  if (sub_fronts.empty()) sub_fronts.push_back(0);
+  if (lvl_nsmall.empty()) lvl_nsmall.push_back(0);
+  CU(SP.d_tf.upload(tf, st)); CU(SP.d_tb.upload(tb, st));
+  CU(SP.d_bundle.upload(bundle, st));
+  CU(SP.d_sub_ptr.upload(sub_ptr, st)); CU(SP.d_lvl_ptr.upload(lvl_ptr, st)); CU(SP.d_lvl_nsmall.upload(lvl_nsmall, st));
+  CU(SP.d_sub_fronts.upload(sub_fronts, st)); CU(SP.d_sub_root.upload(sub_root, st));
+  CU(SP.d_ccnt.alloc(std::max(ncidx, 1)));
+  CU(cudaMemsetAsync(SP.d_ccnt.p, 0, SP.d_ccnt.n * sizeof(int), st));
+  CU(SP.d_part.alloc(std::max<long long>(npart, 1) * 64));
+  DevSolve& V = SP.V;
+  V.tasks = SP.d_tf.p; V.tasks_bwd = SP.d_tb.p; V.ntasks_fwd = SP.ntf; V.ntasks_bwd = SP.ntb;
+  V.bundle = SP.d_bundle.p;
+  V.done_f = sv->d_done_f.p; V.done_b = sv->d_done_b.p;
+  V.bflag_f = sv->d_bflag_f.p; V.bflag_b = sv->d_bflag_b.p; V.bcnt = sv->d_bcnt.p; V.bcnt_b = sv->d_bcnt_b.p;
+  V.boff = sv->d_boff.p; V.bigv_off = sv->d_bigv_off.p; V.bigv = sv->d_bigv.p; V.bigy = sv->d_bigy.p;
+  V.part = SP.d_part.p; V.ccnt = SP.d_ccnt.p;
+  V.ticket = sv->d_ticket.p;
+  V.linv = sv->d_linv.p; V.linv_off = sv->d_linv_off.p;
+  V.sub_ptr = SP.d_sub_ptr.p; V.lvl_ptr = SP.d_lvl_ptr.p; V.lvl_nsmall = SP.d_lvl_nsmall.p;
+  V.sub_fronts = SP.d_sub_fronts.p; V.sub_root = SP.d_sub_root.p; V.nsub = nsub;
+  V.tlog = nullptr;
+  return B200LDLT_SUCCESS;
 }
 
 static int run_analysis(Solver* sv, const double* vals) {
+  // a (re-)analysis invalidates the factors and every buffer sized by the old plan
+  sv->factored = false;
+  sv->reanalyse = false;
+  if (sv->h_rhs) { cudaFreeHost(sv->h_rhs); sv->h_rhs = nullptr; }
+  sv->rhs_cap = 0;
   if (sv->fgraph_exec) { cudaGraphExecDestroy(sv->fgraph_exec); sv->fgraph_exec = nullptr; }
   if (sv->fgraph) { cudaGraphDestroy(sv->fgraph); sv->fgraph = nullptr; }
   AnalyseOptions ao;
@@ -408,38 +525,31 @@ static int run_analysis(Solver* sv, const double* vals) {
   std::vector<int> fl;
   {
     std::vector<char> take(S.nsn, 1);
-    build_level_plans(S, sv->opt.smem_front_max, take, fl, sv->plan);
+    build_level_plans(S, sv->opt.smem_front_max, take, fl, sv->plan, sv->dbg.buckets);
   }
   CU(sv->d_front_list.upload(fl, st));
   CU(cudaFuncSetAttribute(k_front_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CU(cudaFuncSetAttribute(k_front_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  CU(cudaFuncSetAttribute(k_front_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
   CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute(k_bwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaStreamSynchronize(st));
 
 
-  // ---- dataflow solve: task lists (topological), flags, scratch ---------------------------------
+  // ---- triangular solves: flags, scratch, explicit-inverse work lists, plan ------------------------------
   {
-    const int MIDMAX = 256;
-    std::vector<SolveTask> tf, tb;
-    std::vector<int> bundle, boff(S.nsn, 0);
+    std::vector<int> boff(S.nsn, 0);
     sv->shard.active = false;
     std::vector<long long> bigv_off(S.nsn, 0);
     long long bv = 0; int bo = 0;
-    for (int s = 0; s < S.nsn; ++s) if (S.f(s) > MIDMAX) {
+    for (int s = 0; s < S.nsn; ++s) if (S.f(s) > DF_MIDMAX) {
       boff[s] = bo; bo += (S.f(s) + DF_BLK - 1) / DF_BLK;
       bigv_off[s] = bv; bv += S.f(s) + (S.f(s) & 1);
-    }
-    {
-      std::vector<char> take(S.nsn, 1);
-      build_solve_tasks(S, take, tf, tb, bundle);
     }
     // explicit inverses of the big fronts' pivot blocks (k_linv_*): K64 x K64 doubles per big front
     {
       std::vector<long long> linv_off(S.nsn, -1);
       long long tot = 0;
-      for (int s = 0; s < S.nsn; ++s) if (S.f(s) > MIDMAX) {
+      for (int s = 0; s < S.nsn; ++s) if (S.f(s) > DF_MIDMAX) {
         linv_off[s] = tot;
         const long long K64 = (long long)((S.k(s) + DF_BLK - 1) / DF_BLK) * DF_BLK;
         tot += K64 * K64;
@@ -451,52 +561,40 @@ static int run_analysis(Solver* sv, const double* vals) {
       int rc2 = build_linv_plan(sv, S, take, sv->linv_plan, st);
       if (rc2 != B200LDLT_SUCCESS) return rc2;
     }
-    CU(sv->d_tasks_f.upload(tf, st));
-    CU(sv->d_tasks_b.upload(tb, st));
-    if (bundle.empty()) bundle.push_back(0);
-    CU(sv->d_bundle.upload(bundle, st));
     CU(sv->d_boff.upload(boff, st));
     CU(sv->d_bigv_off.upload(bigv_off, st));
-    CU(sv->d_done_f.alloc(S.nsn)); CU(sv->d_done_b.alloc(S.nsn)); CU(sv->d_gflag.alloc(S.nsn));
+    CU(sv->d_done_f.alloc(S.nsn)); CU(sv->d_done_b.alloc(S.nsn));
     CU(sv->d_bcnt.alloc(S.nsn)); CU(sv->d_bcnt_b.alloc(S.nsn));
     CU(sv->d_bflag_f.alloc(std::max(bo, 1))); CU(sv->d_bflag_b.alloc(std::max(bo, 1)));
     CU(sv->d_bigv.alloc(std::max<long long>(bv, 1))); CU(sv->d_bigy.alloc(std::max<long long>(bv, 1)));
     CU(sv->d_ticket.alloc(2));
     CU(cudaMemsetAsync(sv->d_done_f.p, 0, S.nsn * sizeof(int), st));
     CU(cudaMemsetAsync(sv->d_done_b.p, 0, S.nsn * sizeof(int), st));
-    CU(cudaMemsetAsync(sv->d_gflag.p, 0, S.nsn * sizeof(int), st));
     CU(cudaMemsetAsync(sv->d_bcnt.p, 0, S.nsn * sizeof(int), st));
     CU(cudaMemsetAsync(sv->d_bcnt_b.p, 0, S.nsn * sizeof(int), st));
     CU(cudaMemsetAsync(sv->d_bflag_f.p, 0, std::max(bo, 1) * sizeof(int), st));
     CU(cudaMemsetAsync(sv->d_bflag_b.p, 0, std::max(bo, 1) * sizeof(int), st));
     CU(cudaMemsetAsync(sv->d_ticket.p, 0, 2 * sizeof(unsigned long long), st));
     sv->solve_epoch = 0; sv->ticket_f = sv->ticket_b = 0;
-    DevSolve& V = sv->DV;
-    V.tasks = sv->d_tasks_f.p; V.tasks_bwd = sv->d_tasks_b.p;
-    V.ntasks_fwd = (int)tf.size(); V.ntasks_bwd = (int)tb.size();
-    V.bundle = sv->d_bundle.p; V.done_f = sv->d_done_f.p; V.done_b = sv->d_done_b.p; V.gflag = sv->d_gflag.p;
-    V.bflag_f = sv->d_bflag_f.p; V.bflag_b = sv->d_bflag_b.p; V.bcnt = sv->d_bcnt.p; V.bcnt_b = sv->d_bcnt_b.p;
-    V.boff = sv->d_boff.p; V.bigv_off = sv->d_bigv_off.p; V.bigv = sv->d_bigv.p; V.bigy = sv->d_bigy.p;
-    V.ticket = sv->d_ticket.p;
-    V.linv = sv->d_linv.p;
-    V.linv_off = sv->d_linv_off.p;
-    V.tlog = nullptr;
-    V.opts = getenv("B200_GATHER_GLOBAL") ? 1 : 0;
-    if (getenv("B200_SOLVE_TIMELINE")) {
-      CU(sv->d_tlog.alloc(2 * (tf.size() + tb.size())));
-      V.tlog = sv->d_tlog.p;
-      sv->h_tasks = tf; sv->h_tasks.insert(sv->h_tasks.end(), tb.begin(), tb.end());
+    {
+      std::vector<char> take(S.nsn, 1);
+      int rc2 = build_solve_plan(sv, S, take, sv->splan, st);
+      if (rc2 != B200LDLT_SUCCESS) return rc2;
     }
-    const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
-    CU(cudaFuncSetAttribute(k_solve_dataflow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
-    CU(cudaFuncSetAttribute(k_solve_dataflow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, df_smem));
+    if (sv->dbg.solve_timeline) {
+      CU(sv->d_tlog.alloc(2 * (size_t)(sv->splan.ntf + sv->splan.ntb) + 2));
+      sv->splan.V.tlog = sv->d_tlog.p;
+    }
     int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_dataflow<true>, DF_THREADS, df_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_top<true>, DF_THREADS, 0));
+    int occ_b = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_solve_top<false>, DF_THREADS, 0));
     CU(cudaDeviceGetAttribute(&sv->num_sms, cudaDevAttrMultiProcessorCount, sv->dev));
-    sv->df_grid = std::max(1, occ) * sv->num_sms;
+    sv->df_grid = std::max(1, std::min(occ, occ_b)) * sv->num_sms;
     if (sv->opt.verbose)
-      fprintf(stderr, "[b200ldlt] dataflow solve: %d fwd / %d bwd tasks, %d big-front blocks, grid %d x %d thr, %d B smem\n",
-              V.ntasks_fwd, V.ntasks_bwd, bo, sv->df_grid, DF_THREADS, df_smem);
+      fprintf(stderr, "[b200ldlt] solve: %d big-front blocks, top grid %d x %d thr (%d/%d CTAs per SM)\n",
+              bo, sv->df_grid, DF_THREADS, occ, occ_b);
+    CU(cudaStreamSynchronize(st));
   }
 
   b200ldlt_info& I = sv->info;
@@ -553,7 +651,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
   bool any_big = false;
   for (int l = 0; l < S.nlevels; ++l) any_big = any_big || plan[l].big_cnt > 0;
   if (any_big) {
-    cudaStream_t sz = getenv("B200_ONE_STREAM") ? st : sv->stream2;
+    cudaStream_t sz = sv->dbg.one_stream ? st : sv->stream2;
     cudaEvent_t e0 = sv->next_event();
     CU(cudaEventRecord(e0, st));
     CU(cudaStreamWaitEvent(sz, e0, 0));
@@ -573,11 +671,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       const int* bl = fl + P.big_off;
       if (!zero_waited) { CU(cudaStreamWaitEvent(st, sv->ev_zero, 0)); zero_waited = true; }
       k_big_assemble<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_entmax, 256), 64)), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
-      if (getenv("B200_EXTEND_PER_CHILD")) {
-        for (int q = 0; q < P.big_chmax; ++q) {
-          k_big_extend_add<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_fmax, 8), 128)), P.big_cnt), 256, 0, st>>>(D, N, bl, q); ++L;
-        }
-      } else if (P.big_chmax > 0) {
+      if (P.big_chmax > 0) {
         k_big_extend_all<<<dim3(cdiv(P.big_fmax, 8), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
       }
     }
@@ -585,8 +679,6 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
     for (const auto& bk : P.small) {
       if (bk.fmax <= 32) {  // one warp per front (registers), 4 fronts per CTA
         k_front_warp<<<cdiv(bk.cnt, 4), 128, 4 * XS_SMEM_PER_WARP, st>>>(D, N, fl + bk.off, bk.cnt); ++L;
-      } else if (getenv("B200_MID_PANEL")) {   // experimental panelised kernel (slower at 1 CTA/SM today; opt-in)
-        k_front_mid<<<bk.cnt, 256, mid_smem_bytes(bk.fmax), st>>>(D, N, fl + bk.off); ++L;
       } else {
         k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, st>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
       }
@@ -598,16 +690,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       // Panel pipeline on two streams (both inside the captured graph): the CHAIN  diag(p) -> trsm(p) -> diag(p+1)
       // is the critical path; the trailing update of panel p runs on the bulk stream concurrently with diag(p+1),
       // which applies panel p's rank-32 update to its own 32x32 block itself.
-      cudaStream_t sb = getenv("B200_ONE_STREAM") ? st : sv->stream2;
-      // opt-in (B200_SCHUR_FUSED=1): per-panel rank-32 updates of the contribution block on a third stream instead of
-      // one Schur GEMM per level; measured equal within noise at N=400 (7.61 vs 7.57 ms), so the single GEMM stays default
-      const bool fused_cb = getenv("B200_SCHUR_FUSED") && atoi(getenv("B200_SCHUR_FUSED")) != 0;
-      cudaStream_t sc = getenv("B200_ONE_STREAM") ? st : sv->stream3;
-      if (fused_cb) {
-        cudaEvent_t e = sv->next_event();
-        CU(cudaEventRecord(e, st));
-        CU(cudaStreamWaitEvent(sc, e, 0));
-      }
+      cudaStream_t sb = sv->dbg.one_stream ? st : sv->stream2;
       {
         cudaEvent_t e = sv->next_event();
         CU(cudaEventRecord(e, st));
@@ -625,12 +708,6 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaEventRecord(et, sb));
         CU(cudaStreamWaitEvent(st, et, 0));      // diag(p+1) needs L/W of its own rows from trsm(p)
         int rem_k = P.big_kmax - jb - NB;
-        if (fused_cb && P.big_rmax > 0) {
-          // the panel's rank-nb update of the contribution block runs on a third stream: it only needs trsm(p) and
-          // the previous CB update, so it trails behind the chain instead of a Schur GEMM at the end of the level
-          CU(cudaStreamWaitEvent(sc, et, 0));
-          k_big_update<<<dim3(cdiv(P.big_rmax, TM) + 1, cdiv(P.big_rmax, TM) + 1, P.big_cnt), 256, 0, sc>>>(D, N, bl, jb, 2); ++L;
-        }
         if (rem_k > 0) {
           k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, sb>>>(D, N, bl, jb, 0); ++L;
         }
@@ -640,22 +717,9 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaEventRecord(e, sb));
         CU(cudaStreamWaitEvent(st, e, 0));
       }
-      if (fused_cb) {
-        cudaEvent_t e = sv->next_event();
-        CU(cudaEventRecord(e, sc));
-        CU(cudaStreamWaitEvent(st, e, 0));
-      }
       sv->mark("big-chain", l);
-      if (P.big_rmax > 0 && !fused_cb) {
-        if (!getenv("B200_SCHUR_44") && !getenv("B200_SCHUR_DMMA")) {   // default: 8x4 register-blocked DFMA tiles
-          k_big_schur84<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 128, 0, st>>>(D, N, bl); ++L;
-        } else if (!getenv("B200_SCHUR_DMMA")) {
-          k_big_schur<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
-        } else {   // FP64 tensor-pipe (DMMA) contraction, 128x128 tiles: opt-in - measured 2-3 % SLOWER than the 64x64
-                   // DFMA tiles at these front sizes (r <= ~1500: too few 128x128 tiles to fill 148 SMs; B200's FP64
-                   // DMMA and DFMA peaks are equal), see profiles/r1_summary.md
-          k_big_schur_dmma<<<dim3(cdiv(P.big_rmax, DM_T), cdiv(P.big_rmax, DM_T), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
-        }
+      if (P.big_rmax > 0) {   // Schur complement CB -= L21 (L21 D)^T
+        k_big_schur84<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 128, 0, st>>>(D, N, bl); ++L;
       }
     }
   }
@@ -696,6 +760,7 @@ static int finish_factor(Solver* sv, int check_inertia, int expected_neg, int* n
   b200ldlt_info& I = sv->info;
   I.ms_factor_gpu = ms;
   I.launches_factor = sv->launches;
+  ++sv->n_factor;
   I.num_neg = sv->h_counters[CNT_NEG];
   I.num_forced = sv->h_counters[CNT_FORCED];
   I.num_tiny = sv->h_counters[CNT_TINY];
@@ -703,7 +768,10 @@ static int finish_factor(Solver* sv, int check_inertia, int expected_neg, int* n
   I.num_2x2 = sv->h_counters[CNT_2X2];
   sv->num_neg = I.num_neg;
   if (num_neg) *num_neg = I.num_neg;
-  sv->factored = true;
+  // Factors of a matrix with a noise pivot (SINGULAR) are not offered to the solves.  With num_forced > 0 the factors
+  // (and the inertia reported) are those of a matrix perturbed by <= 1e-8 |column| in the lifted pivots; the count is
+  // surfaced in b200ldlt_info and drives increase_quality (re-analysis with the current values).
+  sv->factored = (I.num_tiny == 0);
   if (sv->opt.verbose > 1)
     fprintf(stderr, "[b200ldlt] factor: %.3f ms, %d launches, neg=%d 2x2=%d forced=%d tiny=%d growth=%d (u=%g)\n", ms,
             sv->launches, I.num_neg, I.num_2x2, I.num_forced, I.num_tiny, I.num_growth, sv->pivtol);
@@ -712,12 +780,14 @@ static int finish_factor(Solver* sv, int check_inertia, int expected_neg, int* n
   return B200LDLT_SUCCESS;
 }
 
-static int do_factor(Solver* sv, const double* d_vals_ext, bool from_host, int check_inertia, int expected_neg,
+static int do_factor(Solver* sv, const double* d_vals_ext_in, bool from_host, int check_inertia, int expected_neg,
                      int* num_neg) {
+  const double* d_vals_ext = d_vals_ext_in;
   if (num_neg) *num_neg = -1;
   if (sv->n <= 0) { sv->err = "factor before analyse"; return B200LDLT_FATAL_ERROR; }
   CU(cudaSetDevice(sv->dev));
-  if (!sv->analysed) {
+  if (!sv->analysed || sv->reanalyse) {
+    if (sv->analysed) ++sv->n_reanalysed;
     std::vector<double> hv;
     const double* vals = sv->h_vals;
     if (!from_host && d_vals_ext) {
@@ -727,6 +797,11 @@ static int do_factor(Solver* sv, const double* d_vals_ext, bool from_host, int c
     }
     int rc = run_analysis(sv, vals);
     if (rc != B200LDLT_SUCCESS) return rc;
+    if (!from_host && d_vals_ext) {
+      // the analysis re-allocated the device value array (d_vals_ext may have been that very array): restore it
+      CU(cudaMemcpy(sv->d_vals.p, hv.data(), sv->nnz * sizeof(double), cudaMemcpyHostToDevice));
+      d_vals_ext = sv->d_vals.p;
+    }
   }
   cudaStream_t st = sv->stream;
   CU(cudaEventRecord(sv->ev0, st));
@@ -760,27 +835,50 @@ static int do_factor(Solver* sv, const double* d_vals_ext, bool from_host, int c
   return finish_factor(sv, check_inertia, expected_neg, num_neg);
 }
 
+__global__ void k_mark_flags(int* flags, const int* __restrict__ list, int n, int value) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[list[i]] = value;
+}
+
+// one sweep over the fronts of a plan: forward = subtrees then top, backward = top then subtrees
+static int launch_sweep(Solver* sv, const SolvePlan& SP, bool fwd) {
+  cudaStream_t st = sv->stream;
+  const DevSolve& V = SP.V;
+  const int nt = fwd ? SP.ntf : SP.ntb;
+  const int grid = std::min(sv->df_grid, std::max(nt, 1));
+  if (fwd) {
+    if (SP.nsub > 0) { k_solve_sub<true><<<SP.nsub, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->d_x.p, sv->d_cbv.p); ++sv->launches; }
+    if (nt > 0) {
+      k_solve_top<true><<<grid, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p); ++sv->launches;
+      sv->ticket_f += (unsigned long long)nt + grid;
+    }
+  } else {
+    if (nt > 0) {
+      k_solve_top<false><<<grid, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p); ++sv->launches;
+      sv->ticket_b += (unsigned long long)nt + grid;
+    }
+    if (SP.nsub > 0) { k_solve_sub<false><<<SP.nsub, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->d_x.p, sv->d_cbv.p); ++sv->launches; }
+  }
+  CU(cudaGetLastError());
+  return B200LDLT_SUCCESS;
+}
+
 static int enqueue_solve(Solver* sv, const double* d_b, double* d_out) {
   Symbolic& S = sv->S;
   cudaStream_t st = sv->stream;
   const int n = S.n;
-  const int* fl = sv->d_front_list.p;
   int& L = sv->launches;
   k_rhs_in<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, d_b, sv->d_x.p); ++L;
-  if (sv->opt.use_graph != 2) {   // default: persistent dataflow sweeps (use_graph == 2 selects the level-per-launch kernels)
-    const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
+  if (sv->opt.use_graph != 2) {   // default: subtree + task-queue sweeps (use_graph == 2 selects the level-per-launch kernels)
     sv->solve_epoch++;
-    const DevSolve& V = sv->DV;
-    k_solve_dataflow<true><<<std::min(sv->df_grid, std::max(V.ntasks_fwd, 1)), DF_THREADS, df_smem, st>>>(
-        sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p); ++L;
-    sv->ticket_f += (unsigned long long)V.ntasks_fwd + std::min(sv->df_grid, std::max(V.ntasks_fwd, 1));
-    k_solve_dataflow<false><<<std::min(sv->df_grid, std::max(V.ntasks_bwd, 1)), DF_THREADS, df_smem, st>>>(
-        sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p); ++L;
-    sv->ticket_b += (unsigned long long)V.ntasks_bwd + std::min(sv->df_grid, std::max(V.ntasks_bwd, 1));
+    int rc = launch_sweep(sv, sv->splan, true);
+    if (rc == B200LDLT_SUCCESS) rc = launch_sweep(sv, sv->splan, false);
+    if (rc != B200LDLT_SUCCESS) return rc;
     k_sol_out<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, sv->d_x.p, d_out); ++L;
     CU(cudaGetLastError());
     return B200LDLT_SUCCESS;
   }
+  const int* fl = sv->d_front_list.p;
   for (int l = 0; l < S.nlevels; ++l) {
     const LevelPlan& P = sv->plan[l];
     int threads = P.fmax <= 64 ? 64 : (P.fmax <= 256 ? 256 : 1024);
@@ -792,30 +890,6 @@ static int enqueue_solve(Solver* sv, const double* d_b, double* d_out) {
     k_bwd_front<<<P.all_cnt, threads, (size_t)P.fmax * sizeof(double), st>>>(sv->DS, sv->DN, fl + P.all_off, sv->d_x.p); ++L;
   }
   k_sol_out<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, sv->d_x.p, d_out); ++L;
-  CU(cudaGetLastError());
-  return B200LDLT_SUCCESS;
-}
-
-
-__global__ void k_mark_flags(int* flags, const int* __restrict__ list, int n, int value) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[list[i]] = value;
-}
-
-static int launch_dataflow(Solver* sv, const DevSolve& V, bool fwd) {
-  cudaStream_t st = sv->stream;
-  const int df_smem = 8 * DF_SMALL_SMEM * (int)sizeof(double);
-  const int nt = fwd ? V.ntasks_fwd : V.ntasks_bwd;
-  if (nt <= 0) return B200LDLT_SUCCESS;
-  const int grid = std::min(sv->df_grid, nt);
-  if (fwd) {
-    k_solve_dataflow<true><<<grid, DF_THREADS, df_smem, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p);
-    sv->ticket_f += (unsigned long long)nt + grid;
-  } else {
-    k_solve_dataflow<false><<<grid, DF_THREADS, df_smem, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p);
-    sv->ticket_b += (unsigned long long)nt + grid;
-  }
-  ++sv->launches;
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;
 }
@@ -839,26 +913,12 @@ static int shard_setup(Solver* sv, int rank, int world) {
     }
   }
   for (int ph = 0; ph < 2; ++ph) {
-    std::vector<int> fl, bundle;
-    std::vector<SolveTask> tf, tb;
-    build_level_plans(S, sv->opt.smem_front_max, take[ph], fl, H.plan[ph]);
-    build_solve_tasks(S, take[ph], tf, tb, bundle);
+    std::vector<int> fl;
+    build_level_plans(S, sv->opt.smem_front_max, take[ph], fl, H.plan[ph], sv->dbg.buckets);
     { int rc2 = build_linv_plan(sv, S, take[ph], H.linv_plan[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
+    { int rc2 = build_solve_plan(sv, S, take[ph], H.splan[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
     if (fl.empty()) fl.push_back(0);
-    if (bundle.empty()) bundle.push_back(0);
-    if (tf.empty()) tf.push_back({ST_SMALL, 0, 0, 0});
-    const int ntf = (int)tf.size() - ((tf.size() == 1 && tf[0].b == 0 && tf[0].type == ST_SMALL) ? 1 : 0);
-    if (tb.empty()) tb.push_back({ST_SMALL, 0, 0, 0});
-    const int ntb = (int)tb.size() - ((tb.size() == 1 && tb[0].b == 0 && tb[0].type == ST_SMALL) ? 1 : 0);
     CU(H.d_fl[ph].upload(fl, st));
-    CU(H.d_bundle[ph].upload(bundle, st));
-    CU(H.d_tf[ph].upload(tf, st));
-    CU(H.d_tb[ph].upload(tb, st));
-    H.DV[ph] = sv->DV;
-    H.DV[ph].tasks = H.d_tf[ph].p; H.DV[ph].tasks_bwd = H.d_tb[ph].p;
-    H.DV[ph].ntasks_fwd = ntf; H.DV[ph].ntasks_bwd = ntb;
-    H.DV[ph].bundle = H.d_bundle[ph].p;
-    H.DV[ph].tlog = nullptr;
   }
   if (mark_cut.empty()) mark_cut.push_back(0), H.d_mark_cut.n = 0;
   {
@@ -907,6 +967,7 @@ b200ldlt_handle b200ldlt_create(const b200ldlt_options* opt) {
   if (sv->opt.smem_front_max > 160) sv->opt.smem_front_max = 160;
   if (sv->opt.smem_front_max < 8) sv->opt.smem_front_max = 8;
   sv->pivtol = sv->opt.pivtol;
+  sv->dbg.read();
   memset(&sv->info, 0, sizeof(sv->info));
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1042,15 +1103,15 @@ int b200ldlt_solve(b200ldlt_handle h, int nrhs, double* rhs) {
 /* debug: write the per-task timeline of the last solve (needs env B200_SOLVE_TIMELINE=1 at analyse time) */
 int b200ldlt_dump_solve_timeline(b200ldlt_handle h, const char* path) {
   Solver* sv = (Solver*)h;
-  if (!sv || !sv->DV.tlog) return B200LDLT_FATAL_ERROR;
+  if (!sv || !sv->splan.V.tlog) return B200LDLT_FATAL_ERROR;
   std::vector<unsigned long long> t(sv->d_tlog.n);
   CU(cudaMemcpy(t.data(), sv->d_tlog.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   FILE* fp = fopen(path, "w");
   if (!fp) return B200LDLT_FATAL_ERROR;
   for (size_t i = 0; i < sv->h_tasks.size(); ++i) {
     const SolveTask& T = sv->h_tasks[i];
-    int s = T.type == ST_SMALL ? -1 : T.a;
-    fprintf(fp, "%zu %d %d %d %d %d %llu %llu\n", i, i < (size_t)sv->DV.ntasks_fwd ? 0 : 1, T.type, T.a, T.b,
+    int s = T.type == ST_SMALL ? -1 : T.s;
+    fprintf(fp, "%zu %d %d %d %d %d %llu %llu\n", i, i < (size_t)sv->splan.ntf ? 0 : 1, T.type, T.s, T.blk,
             s >= 0 ? sv->S.sn_level[s] : -1, t[2 * i], t[2 * i + 1]);
   }
   fclose(fp);
@@ -1124,7 +1185,7 @@ int b200ldlt_shard_factor_finish(b200ldlt_handle h, const int* counters_total, i
   I.num_growth = counters_total[CNT_GROWTH]; I.num_2x2 = counters_total[CNT_2X2];
   sv->num_neg = I.num_neg;
   if (num_neg) *num_neg = I.num_neg;
-  sv->factored = true;
+  sv->factored = (I.num_tiny == 0);
   if (I.num_tiny > 0) return B200LDLT_SINGULAR;
   if (check_inertia && I.num_neg != expected_neg) return B200LDLT_WRONG_INERTIA;
   return B200LDLT_SUCCESS;
@@ -1144,14 +1205,14 @@ int b200ldlt_shard_solve(b200ldlt_handle h, int phase, double* d_rhs) {
     sv->launches = 0;
     k_rhs_in<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, d_rhs, sv->d_x.p);
     sv->solve_epoch++;
-    rc = launch_dataflow(sv, H.DV[0], true);
+    rc = launch_sweep(sv, H.splan[0], true);
   } else if (phase == 1) {
     if (H.d_mark_cut.n) k_mark_flags<<<cdiv((long long)H.d_mark_cut.n, 256), 256, 0, st>>>(sv->d_done_f.p, H.d_mark_cut.p, (int)H.d_mark_cut.n, sv->solve_epoch);
-    rc = launch_dataflow(sv, H.DV[1], true);
-    if (rc == B200LDLT_SUCCESS) rc = launch_dataflow(sv, H.DV[1], false);
+    rc = launch_sweep(sv, H.splan[1], true);
+    if (rc == B200LDLT_SUCCESS) rc = launch_sweep(sv, H.splan[1], false);
   } else if (phase == 2) {
     if (H.rank != 0 && H.d_mark_top.n) k_mark_flags<<<cdiv((long long)H.d_mark_top.n, 256), 256, 0, st>>>(sv->d_done_b.p, H.d_mark_top.p, (int)H.d_mark_top.n, sv->solve_epoch);
-    rc = launch_dataflow(sv, H.DV[0], false);
+    rc = launch_sweep(sv, H.splan[0], false);
   } else if (phase == 3) {
     k_sol_out<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_perm.p, sv->d_scale.p, sv->d_x.p, d_rhs);
   } else return B200LDLT_FATAL_ERROR;
@@ -1164,9 +1225,26 @@ int b200ldlt_num_neg(b200ldlt_handle h) { return h ? ((Solver*)h)->num_neg : -1;
 int b200ldlt_increase_quality(b200ldlt_handle h) {
   Solver* sv = (Solver*)h;
   if (!sv) return 0;
+  // The last factorisation lifted pivots (num_forced) or saw growth beyond 1/u: a larger threshold would only reject
+  // more pivots inside the same supernodes.  The pairing / ordering were frozen on the values of the FIRST matrix; redo
+  // the analysis on the current values instead (once per matrix: the second request raises the threshold as usual).
+  if ((sv->info.num_forced > 0 || sv->info.num_growth > 0) && sv->analysed && !sv->shard.active && !sv->reanalysed_since_raise) {
+    sv->reanalyse = true;
+    sv->reanalysed_since_raise = true;
+    return 1;
+  }
   if (sv->pivtol >= sv->opt.pivtolmax) return 0;
   sv->pivtol = std::min(sv->opt.pivtolmax, std::pow(sv->pivtol, 0.75));
+  sv->reanalysed_since_raise = false;
   return 1;
+}
+
+int b200ldlt_set_pivtol(b200ldlt_handle h, double pivtol, double pivtolmax) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !(pivtol > 0.0) || !(pivtolmax >= pivtol)) return B200LDLT_FATAL_ERROR;
+  sv->opt.pivtol = pivtol; sv->opt.pivtolmax = pivtolmax;
+  sv->pivtol = pivtol;
+  return B200LDLT_SUCCESS;
 }
 
 int b200ldlt_get_info(b200ldlt_handle h, b200ldlt_info* info) {

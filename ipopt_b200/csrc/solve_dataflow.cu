@@ -1,13 +1,22 @@
-// Persistent dataflow triangular solve (forward L, D^-1, backward L^T) -- ONE kernel per sweep.
+// Supernodal triangular solve (forward L, D^-1, backward L^T): TWO kernels per sweep.
 //
-// The level-per-launch version (solve_kernels.cu) spends its time in launch gaps and in single-CTA big
-// fronts.  Here every front (or 64-row / 64-column block of a big front) is a TASK in a topologically
-// sorted list; persistent CTAs take tasks with an atomic ticket and wait for their producers through
-// acquire/release flags in global memory.  A task only ever waits for tasks that precede it in the list,
-// and every ticket is held by a resident CTA, so the scheme cannot deadlock.  L is streamed exactly once
-// per sweep (HBM-bound, SURVEY.md 8d: 2*8*nnz(L) bytes per right-hand side); no atomics on the data path
-// (children -> parent through per-front update vectors gathered by the parent), so results are
-// bit-reproducible.  Replaces the vendor back-solve of the reference (MUMPS job=3,
+//   k_solve_sub<FWD> : the BOTTOM of the elimination tree.  The tree below the big separator fronts is cut into
+//                      subtrees of bounded size (bytes of L, number of fronts, front order <= 256); ONE CTA walks one
+//                      subtree level by level -- fronts of order <= 64 one warp each, larger ones by the whole CTA --
+//                      with CTA barriers only: no global flags, no tickets, no atomics.  Subtrees are launched largest
+//                      first (the hardware block scheduler then does LPT scheduling).
+//   k_solve_top<FWD> : everything above the subtrees: a persistent task-queue kernel.  Fronts up to order 256 are one
+//                      task each; a front larger than that is cut into (64-row block) x (4-tile chunk) GEMV tasks on the
+//                      EXPLICIT inverse of its pivot block (k_linv_*), so a separator front of order 1000+ keeps ~50
+//                      CTAs busy instead of a chain of block steps.  A task waits for its producers through
+//                      ld.acquire/st.release flags; it only ever waits for tasks EARLIER in the (topologically sorted)
+//                      list and every ticket holder is resident, so the scheme cannot deadlock.  Chunk partials are
+//                      combined by the last-arriving CTA in chunk order (fence + counter), so results do not depend on
+//                      arrival order: bit-reproducible.
+// Forward: sub then top; backward: top then sub (the kernel boundary is the only synchronisation between the two).
+// L is streamed exactly once per sweep (HBM-bound, SURVEY.md 8d: 2*8*nnz(L) bytes per right-hand side); children ->
+// parent data flows through per-front update vectors gathered by the parent (no atomics on the data path).
+// Replaces the vendor back-solve of the reference (MUMPS job=3,
 // reference src/Algorithm/LinearSolvers/IpMumpsSolverInterface.cpp:543-583).
 #include <cuda_runtime.h>
 #include <math.h>
@@ -17,34 +26,48 @@
 namespace b200 {
 
 #define DF_THREADS 256
-#define DF_BLK 64          // block-row / block-column size of the big-front tasks
-#define DF_SMALL_SMEM (33 * 32 + 64)   // doubles per warp for a small front
+#define DF_BLK 64            // block-row / block-column size of the big-front tasks
+#define DF_CH 4              // 64x64 tiles per chunk task
+#define DF_MIDMAX 256        // fronts above this order are "big" (block tasks + explicit L11 inverse)
+#define DF_SMEM_DOUBLES 1600 // max(mid front: 2*256 + 32*33 = 1568, big task: 256 + 256 + 64 + 128 + 64 = 768)
 
-enum { ST_SMALL = 0, ST_MID = 1, ST_BIG_GATHER = 2, ST_BIG_BLOCK = 3 };
+enum { ST_SMALL = 0, ST_MID = 1, ST_FP = 2, ST_FC = 3, ST_BT = 4, ST_BX = 5 };
 
-struct SolveTask { int type, a, b, c; };
+// ST_SMALL : s = offset into bundle[], blk = number of fronts (<= 8, one warp each, order <= 64)
+// ST_MID   : s = front
+// ST_FP/FC/BT/BX : s = front, blk = 64-block, tiles [t0, t1) of the contraction, chunk q of nq,
+//                  pbase = first partial slot of (s, kind, blk), cidx = its arrival counter
+struct SolveTask { int type, s, blk, t0, t1, q, nq, pbase, cidx, pad; };
 
 struct DevSolve {
-  const SolveTask* tasks;      // forward list
+  const SolveTask* tasks;      // forward list (top part)
   const SolveTask* tasks_bwd;  // backward list
   int ntasks_fwd, ntasks_bwd;
   const int* bundle;           // front ids of the small bundles
   int* done_f;                 // nsn : epoch when the forward work of a front is complete
   int* done_b;                 // nsn : same for backward
-  int* gflag;                  // nsn : big-front gather done
-  int* bflag_f;                // per (big front, block): y block published
-  int* bflag_b;                // per (big front, block): x block published
-  int* bcnt;                   // nsn : finished forward block counter (monotonic)
-  int* bcnt_b;                 // nsn : finished backward block counter (monotonic)
+  int* bflag_f;                // per (big front, pivot block): y block published
+  int* bflag_b;                // per (big front, pivot block): t block published
+  int* bcnt;                   // nsn : finished contribution-row blocks (monotonic)
+  int* bcnt_b;                 // nsn : finished backward x blocks (monotonic)
   const int* boff;             // nsn : offset of a big front's blocks in bflag_*
-  const long long* bigv_off;   // nsn : offset into bigv (f doubles) / bigy (k doubles at the same offset)
-  double* bigv;                // assembled+permuted rhs of big fronts
-  double* bigy;                // y / x blocks of big fronts in pivoted order
+  const long long* bigv_off;   // nsn : offset into bigv / bigy (f doubles per big front)
+  double* bigv;                // big fronts: z = D^-1 y (forward), then t (backward), pivoted order
+  double* bigy;                // big fronts: y (forward), pivoted order
+  double* part;                // chunk partials, 64 doubles per slot
+  int* ccnt;                   // chunk arrival counters (monotonic, modulo nq)
   unsigned long long* ticket;  // [0] fwd, [1] bwd (monotonic)
   const double* linv;          // explicit inverses of the big fronts' pivot blocks L11 (K64 x K64 each, see k_linv_*)
   const long long* linv_off;   // nsn : offset of a big front's inverse in linv, -1 = none
-  unsigned long long* tlog;    // optional (debug): 2 timestamps per task, fwd then bwd; nullptr = off
-  int opts;                    // bit 0: gather through global memory (debug / comparison)
+  // subtrees (k_solve_sub): subtree u owns levels [sub_ptr[u], sub_ptr[u+1]) of lvl_*; level e owns the fronts
+  // sub_fronts[lvl_ptr[e] .. lvl_ptr[e+1]) -- the first lvl_nsmall[e] of them have order <= 64
+  const int* sub_ptr;
+  const int* lvl_ptr;
+  const int* lvl_nsmall;
+  const int* sub_fronts;
+  const int* sub_root;         // root front of each subtree (its done_f is published for the top kernel)
+  int nsub;
+  unsigned long long* tlog;    // optional (debug): 2 timestamps per top task, fwd then bwd; nullptr = off
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -56,137 +79,100 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void wait_eq(const int* p, int epoch) {
-  while (ld_acquire(p) != epoch) __nanosleep(32);
+  while (ld_acquire(p) != epoch) __nanosleep(20);
 }
 
 // ------------------------------------------------------------------------------------------------
-// small fronts (order <= 32): one warp per front, panel staged in shared memory
-// ------------------------------------------------------------------------------------------------
-__device__ void small_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
-                          double* __restrict__ x, double* __restrict__ cbv) {
-  const int lane = threadIdx.x & 31;
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const long long ro = S.rows_ptr[s];
-  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
-  double* Ls = sm;            // f x k, ld 33
-  double* w = sm + 33 * 32;   // 32
-  const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
-  // stage the panel first: it does not depend on the children
-  const double* __restrict__ P = N.L + S.L_off[s];
-  for (int tb = 0; tb < k; tb += 8) {   // 8 independent loads in flight per lane
-    double tmp[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) tmp[q] = (lane < f && tb + q < k) ? P[lane + (size_t)(tb + q) * f] : 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) if (tb + q < k) Ls[lane + (tb + q) * 33] = tmp[q];
-  }
-  w[lane] = (lane < k) ? x[c0 + lane] : 0.0;
-  for (int q = ch0 + lane; q < ch1; q += 32) wait_eq(V.done_f + S.child_idx[q], epoch);
-  __syncwarp();
-  for (int q = ch0; q < ch1; ++q) {
-    const int c = S.child_idx[q];
-    const long long o = S.rows_ptr[c];
-    const int rc = (int)(S.rows_ptr[c + 1] - o);
-    if (lane < rc) w[S.rel[o + lane]] += __ldcg(cbv + o + lane);
-    __syncwarp();
-  }
-  double v = 0.0;
-  if (lane < f) v = (lane < k) ? w[N.lperm[c0 + lane]] : w[lane];
-  for (int t = 0; t < k; ++t) {
-    const double yt = __shfl_sync(0xffffffffu, v, t);
-    if (lane > t && lane < f) v = fma(-Ls[lane + t * 33], yt, v);
-  }
-  // D^-1 (2x2 partners are neighbouring lanes)
-  const double vn = __shfl_down_sync(0xffffffffu, v, 1), vp = __shfl_up_sync(0xffffffffu, v, 1);
-  if (lane < k) {
-    const int ty = N.ptype[c0 + lane];
-    double y;
-    if (ty == 1) y = v * N.dinv[c0 + lane];
-    else if (ty == 2) y = v * N.dinv[c0 + lane] + vn * N.doff[c0 + lane];
-    else y = vp * N.doff[c0 + lane - 1] + v * N.dinv[c0 + lane];
-    x[c0 + lane] = y;
-  } else if (lane < f) cbv[ro + lane - k] = v;
-  __syncwarp();
-  if (lane == 0) { st_release(V.done_f + s, epoch); }
-}
-
-__device__ void small_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
-                          double* __restrict__ x) {
-  const int lane = threadIdx.x & 31;
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const long long ro = S.rows_ptr[s];
-  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
-  double* Ls = sm;
-  const double* __restrict__ P = N.L + S.L_off[s];
-  for (int tb = 0; tb < k; tb += 8) {   // 8 independent loads in flight per lane
-    double tmp[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) tmp[q] = (lane < f && tb + q < k) ? P[lane + (size_t)(tb + q) * f] : 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) if (tb + q < k) Ls[lane + (tb + q) * 33] = tmp[q];
-  }
-  const int par = S.sn_parent[s];
-  if (par >= 0 && lane == 0) wait_eq(V.done_b + par, epoch);
-  __syncwarp();
-  double v = 0.0;  // lane i holds entry i of [D^-1 y ; x(rows)]
-  if (lane < k) v = x[c0 + lane];
-  else if (lane < f) v = __ldcg(x + S.rows[ro + lane - k]);
-  // columns from the last to the first: v_t -= sum_{i>t} L[i,t] v_i.  Lane t owns column t.
-  for (int i = f - 1; i >= 1; --i) {
-    const double vi = __shfl_sync(0xffffffffu, v, i);
-    if (lane < i && lane < k) v = fma(-Ls[i + lane * 33], vi, v);
-  }
-  if (lane < k) x[c0 + N.lperm[c0 + lane]] = v;
-  __syncwarp();
-  if (lane == 0) { st_release(V.done_b + s, epoch); }
-}
-
-// ------------------------------------------------------------------------------------------------
-// fronts of order 33..64: one warp per front, two rows per lane (lane, lane+32), no shared-memory staging:
-// the L loads do not depend on the running vector, so they are issued ahead of the shuffle chain.
+// fronts of order <= 64: one warp per front, two rows per lane (lane, lane+32), L streamed straight from global
+// memory: the loads do not depend on the running vector, so 16 columns are always in flight ahead of the shuffle chain.
+// FLAGS = true : top kernel (wait for the children / the parent, publish done flags)
+// FLAGS = false: subtree kernel (ordering comes from CTA barriers)
 // smem per warp: w[64]
 // ------------------------------------------------------------------------------------------------
-__device__ void w64_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+__device__ __forceinline__ void w64_load8(const double* __restrict__ P, int f, int k, int i0, int i1, int tb,
+                                          double (&l0)[8], double (&l1)[8]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int t = tb + q;
+    l0[q] = (t < k && i0 > t && i0 < f) ? P[i0 + (size_t)t * f] : 0.0;
+    l1[q] = (t < k && i1 > t && i1 < f) ? P[i1 + (size_t)t * f] : 0.0;
+  }
+}
+__device__ __forceinline__ void w64_fstep8(int k, int tb, const double (&l0)[8], const double (&l1)[8], double& v0,
+                                           double& v1) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int t = tb + q;
+    if (t < k) {   // warp-uniform
+      const double yt = (t < 32) ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
+      v0 = fma(-l0[q], yt, v0);
+      v1 = fma(-l1[q], yt, v1);
+    }
+  }
+}
+
+template <bool FLAGS>
+__device__ void w64_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* w,
                         double* __restrict__ x, double* __restrict__ cbv) {
   const int lane = threadIdx.x & 31;
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   const long long ro = S.rows_ptr[s];
   const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
-  double* w = sm;  // 64
-  const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
+  const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
   const int i0 = lane, i1 = lane + 32;
+  const double* __restrict__ P = N.L + S.L_off[s];
+  double a0[8], a1[8], b0[8], b1[8];
+  w64_load8(P, f, k, i0, i1, 0, a0, a1);            // in flight while the children are gathered
   w[i0] = (i0 < k) ? x[c0 + i0] : 0.0;
   w[i1] = (i1 < k) ? x[c0 + i1] : 0.0;
-  for (int q = ch0 + lane; q < ch1; q += 32) wait_eq(V.done_f + S.child_idx[q], epoch);
   __syncwarp();
-  for (int q = ch0; q < ch1; ++q) {
-    const int c = S.child_idx[q];
-    const long long o = S.rows_ptr[c];
-    const int rc = (int)(S.rows_ptr[c + 1] - o);
-    for (int t = lane; t < rc; t += 32) w[S.rel[o + t]] += __ldcg(cbv + o + t);
+  for (int q0 = 0; q0 < nch; q0 += 32) {
+    // child metadata lane-parallel, then the children one after the other (their targets may overlap); the
+    // (index, value) pairs of child q+1 are in flight while child q is added
+    const int m = min(32, nch - q0);
+    int cq = -1, rq = 0;
+    long long oq = 0;
+    if (lane < m) {
+      cq = S.child_idx[ch0 + q0 + lane];
+      oq = S.rows_ptr[cq];
+      rq = (int)(S.rows_ptr[cq + 1] - oq);
+      if (FLAGS) wait_eq(V.done_f + cq, epoch);
+    }
     __syncwarp();
+    int nidx0 = 0, nidx1 = 0;
+    double nval0 = 0.0, nval1 = 0.0;
+    bool nok0 = false, nok1 = false;
+    {
+      const long long o = __shfl_sync(0xffffffffu, oq, 0);
+      const int rc = __shfl_sync(0xffffffffu, rq, 0);
+      nok0 = lane < rc; nok1 = lane + 32 < rc;
+      if (nok0) { nidx0 = S.rel[o + lane]; nval0 = __ldcg(cbv + o + lane); }
+      if (nok1) { nidx1 = S.rel[o + lane + 32]; nval1 = __ldcg(cbv + o + lane + 32); }
+    }
+    for (int q = 0; q < m; ++q) {
+      const int idx0 = nidx0, idx1 = nidx1;
+      const double val0 = nval0, val1 = nval1;
+      const bool ok0 = nok0, ok1 = nok1;
+      if (q + 1 < m) {
+        const long long o = __shfl_sync(0xffffffffu, oq, q + 1);
+        const int rc = __shfl_sync(0xffffffffu, rq, q + 1);
+        nok0 = lane < rc; nok1 = lane + 32 < rc;
+        if (nok0) { nidx0 = S.rel[o + lane]; nval0 = __ldcg(cbv + o + lane); }
+        if (nok1) { nidx1 = S.rel[o + lane + 32]; nval1 = __ldcg(cbv + o + lane + 32); }
+      }
+      if (ok0) w[idx0] += val0;   // rel is strictly increasing inside a child: no two lanes hit the same entry
+      if (ok1) w[idx1] += val1;
+      __syncwarp();
+    }
   }
   double v0 = 0.0, v1 = 0.0;
   if (i0 < f) v0 = (i0 < k) ? w[N.lperm[c0 + i0]] : w[i0];
   if (i1 < f) v1 = (i1 < k) ? w[N.lperm[c0 + i1]] : w[i1];
-  const double* __restrict__ P = N.L + S.L_off[s];
-  for (int tb = 0; tb < k; tb += 8) {
-    double l0[8], l1[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int t = tb + q;
-      l0[q] = (t < k && i0 > t && i0 < f) ? P[i0 + (size_t)t * f] : 0.0;
-      l1[q] = (t < k && i1 > t && i1 < f) ? P[i1 + (size_t)t * f] : 0.0;
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int t = tb + q;
-      if (t < k) {
-        const double yt = (t < 32) ? __shfl_sync(0xffffffffu, v0, t) : __shfl_sync(0xffffffffu, v1, t - 32);
-        v0 = fma(-l0[q], yt, v0);
-        v1 = fma(-l1[q], yt, v1);
-      }
-    }
+  for (int tb = 0; tb < k; tb += 16) {
+    if (tb + 8 < k) w64_load8(P, f, k, i0, i1, tb + 8, b0, b1);
+    w64_fstep8(k, tb, a0, a1, v0, v1);
+    if (tb + 16 < k) w64_load8(P, f, k, i0, i1, tb + 16, a0, a1);
+    if (tb + 8 < k) w64_fstep8(k, tb + 8, b0, b1, v0, v1);
   }
   // D^-1: partner values through shared memory (w is free now)
   __syncwarp();
@@ -206,10 +192,46 @@ __device__ void w64_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
     } else if (i < f) cbv[ro + i - k] = v;
   }
   __syncwarp();
-  if (lane == 0) { st_release(V.done_f + s, epoch); }
+  if (FLAGS && lane == 0) st_release(V.done_f + s, epoch);
 }
 
-__device__ void w64_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
+// sum over the 32 lanes of p[t], t = 0..31: lane t receives the total of column t (31 shuffles instead of 32 x 5)
+__device__ __forceinline__ double warp_transpose_reduce(double (&p)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool hi = lane & 16;
+    const double send = hi ? p[j] : p[j + 16], keep = hi ? p[j + 16] : p[j];
+    p[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool hi = lane & 8;
+    const double send = hi ? p[j] : p[j + 8], keep = hi ? p[j + 8] : p[j];
+    p[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool hi = lane & 4;
+    const double send = hi ? p[j] : p[j + 4], keep = hi ? p[j + 4] : p[j];
+    p[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const bool hi = lane & 2;
+    const double send = hi ? p[j] : p[j + 2], keep = hi ? p[j + 2] : p[j];
+    p[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool hi = lane & 1;
+    const double send = hi ? p[0] : p[1], keep = hi ? p[1] : p[0];
+    p[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return p[0];
+}
+
+template <bool FLAGS>
+__device__ void w64_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch,
                         double* __restrict__ x) {
   const int lane = threadIdx.x & 31;
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
@@ -217,42 +239,80 @@ __device__ void w64_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
   const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
   const int i0 = lane, i1 = lane + 32;
   const double* __restrict__ P = N.L + S.L_off[s];
-  const int par = S.sn_parent[s];
-  if (par >= 0 && lane == 0) wait_eq(V.done_b + par, epoch);
-  __syncwarp();
+  if (FLAGS) {
+    const int par = S.sn_parent[s];
+    if (par >= 0 && lane == 0) wait_eq(V.done_b + par, epoch);
+    __syncwarp();
+  }
   double v0 = 0.0, v1 = 0.0;  // entries i0 / i1 of [D^-1 y ; x(rows)]
   if (i0 < k) v0 = x[c0 + i0]; else if (i0 < f) v0 = __ldcg(x + S.rows[ro + i0 - k]);
   if (i1 < k) v1 = x[c0 + i1]; else if (i1 < f) v1 = __ldcg(x + S.rows[ro + i1 - k]);
-  // columns from the last to the first: v_t -= sum_{i>t} L[i,t] v_i  (column read coalesced, warp-sum)
-  for (int tb = k - 1; tb >= 0; tb -= 8) {
-    double l0[8], l1[8];
+  if (k <= 32) {
+    // (1) rectangular part  u_t = sum_{i >= k} L[i,t] v_i : no chain -- coalesced column loads (lane = row), per-lane
+    //     products for all 32 columns, one transposing warp reduction (lane t gets u_t)
+    const bool cb0 = i0 >= k && i0 < f, cb1 = i1 < f;
+    const double m0 = cb0 ? v0 : 0.0, m1 = cb1 ? v1 : 0.0;
+    double p[32];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int t = tb - q;
-      l0[q] = (t >= 0 && i0 > t && i0 < f) ? P[i0 + (size_t)t * f] : 0.0;
-      l1[q] = (t >= 0 && i1 > t && i1 < f) ? P[i1 + (size_t)t * f] : 0.0;
+    for (int tb = 0; tb < 32; tb += 8) {
+      double l0[8], l1[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int t = tb + q;
+        l0[q] = (t < k && cb0) ? P[i0 + (size_t)t * f] : 0.0;
+        l1[q] = (t < k && cb1) ? P[i1 + (size_t)t * f] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) p[tb + q] = fma(l0[q], m0, l1[q] * m1);
     }
+    // (2) triangle: lane t owns column t; its sub-diagonal entries L[ii, t] (ii > t) are 31 independent loads
+    //     (column t is contiguous: 16 consecutive ii share a 128-byte line), then a chain of k-1 shuffle+FMA steps
+    double lr[32];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int t = tb - q;
-      if (t >= 0) {
-        double part = fma(l0[q], v0, l1[q] * v1);
+    for (int ii = 1; ii < 32; ++ii) lr[ii] = (ii < k && lane < ii) ? P[ii + (size_t)lane * f] : 0.0;
+    const double u = warp_transpose_reduce(p);
+    double z = (lane < k) ? v0 - u : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (t < 32) { if (lane == t) v0 -= part; } else { if (lane == t - 32) v1 -= part; }
+    for (int ii = 31; ii >= 1; --ii) {
+      if (ii < k) {   // warp-uniform
+        const double xi = __shfl_sync(0xffffffffu, z, ii);
+        z = fma(-lr[ii], xi, z);
       }
     }
+    if (lane < k) x[c0 + N.lperm[c0 + lane]] = z;
+  } else {
+    // columns from the last to the first: v_t -= sum_{i>t} L[i,t] v_i  (column read coalesced, warp-sum)
+    for (int tb = k - 1; tb >= 0; tb -= 8) {
+      double l0[8], l1[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int t = tb - q;
+        l0[q] = (t >= 0 && i0 > t && i0 < f) ? P[i0 + (size_t)t * f] : 0.0;
+        l1[q] = (t >= 0 && i1 > t && i1 < f) ? P[i1 + (size_t)t * f] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int t = tb - q;
+        if (t >= 0) {
+          double part = fma(l0[q], v0, l1[q] * v1);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (t < 32) { if (lane == t) v0 -= part; } else { if (lane == t - 32) v1 -= part; }
+        }
+      }
+    }
+    if (i0 < k) x[c0 + N.lperm[c0 + i0]] = v0;
+    if (i1 < k) x[c0 + N.lperm[c0 + i1]] = v1;
   }
-  if (i0 < k) x[c0 + N.lperm[c0 + i0]] = v0;
-  if (i1 < k) x[c0 + N.lperm[c0 + i1]] = v1;
   __syncwarp();
-  if (lane == 0) { st_release(V.done_b + s, epoch); }
+  if (FLAGS && lane == 0) st_release(V.done_b + s, epoch);
 }
 
 // ------------------------------------------------------------------------------------------------
-// mid fronts (33 .. mid_max): one CTA, blocked by 32 (same algorithm as solve_kernels.cu)
+// mid fronts (65 .. 256): one CTA, blocked by 32
 // smem: v[f] | w[f] | Lb[32*33]
 // ------------------------------------------------------------------------------------------------
+template <bool FLAGS>
 __device__ void mid_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
                         double* __restrict__ x, double* __restrict__ cbv) {
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
@@ -262,7 +322,7 @@ __device__ void mid_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
   double* Lb = sm + 2 * f;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
-  for (int q = ch0 + tid; q < ch1; q += nt) wait_eq(V.done_f + S.child_idx[q], epoch);
+  if (FLAGS) for (int q = ch0 + tid; q < ch1; q += nt) wait_eq(V.done_f + S.child_idx[q], epoch);
   for (int i = tid; i < f; i += nt) w[i] = (i < k) ? x[c0 + i] : 0.0;
   __syncthreads();
   for (int q = ch0; q < ch1; ++q) {
@@ -311,9 +371,10 @@ __device__ void mid_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
   double* __restrict__ out = cbv + S.rows_ptr[s];
   for (int i = tid; i < r; i += nt) out[i] = v[k + i];
   __syncthreads();
-  if (tid == 0) { st_release(V.done_f + s, epoch); }
+  if (FLAGS && tid == 0) st_release(V.done_f + s, epoch);
 }
 
+template <bool FLAGS>
 __device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
                         double* __restrict__ x) {
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
@@ -322,8 +383,10 @@ __device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
   double* v = sm;
   double* Lb = sm + 2 * f;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-  const int par = S.sn_parent[s];
-  if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
+  if (FLAGS) {
+    const int par = S.sn_parent[s];
+    if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
+  }
   __syncthreads();
   for (int i = tid; i < f; i += nt) v[i] = (i < k) ? x[c0 + i] : __ldcg(x + S.rows[ro + (i - k)]);
   __syncthreads();
@@ -357,222 +420,58 @@ __device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
   const int* __restrict__ lp = N.lperm + c0;
   for (int t = tid; t < k; t += nt) x[c0 + lp[t]] = v[t];
   __syncthreads();
-  if (tid == 0) { st_release(V.done_b + s, epoch); }
+  if (FLAGS && tid == 0) st_release(V.done_b + s, epoch);
 }
 
 // ------------------------------------------------------------------------------------------------
-// big fronts: gather task + one task per 64-row block (forward) / 64-column block (backward)
+// Big fronts (order > 256).  With the EXPLICIT inverse of the unit-lower-triangular pivot block L11 (k_linv_* below,
+// once per factorisation) the in-front recurrences become block GEMVs with no chain:
+//   forward   FP: y_b   = sum_{c<=b} Linv[b,c] w_c          (w = assembled, pivot-permuted right-hand side)
+//             FC: u_j   = w_j - L21[j,:] y                   (update vector handed to the parent)
+//   backward  BT: t_b   = z_b - L21[:,b]^T x(rows)           (z = D^-1 y)
+//             BX: x_b   = sum_{c>=b} Linv[c,b]^T t_c
+// Each (64-block, chunk of <= DF_CH tiles) is one task; the w entries a task needs are gathered on the fly from the
+// children's update vectors through the inverse row maps (S.einv) -- no separate gather task, no staging buffer.
+// The right-hand side of a big front stays in x[c0..c0+k) until BX overwrites it with the solution: the forward result
+// z lives in V.bigv (so FP tasks of other blocks can still read the right-hand side).
+// smem: stage[256] | part[256] | ys[64] | red[128] | colacc[64]
 // ------------------------------------------------------------------------------------------------
-__device__ void big_gather_global(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch,
-                                  const double* __restrict__ x, const double* __restrict__ cbv) {
-  // w = [x(cols) ; 0] + scatter(children update vectors), then the in-front pivot permutation; result in bigv.
-  // Children write disjoint... no: two children may hit the same parent row, so children are applied one
-  // after the other (deterministic), each child fully parallel.
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]), f = k + r;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  double* w = V.bigv + V.bigv_off[s];      // scratch (pre-permutation) lives in bigy, result in bigv
-  double* tmp = V.bigy + V.bigv_off[s];    // f doubles available (bigy has the same per-front extent)
-  const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
-  for (int q = ch0 + tid; q < ch1; q += nt) wait_eq(V.done_f + S.child_idx[q], epoch);
-  for (int i = tid; i < f; i += nt) tmp[i] = (i < k) ? x[c0 + i] : 0.0;
-  __syncthreads();
-  for (int q = ch0; q < ch1; ++q) {
-    const int c = S.child_idx[q];
-    const long long o = S.rows_ptr[c];
-    const int rc = (int)(S.rows_ptr[c + 1] - o);
-    for (int t = tid; t < rc; t += nt) tmp[S.rel[o + t]] += __ldcg(cbv + o + t);
-    __syncthreads();
-  }
-  const int* __restrict__ lp = N.lperm + c0;
-  for (int i = tid; i < f; i += nt) w[i] = (i < k) ? tmp[lp[i]] : tmp[i];
-  __syncthreads();
-  if (tid == 0) { st_release(V.gflag + s, epoch); }
-}
-
-#define DF_STAGE 8192      // doubles of the shared staging area (vectors are staged in chunks of this many rows)
-#define DF_GATHER_MAXCH 256
-
-// Same result as big_gather_global with the assembled vector held in shared memory and the children's update
-// vectors software-pipelined (the (rel, value) pair of the next chunk is in flight while the current one is added;
-// a barrier only between children, whose targets may overlap).  Falls back to the global version for fronts that do
-// not fit (order > DF_STAGE or more than DF_GATHER_MAXCH children).
-// smem: tmp[DF_STAGE] | meta_o[DF_GATHER_MAXCH] (long long) | meta_rc[DF_GATHER_MAXCH] (int)
-__device__ void big_gather(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
-                           const double* __restrict__ x, const double* __restrict__ cbv) {
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]), f = k + r;
-  const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
-  if (f > DF_STAGE || nch > DF_GATHER_MAXCH || (V.opts & 1)) { big_gather_global(S, N, V, s, epoch, x, cbv); return; }
-  const int tid = threadIdx.x, nt = blockDim.x;
-  double* tmp = sm;
-  long long* meta_o = reinterpret_cast<long long*>(sm + DF_STAGE);
-  int* meta_rc = reinterpret_cast<int*>(meta_o + DF_GATHER_MAXCH);
-  for (int q = tid; q < nch; q += nt) {
+__device__ __forceinline__ double big_gather_row(const DevSym& S, int j, int k, int c0, int ch0, int nch,
+                                                 const double* __restrict__ x, const double* __restrict__ cbv) {
+  double v = (j < k) ? x[c0 + j] : 0.0;
+  for (int q = 0; q < nch; ++q) {   // fixed child order: deterministic
     const int c = S.child_idx[ch0 + q];
-    const long long o = S.rows_ptr[c];
-    meta_o[q] = o;
-    meta_rc[q] = (int)(S.rows_ptr[c + 1] - o);
-    wait_eq(V.done_f + c, epoch);
+    const int e = S.einv[S.einv_off[c] + j];
+    if (e >= 0) v += __ldcg(cbv + S.rows_ptr[c] + e);
   }
-  for (int i = tid; i < f; i += nt) tmp[i] = (i < k) ? x[c0 + i] : 0.0;
-  __syncthreads();
-  {
-    int q = 0, t = tid;
-    int idx = 0; double val = 0.0; bool ok = false;
-    if (nch > 0) {
-      ok = t < meta_rc[0];
-      if (ok) { idx = S.rel[meta_o[0] + t]; val = __ldcg(cbv + meta_o[0] + t); }
-    }
-    while (q < nch) {
-      const int cidx = idx; const double cval = val; const bool cok = ok;
-      int nq = q, ntt = t + nt;
-      if (ntt - tid >= meta_rc[q]) { nq = q + 1; ntt = tid; }   // (uniform: depends on the chunk base only)
-      ok = false;
-      if (nq < nch) {
-        const long long o = meta_o[nq];
-        ok = ntt < meta_rc[nq];
-        if (ok) { idx = S.rel[o + ntt]; val = __ldcg(cbv + o + ntt); }
-      }
-      if (cok) tmp[cidx] += cval;
-      if (nq != q) __syncthreads();
-      q = nq; t = ntt;
-    }
-  }
-  double* w = V.bigv + V.bigv_off[s];
-  const int* __restrict__ lp = N.lperm + c0;
-  for (int i = tid; i < f; i += nt) w[i] = (i < k) ? tmp[lp[i]] : tmp[i];
-  __syncthreads();
-  if (tid == 0) { st_release(V.gflag + s, epoch); }
+  return v;
 }
 
-// Big fronts use the EXPLICIT inverse of their unit-lower-triangular pivot block L11 (k_linv_* below, computed once
-// per factorisation): the in-front recurrences  y = L11^-1 w  and  x = L11^-T t  become block GEMVs whose 64-row /
-// 64-column blocks are independent tasks -- no chain of nkb dependent steps per front.  Linv is stored K64 x K64
-// (K64 = 64*ceil(k/64), column-major, zero-padded, upper block triangle never read).
-__device__ __forceinline__ void wait_flags(const int* flags, int first, int last, int epoch) {
-  // flags[first..last) all equal to epoch (one flag per thread, in parallel), then a CTA barrier
-  for (int c = first + (int)threadIdx.x; c < last; c += blockDim.x) wait_eq(flags + c, epoch);
-  __syncthreads();
-}
-
-// forward, pivot block b (rows [64b, 64b+64) of the pivoted front): y_b = sum_{c<=b} Linv[b,c] w_c
-// smem: stage[DF_STAGE] | part[256] | ys[64]
-__device__ void big_fwd_piv(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
-                            double* sm, double* __restrict__ x) {
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-  const int nkb = (k + DF_BLK - 1) / DF_BLK;
-  const long long K64 = (long long)nkb * DF_BLK;
-  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-  double* stage = sm;
-  double* part = sm + DF_STAGE;
-  double* ys = part + 256;
-  const int t0 = b * DF_BLK, nrow = min(DF_BLK, k - t0);
-  const double* __restrict__ Li = V.linv + V.linv_off[s] + (t0 + tx);
-  const double* __restrict__ w = V.bigv + V.bigv_off[s];
-  // first tile in flight before the gather flag is seen (Linv does not depend on the right-hand side)
-  double ltn[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)(ty + 4 * q) * K64];
-  if (tid == 0) wait_eq(V.gflag + s, epoch);
-  __syncthreads();
-  double acc = 0.0;
-  const int ntile = b + 1;
-  for (int base = 0; base < ntile; base += DF_STAGE / DF_BLK) {
-    const int lim = min(ntile, base + DF_STAGE / DF_BLK);
-    __syncthreads();
-    for (int i = base * DF_BLK + tid; i < lim * DF_BLK; i += blockDim.x) stage[i - base * DF_BLK] = (i < k) ? __ldcg(w + i) : 0.0;
-    __syncthreads();
-    for (int c = base; c < lim; ++c) {
-      double lt[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-      if (c + 1 < ntile) {
-        const double* nx = Li + (long long)(c + 1) * DF_BLK * K64;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) ltn[q] = nx[(long long)(ty + 4 * q) * K64];
-      }
-      const double* wc = stage + (c - base) * DF_BLK + ty;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc = fma(lt[q], wc[4 * q], acc);
-    }
-  }
-  part[ty * 64 + tx] = acc;
-  __syncthreads();
-  if (tid < 64) ys[tid] = (tid < nrow) ? part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid] : 0.0;
-  __syncthreads();
-  if (tid < nrow) {
-    const int i = t0 + tid;
-    V.bigy[V.bigv_off[s] + i] = ys[tid];   // y block for the contribution rows (pivoted order)
-    const int ty2 = N.ptype[c0 + i];
-    double y;
-    if (ty2 == 1) y = ys[tid] * N.dinv[c0 + i];
-    else if (ty2 == 2) y = ys[tid] * N.dinv[c0 + i] + ys[tid + 1] * N.doff[c0 + i];
-    else y = ys[tid - 1] * N.doff[c0 + i - 1] + ys[tid] * N.dinv[c0 + i];
-    x[c0 + i] = y;
-  }
+// Combine the chunk partials of one (front, kind, block): every CTA stores its 64 partial sums, the LAST one to arrive
+// adds them in chunk order (independent of the arrival order).  `out` (shared, 64 doubles) holds this CTA's partial on
+// entry and the total on exit.  Returns true (in all threads) for the CTA that must finalise the block.
+__device__ __forceinline__ bool chunk_combine(const DevSolve& V, const SolveTask& T, double* out, int* s_flag) {
+  if (T.nq == 1) return true;
+  const int tid = threadIdx.x;
+  if (tid < 64) __stcg(V.part + ((long long)T.pbase + T.q) * 64 + tid, out[tid]);
   __syncthreads();
   if (tid == 0) {
-    st_release(V.bflag_f + V.boff[s] + b, epoch);
-    const int nblk = nkb + (f - k + DF_BLK - 1) / DF_BLK;
-    const int old = atomicAdd(V.bcnt + s, 1);
-    if ((old + 1) % nblk == 0) { st_release(V.done_f + s, epoch); }
+    __threadfence();                                    // release: this CTA's partial before the counter
+    const int old = atomicAdd(V.ccnt + T.cidx, 1);
+    const int last = ((old + 1) % T.nq) == 0;
+    if (last) __threadfence();                          // acquire: the other CTAs' partials after the counter
+    *s_flag = last;
   }
-}
-
-// forward, contribution rows [k + 64j, ...): update vector = w - L21[rows, :] y
-__device__ void big_fwd_cb(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int j, int epoch,
-                           double* sm, double* __restrict__ cbv) {
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-  const int nkb = (k + DF_BLK - 1) / DF_BLK;
-  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-  double* stage = sm;
-  double* part = sm + DF_STAGE;
-  const int rbase = k + j * DF_BLK, nr = min(DF_BLK, f - rbase);
-  const double* __restrict__ P = N.L + S.L_off[s] + (rbase + tx);
-  const double* __restrict__ yb = V.bigy + V.bigv_off[s];
-  double ltn[16];
-  {
-    const int nc0 = min(DF_BLK, k);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < nc0) ? P[(size_t)t * f] : 0.0; }
-  }
-  if (tid == 0) wait_eq(V.gflag + s, epoch);
   __syncthreads();
-  const double wmine = (tid < nr) ? __ldcg(V.bigv + V.bigv_off[s] + rbase + tid) : 0.0;
-  wait_flags(V.bflag_f + V.boff[s], 0, nkb, epoch);
-  double acc = 0.0;
-  for (int base = 0; base < nkb; base += DF_STAGE / DF_BLK) {
-    const int lim = min(nkb, base + DF_STAGE / DF_BLK);
-    __syncthreads();
-    for (int i = base * DF_BLK + tid; i < lim * DF_BLK; i += blockDim.x) stage[i - base * DF_BLK] = (i < k) ? __ldcg(yb + i) : 0.0;
-    __syncthreads();
-    for (int c = base; c < lim; ++c) {
-      double lt[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-      if (c + 1 < nkb) {
-        const int t0n = (c + 1) * DF_BLK, ncn = min(DF_BLK, k - t0n);
-        const double* nx = P + (size_t)t0n * f;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncn) ? nx[(size_t)t * f] : 0.0; }
-      }
-      const double* yc = stage + (c - base) * DF_BLK + ty;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc = fma(lt[q], yc[4 * q], acc);
-    }
+  if (!*s_flag) return false;
+  if (tid < 64) {
+    const double* base = V.part + (long long)T.pbase * 64 + tid;
+    double a = 0.0;
+    for (int q = 0; q < T.nq; ++q) a += __ldcg(base + (long long)q * 64);
+    out[tid] = a;
   }
-  part[ty * 64 + tx] = acc;
   __syncthreads();
-  if (tid < nr) cbv[S.rows_ptr[s] + (rbase - k) + tid] = wmine - (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]);
-  __syncthreads();
-  if (tid == 0) {
-    const int nblk = nkb + (f - k + DF_BLK - 1) / DF_BLK;
-    const int old = atomicAdd(V.bcnt + s, 1);
-    if ((old + 1) % nblk == 0) { st_release(V.done_f + s, epoch); }
-  }
+  return true;
 }
 
 // sum the per-thread partials pacc[q] (column t = ty + 4q, row lane tx) over the 64 row lanes -> colacc[64] (smem)
@@ -594,103 +493,246 @@ __device__ __forceinline__ void reduce_cols(double (&pacc)[16], double* red, dou
   __syncthreads();
 }
 
-// backward phase 1, column block b: t_b = z_b - L21[:, b]^T x(contribution rows)   (no dependence on other blocks)
-// smem: stage[DF_STAGE] | red[128] | colacc[64]
-__device__ void big_bwd_t(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
-                          double* sm, const double* __restrict__ x) {
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const long long ro = S.rows_ptr[s];
-  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
-  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-  double* stage = sm;
-  double* red = sm + DF_STAGE;
-  double* colacc = red + 128;
-  const int t0 = b * DF_BLK, ncol = min(DF_BLK, k - t0);
-  const double* __restrict__ P = N.L + S.L_off[s] + (size_t)t0 * f;
-  const int nchunk = (r + DF_BLK - 1) / DF_BLK;
-  double pacc[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
-  double ltn[16];
-  if (nchunk > 0) {
-    const int nr = min(DF_BLK, r);
-    const double* base = P + (k + tx);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncol) ? base[(size_t)t * f] : 0.0; }
-  }
-  const int par = S.sn_parent[s];
-  if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
-  __syncthreads();
-  for (int cb = 0; cb < nchunk; cb += DF_STAGE / DF_BLK) {
-    const int lim = min(nchunk, cb + DF_STAGE / DF_BLK);
-    __syncthreads();
-    for (int i = cb * DF_BLK + tid; i < lim * DF_BLK; i += blockDim.x) stage[i - cb * DF_BLK] = (i < r) ? __ldcg(x + S.rows[ro + i]) : 0.0;
-    __syncthreads();
-    for (int ch = cb; ch < lim; ++ch) {
-      double lt[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-      if (ch + 1 < nchunk) {
-        const int rb2 = k + (ch + 1) * DF_BLK, nr2 = min(DF_BLK, f - rb2);
-        const double* base = P + (rb2 + tx);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
-      }
-      const double xi = stage[(ch - cb) * DF_BLK + tx];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], xi, pacc[q]);
-    }
-  }
-  reduce_cols(pacc, red, colacc);
-  if (tid < ncol) V.bigv[V.bigv_off[s] + t0 + tid] = x[c0 + t0 + tid] - colacc[tid];
-  __syncthreads();
-  if (tid == 0) st_release(V.bflag_b + V.boff[s] + b, epoch);
-}
-
-// backward phase 2, column block b: x_b = sum_{c>=b} Linv[c,b]^T t_c
-__device__ void big_bwd_x(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int b, int epoch,
-                          double* sm, double* __restrict__ x) {
+// FP: pivot rows [64 blk, +64) of front s, tiles [t0, t1) of Linv's block row
+__device__ void big_fp(const DevSym& S, const DevNum& N, const DevSolve& V, const SolveTask& T, int epoch, double* sm,
+                       int* s_flag, const double* __restrict__ x, const double* __restrict__ cbv) {
+  const int s = T.s, rb = T.blk;
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   const int nkb = (k + DF_BLK - 1) / DF_BLK;
   const long long K64 = (long long)nkb * DF_BLK;
   const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
   double* stage = sm;
-  double* red = sm + DF_STAGE;
+  double* part = sm + 256;
+  double* ys = part + 256;
+  const int r0 = rb * DF_BLK, nrow = min(DF_BLK, k - r0);
+  const double* __restrict__ Li = V.linv + V.linv_off[s] + (r0 + tx);
+  // first tile in flight before the children are seen (Linv does not depend on the right-hand side)
+  double ltn[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) ltn[q] = Li[((long long)T.t0 * DF_BLK + ty + 4 * q) * K64];
+  const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
+  for (int q = tid; q < nch; q += DF_THREADS) wait_eq(V.done_f + S.child_idx[ch0 + q], epoch);
+  __syncthreads();
+  {
+    const int* __restrict__ lp = N.lperm + c0;
+    const int ncols = (T.t1 - T.t0) * DF_BLK;
+    for (int i = tid; i < ncols; i += DF_THREADS) {
+      const int gi = T.t0 * DF_BLK + i;
+      stage[i] = (gi < k) ? big_gather_row(S, lp[gi], k, c0, ch0, nch, x, cbv) : 0.0;
+    }
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int c = T.t0; c < T.t1; ++c) {
+    double lt[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+    if (c + 1 < T.t1) {
+      const double* nx = Li + (long long)(c + 1) * DF_BLK * K64;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) ltn[q] = nx[(long long)(ty + 4 * q) * K64];
+    }
+    const double* wc = stage + (c - T.t0) * DF_BLK + ty;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc = fma(lt[q], wc[4 * q], acc);
+  }
+  part[ty * 64 + tx] = acc;
+  __syncthreads();
+  if (tid < 64) ys[tid] = part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid];
+  __syncthreads();
+  if (!chunk_combine(V, T, ys, s_flag)) return;
+  if (tid < nrow) {
+    const int i = r0 + tid;
+    const long long o = V.bigv_off[s];
+    V.bigy[o + i] = ys[tid];              // y block for the contribution rows (pivoted order)
+    const int ty2 = N.ptype[c0 + i];      // 2x2 partners never straddle a 32-column panel, so they sit in this block
+    double z;
+    if (ty2 == 1) z = ys[tid] * N.dinv[c0 + i];
+    else if (ty2 == 2) z = ys[tid] * N.dinv[c0 + i] + ys[tid + 1] * N.doff[c0 + i];
+    else z = ys[tid - 1] * N.doff[c0 + i - 1] + ys[tid] * N.dinv[c0 + i];
+    V.bigv[o + i] = z;
+  }
+  __syncthreads();
+  if (tid == 0) st_release(V.bflag_f + V.boff[s] + rb, epoch);
+}
+
+// FC: contribution rows [k + 64 blk, +64), tiles [t0, t1) of L21's block row
+__device__ void big_fc(const DevSym& S, const DevNum& N, const DevSolve& V, const SolveTask& T, int epoch, double* sm,
+                       int* s_flag, const double* __restrict__ x, double* __restrict__ cbv) {
+  const int s = T.s, j = T.blk;
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  double* stage = sm;
+  double* part = sm + 256;
+  double* ys = part + 256;
+  const int rbase = k + j * DF_BLK, nr = min(DF_BLK, f - rbase);
+  const double* __restrict__ P = N.L + S.L_off[s] + (rbase + tx);
+  double ltn[16];
+  {
+    const int tc0 = T.t0 * DF_BLK, ncn = min(DF_BLK, k - tc0);
+    const double* nx = P + (size_t)tc0 * f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncn) ? nx[(size_t)t * f] : 0.0; }
+  }
+  for (int c = T.t0 + tid; c < T.t1; c += DF_THREADS) wait_eq(V.bflag_f + V.boff[s] + c, epoch);
+  __syncthreads();
+  {
+    const double* __restrict__ yb = V.bigy + V.bigv_off[s];
+    const int ncols = (T.t1 - T.t0) * DF_BLK;
+    for (int i = tid; i < ncols; i += DF_THREADS) {
+      const int gi = T.t0 * DF_BLK + i;
+      stage[i] = (gi < k) ? __ldcg(yb + gi) : 0.0;
+    }
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int c = T.t0; c < T.t1; ++c) {
+    double lt[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+    if (c + 1 < T.t1) {
+      const int tcn = (c + 1) * DF_BLK, ncn = min(DF_BLK, k - tcn);
+      const double* nx = P + (size_t)tcn * f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncn) ? nx[(size_t)t * f] : 0.0; }
+    }
+    const double* yc = stage + (c - T.t0) * DF_BLK + ty;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc = fma(lt[q], yc[4 * q], acc);
+  }
+  part[ty * 64 + tx] = acc;
+  __syncthreads();
+  if (tid < 64) ys[tid] = part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid];
+  __syncthreads();
+  if (!chunk_combine(V, T, ys, s_flag)) return;
+  if (tid < nr) {
+    // the children are complete (every FP task of this front waited for them before publishing the flags seen above)
+    const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
+    const double wv = big_gather_row(S, rbase + tid, k, c0, ch0, nch, x, cbv);
+    cbv[S.rows_ptr[s] + (rbase - k) + tid] = wv - ys[tid];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int ncb = (f - k + DF_BLK - 1) / DF_BLK;
+    __threadfence();                                 // this block's update vector before the counter
+    const int old = atomicAdd(V.bcnt + s, 1);
+    if ((old + 1) % ncb == 0) { __threadfence(); st_release(V.done_f + s, epoch); }
+  }
+}
+
+// BT: column block blk, contribution-row tiles [t0, t1):  t_b = z_b - L21[:, b]^T x(rows)
+__device__ void big_bt(const DevSym& S, const DevNum& N, const DevSolve& V, const SolveTask& T, int epoch, double* sm,
+                       int* s_flag, const double* __restrict__ x) {
+  const int s = T.s, b = T.blk;
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const long long ro = S.rows_ptr[s];
+  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  double* stage = sm;
+  double* red = sm + 576;
   double* colacc = red + 128;
-  const int t0 = b * DF_BLK, ncol = min(DF_BLK, k - t0);
-  const double* __restrict__ Li = V.linv + V.linv_off[s] + (long long)t0 * K64 + tx;
+  const int tc0 = b * DF_BLK, ncol = min(DF_BLK, k - tc0);
+  const double* __restrict__ P = N.L + S.L_off[s] + (size_t)tc0 * f;
+  double pacc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
+  double ltn[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) ltn[q] = 0.0;
+  if (T.t1 > T.t0) {
+    const int rb2 = k + T.t0 * DF_BLK, nr2 = min(DF_BLK, f - rb2);
+    const double* base = P + (rb2 + tx);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
+  }
+  {
+    const int par = S.sn_parent[s];
+    if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
+  }
+  __syncthreads();
+  {
+    const int nrows = (T.t1 - T.t0) * DF_BLK;
+    for (int i = tid; i < nrows; i += DF_THREADS) {
+      const int ri = T.t0 * DF_BLK + i;
+      stage[i] = (ri < r) ? __ldcg(x + S.rows[ro + ri]) : 0.0;
+    }
+  }
+  __syncthreads();
+  for (int ch = T.t0; ch < T.t1; ++ch) {
+    double lt[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+    if (ch + 1 < T.t1) {
+      const int rb2 = k + (ch + 1) * DF_BLK, nr2 = min(DF_BLK, f - rb2);
+      const double* base = P + (rb2 + tx);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
+    }
+    const double xi = stage[(ch - T.t0) * DF_BLK + tx];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], xi, pacc[q]);
+  }
+  reduce_cols(pacc, red, colacc);
+  if (!chunk_combine(V, T, colacc, s_flag)) return;
+  if (tid < ncol) {
+    double* tv = V.bigv + V.bigv_off[s] + tc0 + tid;
+    *tv = *tv - colacc[tid];            // z (written by FP in the forward sweep) -> t, in place
+  }
+  __syncthreads();
+  if (tid == 0) st_release(V.bflag_b + V.boff[s] + b, epoch);
+}
+
+// BX: column block blk, tiles [t0, t1) of Linv's block column (t0 >= blk):  x_b = sum_c Linv[c,b]^T t_c
+__device__ void big_bx(const DevSym& S, const DevNum& N, const DevSolve& V, const SolveTask& T, int epoch, double* sm,
+                       int* s_flag, double* __restrict__ x) {
+  const int s = T.s, b = T.blk;
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int nkb = (k + DF_BLK - 1) / DF_BLK;
+  const long long K64 = (long long)nkb * DF_BLK;
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  double* stage = sm;
+  double* red = sm + 576;
+  double* colacc = red + 128;
+  const int tc0 = b * DF_BLK, ncol = min(DF_BLK, k - tc0);
+  const double* __restrict__ Li = V.linv + V.linv_off[s] + (long long)tc0 * K64 + tx;
   const double* __restrict__ tv = V.bigv + V.bigv_off[s];
   double pacc[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
   double ltn[16];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)b * DF_BLK + (long long)(ty + 4 * q) * K64];
-  wait_flags(V.bflag_b + V.boff[s], b, nkb, epoch);
-  for (int cb = b; cb < nkb; cb += DF_STAGE / DF_BLK) {
-    const int lim = min(nkb, cb + DF_STAGE / DF_BLK);
-    __syncthreads();
-    for (int i = cb * DF_BLK + tid; i < lim * DF_BLK; i += blockDim.x) stage[i - cb * DF_BLK] = (i < k) ? __ldcg(tv + i) : 0.0;
-    __syncthreads();
-    for (int c = cb; c < lim; ++c) {
-      double lt[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-      if (c + 1 < nkb) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)(c + 1) * DF_BLK + (long long)(ty + 4 * q) * K64];
-      }
-      const double ti = stage[(c - cb) * DF_BLK + tx];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], ti, pacc[q]);
+  for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)T.t0 * DF_BLK + (long long)(ty + 4 * q) * K64];
+  for (int c = T.t0 + tid; c < T.t1; c += DF_THREADS) wait_eq(V.bflag_b + V.boff[s] + c, epoch);
+  __syncthreads();
+  {
+    const int nrows = (T.t1 - T.t0) * DF_BLK;
+    for (int i = tid; i < nrows; i += DF_THREADS) {
+      const int gi = T.t0 * DF_BLK + i;
+      stage[i] = (gi < k) ? __ldcg(tv + gi) : 0.0;
     }
   }
+  __syncthreads();
+  for (int c = T.t0; c < T.t1; ++c) {
+    double lt[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
+    if (c + 1 < T.t1) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)(c + 1) * DF_BLK + (long long)(ty + 4 * q) * K64];
+    }
+    const double ti = stage[(c - T.t0) * DF_BLK + tx];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], ti, pacc[q]);
+  }
   reduce_cols(pacc, red, colacc);
-  if (tid < ncol) x[c0 + N.lperm[c0 + t0 + tid]] = colacc[tid];   // final value (the permutation is panel-local)
+  if (!chunk_combine(V, T, colacc, s_flag)) return;
+  if (tid < ncol) x[c0 + N.lperm[c0 + tc0 + tid]] = colacc[tid];   // final value (the permutation is panel-local)
   __syncthreads();
   if (tid == 0) {
+    __threadfence();                                 // this block's solution entries before the counter
     const int old = atomicAdd(V.bcnt_b + s, 1);
-    if ((old + 1) % nkb == 0) { st_release(V.done_b + s, epoch); }
+    if ((old + 1) % nkb == 0) { __threadfence(); st_release(V.done_b + s, epoch); }
   }
 }
 
@@ -819,12 +861,46 @@ __global__ void __launch_bounds__(128) k_linv_gemm(DevSym S, DevNum N, const Lin
 }
 
 // ------------------------------------------------------------------------------------------------
+// bottom of the tree: one CTA per subtree, level by level, CTA barriers only
+// ------------------------------------------------------------------------------------------------
 template <bool FWD>
-__global__ void __launch_bounds__(DF_THREADS) k_solve_dataflow(DevSym S, DevNum N, DevSolve V, int epoch,
-                                                                unsigned long long ticket_base,
-                                                                double* __restrict__ x, double* __restrict__ cbv) {
-  extern __shared__ double sm[];
+__global__ void __launch_bounds__(DF_THREADS, 2) k_solve_sub(DevSym S, DevNum N, DevSolve V, int epoch,
+                                                          double* __restrict__ x, double* __restrict__ cbv) {
+  __shared__ double sm[DF_SMEM_DOUBLES];
+  const int u = blockIdx.x;
+  const int e0 = V.sub_ptr[u], nlv = V.sub_ptr[u + 1] - e0;
+  const int warp = threadIdx.x >> 5;
+  for (int li = 0; li < nlv; ++li) {
+    const int e = e0 + (FWD ? li : nlv - 1 - li);
+    const int b = V.lvl_ptr[e], en = V.lvl_ptr[e + 1], ns = V.lvl_nsmall[e];
+    for (int q = b + warp; q < b + ns; q += DF_THREADS / 32) {
+      const int s = V.sub_fronts[q];
+      if (FWD) w64_fwd<false>(S, N, V, s, epoch, sm + warp * 64, x, cbv);
+      else w64_bwd<false>(S, N, V, s, epoch, x);
+    }
+    if (en > b + ns) {
+      __syncthreads();   // the per-warp scratch of the small fronts overlaps the mid-front buffers
+      for (int q = b + ns; q < en; ++q) {
+        const int s = V.sub_fronts[q];
+        if (FWD) mid_fwd<false>(S, N, V, s, epoch, sm, x, cbv);
+        else mid_bwd<false>(S, N, V, s, epoch, sm, x);
+      }
+    }
+    __syncthreads();     // (also orders this level's global writes before the next level's reads, CTA scope)
+  }
+  if (FWD && threadIdx.x == 0) V.done_f[V.sub_root[u]] = epoch;   // read by the top kernel (next launch)
+}
+
+// ------------------------------------------------------------------------------------------------
+// top of the tree: persistent task queue
+// ------------------------------------------------------------------------------------------------
+template <bool FWD>
+__global__ void __launch_bounds__(DF_THREADS, 2) k_solve_top(DevSym S, DevNum N, DevSolve V, int epoch,
+                                                          unsigned long long ticket_base,
+                                                          double* __restrict__ x, double* __restrict__ cbv) {
+  __shared__ double sm[DF_SMEM_DOUBLES];
   __shared__ unsigned long long s_ticket;
+  __shared__ int s_flag;
   const SolveTask* tasks = FWD ? V.tasks : V.tasks_bwd;
   const int ntasks = FWD ? V.ntasks_fwd : V.ntasks_bwd;
   while (true) {
@@ -835,28 +911,29 @@ __global__ void __launch_bounds__(DF_THREADS) k_solve_dataflow(DevSym S, DevNum 
     if (tk >= (unsigned long long)ntasks) return;
     const SolveTask T = tasks[tk];
     unsigned long long t_start = 0;
-    if (V.tlog && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    if (V.tlog && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     if (T.type == ST_SMALL) {
       const int w = threadIdx.x >> 5;
-      if (w < T.b) {
-        const int s = V.bundle[T.a + w];
-        double* wsm = sm + (size_t)w * DF_SMALL_SMEM;
-        const int fs = (S.sn_start[s + 1] - S.sn_start[s]) + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-        if (fs <= 32) { if (FWD) small_fwd(S, N, V, s, epoch, wsm, x, cbv); else small_bwd(S, N, V, s, epoch, wsm, x); }
-        else { if (FWD) w64_fwd(S, N, V, s, epoch, wsm, x, cbv); else w64_bwd(S, N, V, s, epoch, wsm, x); }
+      if (w < T.blk) {
+        const int s = V.bundle[T.s + w];
+        if (FWD) w64_fwd<true>(S, N, V, s, epoch, sm + w * 64, x, cbv);
+        else w64_bwd<true>(S, N, V, s, epoch, x);
       }
     } else if (T.type == ST_MID) {
-      if (FWD) mid_fwd(S, N, V, T.a, epoch, sm, x, cbv); else mid_bwd(S, N, V, T.a, epoch, sm, x);
-    } else if (T.type == ST_BIG_GATHER) {
-      big_gather(S, N, V, T.a, epoch, sm, x, cbv);
+      if (FWD) mid_fwd<true>(S, N, V, T.s, epoch, sm, x, cbv); else mid_bwd<true>(S, N, V, T.s, epoch, sm, x);
+    } else if (T.type == ST_FP) {
+      big_fp(S, N, V, T, epoch, sm, &s_flag, x, cbv);
+    } else if (T.type == ST_FC) {
+      big_fc(S, N, V, T, epoch, sm, &s_flag, x, cbv);
+    } else if (T.type == ST_BT) {
+      big_bt(S, N, V, T, epoch, sm, &s_flag, x);
     } else {
-      if (FWD) { if (T.c == 0) big_fwd_piv(S, N, V, T.a, T.b, epoch, sm, x); else big_fwd_cb(S, N, V, T.a, T.b, epoch, sm, cbv); }
-      else { if (T.c == 0) big_bwd_t(S, N, V, T.a, T.b, epoch, sm, x); else big_bwd_x(S, N, V, T.a, T.b, epoch, sm, x); }
+      big_bx(S, N, V, T, epoch, sm, &s_flag, x);
     }
     __syncthreads();
     if (V.tlog && threadIdx.x == 0) {
       unsigned long long t_end;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
       unsigned long long* rec = V.tlog + 2 * ((FWD ? 0 : (unsigned long long)V.ntasks_fwd) + tk);
       rec[0] = t_start; rec[1] = t_end;
     }

@@ -41,11 +41,12 @@ static int b200_solve(void* h, int nrhs, double* r) { return b200ldlt_solve((b20
 static int b200_numneg(void* h) { return b200ldlt_num_neg((b200ldlt_handle) h); }
 static int b200_incq(void* h) { return b200ldlt_increase_quality((b200ldlt_handle) h); }
 static int b200_refactor(void* h, int c, int e, int* n) { return b200ldlt_refactor((b200ldlt_handle) h, c, e, n); }
+static int b200_set_pivtol(void* h, double u, double umax) { return b200ldlt_set_pivtol((b200ldlt_handle) h, u, umax); }
 
 const LdltBackend* GetB200LdltBackend()
 {
    static const LdltBackend be = {"b200-ldlt", b200_create, b200_destroy, b200_analyse, b200_values, b200_factor,
-                                  b200_solve, b200_numneg, b200_incq, b200_refactor};
+                                  b200_solve, b200_numneg, b200_incq, b200_refactor, b200_set_pivtol};
    return &be;
 }
 
@@ -110,6 +111,9 @@ bool B200LdltSolverInterface::InitializeImpl(const OptionsList& options, const s
    else
    {
       ASSERT_EXCEPTION(initialized_, INVALID_WARMSTART, "B200LdltSolverInterface called with warm_start_same_structure, but the problem is solved for the first time.");
+      // kept handle: the freshly read thresholds replace whatever an earlier IncreaseQuality left behind
+      // (the reference adapters reset pivtol in every InitializeImpl, IpMumpsSolverInterface.cpp:191-245)
+      if( be_->set_pivtol ) be_->set_pivtol(h_, pivtol_, pivtolmax_);
    }
    return true;
 }

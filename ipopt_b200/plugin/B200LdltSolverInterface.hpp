@@ -30,6 +30,7 @@ struct LdltBackend
    int (*increase_quality)(void*);
    /** re-factor the matrix kept by the backend (NULL: use the CALL_AGAIN protocol instead) */
    int (*refactor)(void*, int, int, int*);
+   int (*set_pivtol)(void*, double, double);   // optional (NULL: not supported)
 };
 
 /** the B200 product backend (libb200ldlt.so) */

@@ -156,7 +156,10 @@ void analyse(Oracle& O) {
       vw[v] = m2[v] >= 0 ? 2 : 1;
     }
     int64_t nv = nc;
-    if (!ca.empty() && METIS_NodeND(&nv, cx.data(), ca.data(), vw.data(), nullptr, mp.data(), mip.data()) == 1)
+    // ORACLE_METIS_SEED: another (equally valid) nested-dissection ordering, for solver-to-solver spread controls
+    std::vector<int64_t> mopt(40, -1);   // METIS_NOPTIONS = 40, -1 = default; [8] = METIS_OPTION_SEED
+    if (const char* e = getenv("ORACLE_METIS_SEED")) mopt[8] = atoll(e);
+    if (!ca.empty() && METIS_NodeND(&nv, cx.data(), ca.data(), vw.data(), getenv("ORACLE_METIS_SEED") ? mopt.data() : nullptr, mp.data(), mip.data()) == 1)
       for (int v = 0; v < nc; ++v) corder[v] = (int)mp[v];
   }
   std::vector<int> perm(n), iperm(n);

@@ -67,11 +67,15 @@ static void* orc_create(double pivtol, double pivtolmax, int scaling, int verbos
    // comparator defaults follow the reference's MUMPS adapter: pivtol 1e-6, pivtolmax 0.1
    // (IpMumpsSolverInterface.cpp:137-158); the b200_* options are not applied to the oracle.
    (void) pivtol; (void) pivtolmax; (void) scaling;
-   return oracle_ldlt_create(1e-6, 0.1, 1, verbose);
+   // control experiments (tests/test_dual_spread_control.py): the same oracle with another pivot threshold / scaling
+   // (and ORACLE_METIS_SEED, read by oracle/cpu_ldlt.cpp) to measure the solver-to-solver spread of the final iterates
+   const char* ep = getenv("ORACLE_PIVTOL");
+   const char* es = getenv("ORACLE_SCALING");
+   return oracle_ldlt_create(ep ? atof(ep) : 1e-6, 0.1, es ? atoi(es) : 1, verbose);
 }
 static const LdltBackend oracle_backend = {"cpu-oracle-ldlt", orc_create, oracle_ldlt_destroy, oracle_ldlt_analyse,
                                            oracle_ldlt_values_ptr, oracle_ldlt_factor, oracle_ldlt_solve,
-                                           oracle_ldlt_num_neg, oracle_ldlt_increase_quality, NULL};
+                                           oracle_ldlt_num_neg, oracle_ldlt_increase_quality, NULL, NULL};
 
 // ---- TNLP wrapper that records the final iterate -----------------------------------------------------------
 class CapturingTNLP: public TNLP

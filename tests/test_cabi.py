@@ -11,10 +11,10 @@ from ipopt_b200 import capi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "b200ldlt.h")).read()
+def _declared_symbols(header="b200ldlt.h", prefix="b200ldlt_"):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200ldlt_[a-z_0-9]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(%s[a-z_0-9]+)\s*\(" % prefix, hdr)))
 
 
 def test_header_symbols_are_exported(built_lib):
@@ -24,6 +24,21 @@ def test_header_symbols_are_exported(built_lib):
     for n in names:
         assert hasattr(lib, n), "missing export %s" % n
     assert set(capi.EXPORTED) <= set(names)
+
+
+def test_vector_header_symbols_are_exported(built_lib):
+    """include/b200vec.h: every declared entry point is exported; without a GPU the context
+    constructor refuses (no CPU path)."""
+    lib = ctypes.CDLL(built_lib)
+    names = _declared_symbols("b200vec.h", "b200vec_")
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    import torch
+    if not torch.cuda.is_available():
+        from ipopt_b200.vec import VecContext
+        with pytest.raises(RuntimeError, match="no usable CUDA device"):
+            VecContext()
 
 
 def test_status_codes_match_reference_enum():
