@@ -46,6 +46,8 @@ typedef struct b200ldlt_options {
   int smem_front_max;  /* fronts of order <= this are factored by one CTA in shared memory */
   int use_graph;       /* 1 = replay numeric phases from CUDA graphs */
   int verbose;
+  int tc_schur_min_r;  /* fronts with >= this many contribution rows form their Schur complement on the tensor cores
+                          (tcgen05 int8 Ozaki split, csrc/schur_tc.cu); 0 = off (FP64 DFMA tiles everywhere) */
 } b200ldlt_options;
 
 /* statistics of the last analyse/factor/solve (algorithmic work per SURVEY.md section 8d) */

@@ -25,7 +25,7 @@ class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("stream", C.c_void_p), ("ordering", C.c_int), ("pair_saddle", C.c_int),
                 ("leaf_k", C.c_int), ("relax_frac", C.c_double), ("scaling", C.c_int), ("pivtol", C.c_double),
                 ("pivtolmax", C.c_double), ("tiny", C.c_double), ("smem_front_max", C.c_int),
-                ("use_graph", C.c_int), ("verbose", C.c_int)]
+                ("use_graph", C.c_int), ("verbose", C.c_int), ("tc_schur_min_r", C.c_int)]
 
 
 class Info(C.Structure):

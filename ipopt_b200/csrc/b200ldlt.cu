@@ -16,6 +16,7 @@
 #include "factor_kernels.cu"
 #include "solve_kernels.cu"
 #include "solve_dataflow.cu"
+#include "schur_tc.cu"
 #include "symbolic.hpp"
 
 namespace b200 {
@@ -55,7 +56,8 @@ struct LinvPlan {
 // triangular-solve work of a set of fronts (solve_dataflow.cu): subtrees for k_solve_sub + task lists for k_solve_top
 struct SolvePlan {
   DevBuf<SolveTask> d_tf, d_tb;
-  DevBuf<int> d_bundle, d_sub_ptr, d_lvl_ptr, d_lvl_nsmall, d_sub_fronts, d_sub_root, d_ccnt;
+  DevBuf<int> d_bundle, d_sub_meta, d_ccnt, d_subrow;
+  DevBuf<SubDesc> d_subs;
   DevBuf<double> d_part;
   DevSolve V;
   int nsub = 0, ntf = 0, ntb = 0;
@@ -69,6 +71,20 @@ struct LevelPlan {
   struct Bucket { int off, cnt, fmax, kmax, threads; size_t smem; };
   std::vector<Bucket> small;
   int all_off = 0, all_cnt = 0, fmax = 0;  // whole level (solve)
+  // Schur complements of the level's big fronts: tensor-core (Ozaki int8, schur_tc.cu) for r >= tc_min_r, DFMA tiles else
+  int tc_f_off = 0, tc_f_cnt = 0, tc_t_off = 0, tc_t_cnt = 0, tc_rmax = 0;
+  int df_off = 0, df_cnt = 0, df_rmax = 0;
+};
+
+// device lists behind LevelPlan::tc_* / df_* of one plan set
+struct SchurLists {
+  DevBuf<TcFront> d_f;
+  DevBuf<TcTile> d_t;
+  DevBuf<int> d_dfl;
+  std::vector<TcFront> f;
+  std::vector<TcTile> t;
+  std::vector<int> dfl;
+  long long dig_bytes = 0, exp_ints = 0;   // scratch needed by the largest level
 };
 
 // environment switches for profiling / A-B runs, read ONCE at b200ldlt_create (never on the enqueue path)
@@ -106,12 +122,16 @@ struct Solver {
   int rhs_cap = 0;
   int* h_counters = nullptr;     // pinned
   bool analysed = false, factored = false, have_dev_vals = false;
+  int tc_min_r = 0;                // fronts with r >= this use the tensor-core Schur path (0 = off)
   bool reanalyse = false;          // set by increase_quality after forced pivots: next factor re-runs the analysis on its values
   int n_reanalysed = 0;
   long long n_factor = 0;
   bool reanalysed_since_raise = false;
   Symbolic S;
   std::vector<LevelPlan> plan;
+  SchurLists schur;
+  DevBuf<int8_t> d_tc_dig;           // digit scratch of the tensor-core Schur path (largest level)
+  DevBuf<int> d_tc_exp;
   b200ldlt_info info;
   int num_neg = 0;
   double pivtol = 1e-8;
@@ -134,7 +154,9 @@ struct Solver {
   DevBuf<double> d_bigv, d_bigy;
   DevBuf<unsigned long long> d_ticket, d_tlog;
   DevBuf<double> d_linv;
-  DevBuf<long long> d_linv_off;
+  DevBuf<long long> d_linv_off, d_gmap_off;
+  DevBuf<FrontDesc> d_fdesc;
+  DevBuf<int> d_gmap;
   LinvPlan linv_plan;               // explicit inverses of the big fronts' pivot blocks (all fronts)
   std::vector<SolveTask> h_tasks;   // fwd then bwd (debug timeline)
   SolvePlan splan;                  // all fronts
@@ -146,6 +168,7 @@ struct Solver {
     int rank = 0, world = 1, nsub = 0;
     std::vector<int> owner, cut_roots, top_fronts;
     std::vector<LevelPlan> plan[2];          // [0] my subtrees, [1] top part
+    SchurLists schur[2];
     DevBuf<int> d_fl[2], d_mark_cut, d_mark_top;
     SolvePlan splan[2];
     LinvPlan linv_plan[2];
@@ -202,7 +225,8 @@ struct Solver {
 
 // per level: big fronts first, then the shared-memory classes by descending front order; only fronts with take[s]
 static void build_level_plans(const Symbolic& S, int smax, const std::vector<char>& take, std::vector<int>& fl,
-                              std::vector<LevelPlan>& plan, const std::vector<int>& soft) {
+                              std::vector<LevelPlan>& plan, const std::vector<int>& soft, SchurLists& SL, int tc_min_r) {
+  SL.f.clear(); SL.t.clear(); SL.dfl.clear(); SL.dig_bytes = 0; SL.exp_ints = 0;
   fl.clear();
   fl.reserve(S.nsn);
   plan.assign(S.nlevels, LevelPlan());
@@ -224,6 +248,34 @@ static void build_level_plans(const Symbolic& S, int smax, const std::vector<cha
         P.big_entmax = std::max<long long>(P.big_entmax, S.uent_ptr[s + 1] - S.uent_ptr[s]);
         P.big_zero_max = std::max<long long>(P.big_zero_max, (long long)S.f(s) * S.k(s) + (long long)S.r(s) * S.r(s));
       }
+    }
+    // Schur complements of the big fronts of this level
+    {
+      P.tc_f_off = (int)SL.f.size(); P.tc_t_off = (int)SL.t.size(); P.df_off = (int)SL.dfl.size();
+      long long dig = 0, ex = 0;
+      for (int q = 0; q < P.big_cnt; ++q) {
+        const int s = fl[P.big_off + q];
+        const int r = S.r(s), k = S.k(s);
+        if (r <= 0) continue;
+        if (tc_min_r > 0 && r >= tc_min_r && k >= 32) {
+          TcFront F;
+          F.s = s; F.nks = (k + TC_BK - 1) / TC_BK;
+          const int nra = (r + TC_BM - 1) / TC_BM, nrb = (r + TC_BN - 1) / TC_BN;
+          F.a_off = dig; dig += (long long)nra * F.nks * TC_A_UNIT;
+          F.b_off = dig; dig += (long long)nrb * F.nks * TC_B_UNIT;
+          F.e_off = ex; ex += 2LL * r;
+          const int fi = (int)SL.f.size() - P.tc_f_off;
+          SL.f.push_back(F);
+          for (int ti = 0; ti < nra; ++ti)
+            for (int tj = 0; tj < nrb && tj * TC_BN <= ti * TC_BM + TC_BM - 1; ++tj) SL.t.push_back(TcTile{fi, ti, tj});
+          P.tc_rmax = std::max(P.tc_rmax, r);
+        } else {
+          SL.dfl.push_back(s);
+          P.df_rmax = std::max(P.df_rmax, r);
+        }
+      }
+      P.tc_f_cnt = (int)SL.f.size() - P.tc_f_off; P.tc_t_cnt = (int)SL.t.size() - P.tc_t_off; P.df_cnt = (int)SL.dfl.size() - P.df_off;
+      SL.dig_bytes = std::max(SL.dig_bytes, dig); SL.exp_ints = std::max(SL.exp_ints, ex);
     }
     // small fronts (level_sn is sorted by f descending inside a level)
     // Size classes: (64, smax] 256 threads, (32, 64] 128 threads, <= 32 one warp per front.  Inside a class the
@@ -308,43 +360,59 @@ static int build_linv_plan(Solver* sv, const Symbolic& S, const std::vector<char
 static int enqueue_linv(Solver* sv, const LinvPlan& LP);
 
 // Triangular-solve plan of the fronts in take[] (see solve_dataflow.cu).
-//  * Subtrees: maximal subtrees (of the forest induced by take[]) whose fronts are all of order <= DF_MIDMAX and whose
-//    L panels stay below a byte / front-count cap -> one CTA each in k_solve_sub, largest first.
+//  * Subtrees: maximal subtrees whose fronts are all taken, of order <= DF_MIDMAX, and whose whole working set (SubLayout)
+//    fits the dynamic shared memory of k_solve_sub -> one CTA each, largest first.  Supernodes are numbered in postorder,
+//    so a subtree is the contiguous range [root - size + 1, root] and so are its panels, columns, row lists, child lists.
 //  * Everything else -> topologically sorted task lists for k_solve_top (forward: levels ascending; backward: descending).
-static const long long kSubBytesCap = 256 * 1024;
-static const int kSubFrontsCap = 96;
-
 static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<char>& take, SolvePlan& SP, cudaStream_t st) {
   const int nsn = S.nsn;
-  std::vector<long long> subB(nsn, 0);
-  std::vector<int> subN(nsn, 0), subF(nsn, 0);
-  for (int s = 0; s < nsn; ++s) if (take[s]) {   // children precede parents
-    subB[s] += (long long)S.f(s) * S.k(s) * 8; subN[s] += 1; subF[s] = std::max(subF[s], S.f(s));
+  std::vector<int> size(nsn, 1), ntaken(nsn, 0), subF(nsn, 0);
+  for (int s = 0; s < nsn; ++s) {   // children precede parents
+    ntaken[s] += take[s] ? 1 : 0; subF[s] = std::max(subF[s], S.f(s));
     const int p = S.sn_parent[s];
-    if (p >= 0 && take[p]) { subB[p] += subB[s]; subN[p] += subN[s]; subF[p] = std::max(subF[p], subF[s]); }
+    if (p >= 0) { size[p] += size[s]; ntaken[p] += ntaken[s]; subF[p] = std::max(subF[p], subF[s]); }
   }
-  auto ok = [&](int s) { return take[s] && subF[s] <= DF_MIDMAX && subB[s] <= kSubBytesCap && subN[s] <= kSubFrontsCap; };
-  std::vector<int> sub_of(nsn, -1), roots;
+  auto layout_of = [&](int s) {
+    const int s0 = s - size[s] + 1;
+    SubLayout L;
+    L.nL = S.L_off[s + 1] - S.L_off[s0];
+    L.ncol = S.sn_start[s + 1] - S.sn_start[s0];
+    L.nrt = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s0]);
+    L.rroot = S.r(s);
+    L.nchi = S.child_ptr[s + 1] - S.child_ptr[s0];
+    L.nfront = size[s];
+    L.nmeta = 2 * (S.sn_level[s] + 1) + 1 + size[s];   // upper bound (levels <= height of the root + 1)
+    return L;
+  };
+  auto ok = [&](int s) {
+    if (!take[s] || ntaken[s] != size[s] || subF[s] > DF_MIDMAX || size[s] > 4096) return false;
+    if (s - size[s] + 1 < 0) return false;
+    return layout_of(s).bytes() <= (long long)DF_DYN_SMEM;
+  };
+  std::vector<char> okv(nsn);
+  for (int s = 0; s < nsn; ++s) okv[s] = ok(s) ? 1 : 0;
+  std::vector<int> roots;
+  std::vector<char> insub(nsn, 0);
   for (int s = nsn - 1; s >= 0; --s) {
-    if (!ok(s)) continue;
+    if (!okv[s]) continue;
     const int p = S.sn_parent[s];
-    if (p >= 0 && take[p] && ok(p)) sub_of[s] = sub_of[p];
-    else { sub_of[s] = (int)roots.size(); roots.push_back(s); }
+    if (p >= 0 && okv[p]) continue;
+    roots.push_back(s);
+    for (int q = s - size[s] + 1; q <= s; ++q) insub[q] = 1;
   }
-  // largest subtree first
-  std::vector<int> order(roots.size());
-  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subB[roots[a]] > subB[roots[b]]; });
-  std::vector<int> rank_of(roots.size());
-  for (size_t i = 0; i < order.size(); ++i) rank_of[order[i]] = (int)i;
+  // largest subtree (bytes of L) first
+  std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) {
+    return S.L_off[a + 1] - S.L_off[a - size[a] + 1] > S.L_off[b + 1] - S.L_off[b - size[b] + 1];
+  });
   const int nsub = (int)roots.size();
-  std::vector<std::vector<int>> members(nsub);
+  std::vector<SubDesc> subs(std::max(nsub, 1), SubDesc{0, 0, 0, 0});
+  std::vector<int> meta;
   SP.sub_bytes = 0;
-  for (int s = 0; s < nsn; ++s) if (sub_of[s] >= 0) { members[rank_of[sub_of[s]]].push_back(s); SP.sub_bytes += (long long)S.f(s) * S.k(s) * 8; }
-  std::vector<int> sub_ptr(1, 0), lvl_ptr(1, 0), lvl_nsmall, sub_fronts, sub_root(std::max(nsub, 1), 0);
   for (int u = 0; u < nsub; ++u) {
-    std::vector<int>& M = members[u];
-    sub_root[u] = roots[order[u]];
+    const int sR = roots[u], s0 = sR - size[sR] + 1;
+    SP.sub_bytes += (S.L_off[sR + 1] - S.L_off[s0]) * 8;
+    std::vector<int> M(size[sR]);
+    for (int q = 0; q < size[sR]; ++q) M[q] = s0 + q;
     // by (level, small first, larger first)
     std::stable_sort(M.begin(), M.end(), [&](int a, int b) {
       if (S.sn_level[a] != S.sn_level[b]) return S.sn_level[a] < S.sn_level[b];
@@ -352,16 +420,38 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
       if (sa != sb) return sa;
       return S.f(a) > S.f(b);
     });
+    std::vector<int> lvl(1, 0), nsm;
     for (size_t q = 0; q < M.size();) {
       size_t e = q; int ns = 0;
       while (e < M.size() && S.sn_level[M[e]] == S.sn_level[M[q]]) { if (S.f(M[e]) <= 64) ++ns; ++e; }
-      for (size_t t = q; t < e; ++t) sub_fronts.push_back(M[t]);
-      lvl_ptr.push_back((int)sub_fronts.size());
-      lvl_nsmall.push_back(ns);
+      lvl.push_back((int)e); nsm.push_back(ns);
       q = e;
     }
-    sub_ptr.push_back((int)lvl_nsmall.size());
+    subs[u] = SubDesc{s0, sR, (int)meta.size(), (int)nsm.size()};
+    meta.insert(meta.end(), lvl.begin(), lvl.end());
+    meta.insert(meta.end(), nsm.begin(), nsm.end());
+    meta.insert(meta.end(), M.begin(), M.end());
   }
+  // backward addresses of the contribution rows of the subtree fronts: a row inside the subtree's column range is a local
+  // index into its x slice (>= 0); a row above it is one of the ROOT's contribution rows (every row of a descendant
+  // beyond the root's columns is in the root's row list): -(1 + position there)
+  std::vector<int> subrow(std::max<size_t>(S.rows.size(), 1), 0);
+  for (int u = 0; u < nsub; ++u) {
+    const int sR = roots[u], s0 = sR - size[sR] + 1;
+    const int col0 = S.sn_start[s0], col1 = S.sn_start[sR + 1];
+    const int* rr = S.rows.data() + S.rows_ptr[sR];
+    const int nr = S.r(sR);
+    for (long long e = S.rows_ptr[s0]; e < S.rows_ptr[sR + 1]; ++e) {
+      const int g = S.rows[e];
+      if (g < col1) subrow[e] = g - col0;
+      else {
+        const int* it = std::lower_bound(rr, rr + nr, g);
+        if (it == rr + nr || *it != g) { sv->err = "solve plan: row of a subtree front missing from the root's row list"; return B200LDLT_FATAL_ERROR; }
+        subrow[e] = -(1 + (int)(it - rr));
+      }
+    }
+  }
+  CU(SP.d_subrow.upload(subrow, st));
   // top task lists
   std::vector<SolveTask> tf, tb;
   std::vector<int> bundle;
@@ -385,7 +475,7 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
       for (int phase = 0; phase < 2; ++phase)
         for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
           const int s = S.level_sn[q];
-          if (!take[s] || sub_of[s] >= 0 || S.f(s) <= DF_MIDMAX) continue;
+          if (!take[s] || insub[s] || S.f(s) <= DF_MIDMAX) continue;
           const int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK, ncb = (S.r(s) + DF_BLK - 1) / DF_BLK;
           if (pass == 0 && phase == 0) for (int b = nkb - 1; b >= 0; --b) chunked(T, ST_FP, s, b, 0, b + 1);
           if (pass == 0 && phase == 1) for (int j = 0; j < ncb; ++j) chunked(T, ST_FC, s, j, 0, nkb);
@@ -394,7 +484,7 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
         }
       for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
         const int s = S.level_sn[q];
-        if (!take[s] || sub_of[s] >= 0 || S.f(s) > DF_MIDMAX) continue;
+        if (!take[s] || insub[s] || S.f(s) > DF_MIDMAX) continue;
         if (S.f(s) > 64) T.push_back(SolveTask{ST_MID, s, 0, 0, 0, 0, 1, 0, 0, 0});
         else smalls.push_back(s);
       }
@@ -408,17 +498,15 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
   SP.nsub = nsub; SP.ntf = (int)tf.size(); SP.ntb = (int)tb.size();
   if (sv->opt.verbose)
     fprintf(stderr, "[b200ldlt] solve plan: %d subtrees (%.1f MB of L, largest %.0f KB), top: %d fwd / %d bwd tasks, %lld partial slots\n",
-            nsub, SP.sub_bytes / 1e6, nsub ? subB[roots[order[0]]] / 1e3 : 0.0, SP.ntf, SP.ntb, npart);
+            nsub, SP.sub_bytes / 1e6, nsub ? (S.L_off[roots[0] + 1] - S.L_off[roots[0] - size[roots[0]] + 1]) * 8 / 1e3 : 0.0, SP.ntf, SP.ntb, npart);
   if (sv->dbg.solve_timeline) { sv->h_tasks = tf; sv->h_tasks.insert(sv->h_tasks.end(), tb.begin(), tb.end()); }
   if (tf.empty()) tf.push_back(SolveTask{ST_SMALL, 0, 0, 0, 0, 0, 1, 0, 0, 0});
   if (tb.empty()) tb.push_back(SolveTask{ST_SMALL, 0, 0, 0, 0, 0, 1, 0, 0, 0});
   if (bundle.empty()) bundle.push_back(0);
-  if (sub_fronts.empty()) sub_fronts.push_back(0);
-  if (lvl_nsmall.empty()) lvl_nsmall.push_back(0);
+  if (meta.empty()) meta.push_back(0);
   CU(SP.d_tf.upload(tf, st)); CU(SP.d_tb.upload(tb, st));
   CU(SP.d_bundle.upload(bundle, st));
-  CU(SP.d_sub_ptr.upload(sub_ptr, st)); CU(SP.d_lvl_ptr.upload(lvl_ptr, st)); CU(SP.d_lvl_nsmall.upload(lvl_nsmall, st));
-  CU(SP.d_sub_fronts.upload(sub_fronts, st)); CU(SP.d_sub_root.upload(sub_root, st));
+  CU(SP.d_subs.upload(subs, st)); CU(SP.d_sub_meta.upload(meta, st));
   CU(SP.d_ccnt.alloc(std::max(ncidx, 1)));
   CU(cudaMemsetAsync(SP.d_ccnt.p, 0, SP.d_ccnt.n * sizeof(int), st));
   CU(SP.d_part.alloc(std::max<long long>(npart, 1) * 64));
@@ -431,9 +519,60 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
   V.part = SP.d_part.p; V.ccnt = SP.d_ccnt.p;
   V.ticket = sv->d_ticket.p;
   V.linv = sv->d_linv.p; V.linv_off = sv->d_linv_off.p;
-  V.sub_ptr = SP.d_sub_ptr.p; V.lvl_ptr = SP.d_lvl_ptr.p; V.lvl_nsmall = SP.d_lvl_nsmall.p;
-  V.sub_fronts = SP.d_sub_fronts.p; V.sub_root = SP.d_sub_root.p; V.nsub = nsub;
+  V.fdesc = sv->d_fdesc.p; V.gmap = sv->d_gmap.p; V.gmap_off = sv->d_gmap_off.p;
+  V.subs = SP.d_subs.p; V.sub_meta = SP.d_sub_meta.p; V.subrow = SP.d_subrow.p; V.nsub = nsub;
+  V.upper_max = sv->opt.smem_front_max;
   V.tlog = nullptr;
+  return B200LDLT_SUCCESS;
+}
+
+// per-front records shared by every solve plan: descriptors, gather maps of the big fronts, backward row addresses
+static int build_solve_tables(Solver* sv, const Symbolic& S, cudaStream_t st) {
+  const int nsn = S.nsn;
+  std::vector<FrontDesc> fd(nsn);
+  for (int s = 0; s < nsn; ++s) {
+    FrontDesc& d = fd[s];
+    d.c0 = S.sn_start[s]; d.k = (unsigned short)S.k(s); d.r = (unsigned short)S.r(s);
+    d.ch0 = S.child_ptr[s];
+    const int nch = S.child_ptr[s + 1] - S.child_ptr[s];
+    if (nch > 65535) { sv->err = "front with more than 65535 children"; return B200LDLT_FATAL_ERROR; }
+    d.nch = (unsigned short)nch; d.pad = 0;
+    d.L_off = S.L_off[s]; d.ro = S.rows_ptr[s];
+  }
+  CU(sv->d_fdesc.upload(fd, st));
+  // gather maps of the big fronts: for child slot q and parent row j, the index into cbv (or -1)
+  {
+    std::vector<long long> goff(nsn, 0);
+    long long tot = 0;
+    for (int s = 0; s < nsn; ++s) if (S.f(s) > DF_MIDMAX) {
+      goff[s] = tot; tot += (long long)S.f(s) * (S.child_ptr[s + 1] - S.child_ptr[s]);
+    }
+    if (S.rows.size() >= (size_t)1 << 31) { sv->err = "row structure too large for 32-bit gather maps"; return B200LDLT_FATAL_ERROR; }
+    std::vector<int> gm((size_t)std::max<long long>(tot, 1), -1);
+    for (int s = 0; s < nsn; ++s) if (S.f(s) > DF_MIDMAX) {
+      const int f = S.f(s);
+      for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) {
+        const int c = S.child_idx[q];
+        const long long ro = S.rows_ptr[c];
+        const int rc = S.r(c);
+        int* dst = gm.data() + goff[s] + (long long)(q - S.child_ptr[s]) * f;
+        for (int j = 0; j < rc; ++j) dst[S.rel[ro + j]] = (int)(ro + j);
+      }
+    }
+    CU(sv->d_gmap_off.upload(goff, st));
+    CU(sv->d_gmap.upload(gm, st));
+  }
+  return B200LDLT_SUCCESS;
+}
+
+static int upload_schur_lists(Solver* sv, SchurLists& SL, cudaStream_t st) {
+  std::vector<TcFront> f = SL.f; std::vector<TcTile> t = SL.t; std::vector<int> d = SL.dfl;
+  if (f.empty()) f.push_back(TcFront{0, 0, 0, 0, 0});
+  if (t.empty()) t.push_back(TcTile{0, 0, 0});
+  if (d.empty()) d.push_back(0);
+  CU(SL.d_f.upload(f, st)); CU(SL.d_t.upload(t, st)); CU(SL.d_dfl.upload(d, st));
+  if ((long long)sv->d_tc_dig.n < SL.dig_bytes) CU(sv->d_tc_dig.alloc(SL.dig_bytes));
+  if ((long long)sv->d_tc_exp.n < SL.exp_ints) CU(sv->d_tc_exp.alloc(SL.exp_ints));
   return B200LDLT_SUCCESS;
 }
 
@@ -525,9 +664,11 @@ static int run_analysis(Solver* sv, const double* vals) {
   std::vector<int> fl;
   {
     std::vector<char> take(S.nsn, 1);
-    build_level_plans(S, sv->opt.smem_front_max, take, fl, sv->plan, sv->dbg.buckets);
+    build_level_plans(S, sv->opt.smem_front_max, take, fl, sv->plan, sv->dbg.buckets, sv->schur, sv->tc_min_r);
   }
   CU(sv->d_front_list.upload(fl, st));
+  { int rc2 = upload_schur_lists(sv, sv->schur, st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
+  CU(cudaFuncSetAttribute(k_tc_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CU(cudaFuncSetAttribute(k_front_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CU(cudaFuncSetAttribute(k_front_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -577,18 +718,24 @@ static int run_analysis(Solver* sv, const double* vals) {
     CU(cudaMemsetAsync(sv->d_ticket.p, 0, 2 * sizeof(unsigned long long), st));
     sv->solve_epoch = 0; sv->ticket_f = sv->ticket_b = 0;
     {
+      int rc2 = build_solve_tables(sv, S, st);
+      if (rc2 != B200LDLT_SUCCESS) return rc2;
       std::vector<char> take(S.nsn, 1);
-      int rc2 = build_solve_plan(sv, S, take, sv->splan, st);
+      rc2 = build_solve_plan(sv, S, take, sv->splan, st);
       if (rc2 != B200LDLT_SUCCESS) return rc2;
     }
+    CU(cudaFuncSetAttribute(k_solve_sub<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
+    CU(cudaFuncSetAttribute(k_solve_sub<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
+    CU(cudaFuncSetAttribute(k_solve_top<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
+    CU(cudaFuncSetAttribute(k_solve_top<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
     if (sv->dbg.solve_timeline) {
-      CU(sv->d_tlog.alloc(2 * (size_t)(sv->splan.ntf + sv->splan.ntb) + 2));
+      CU(sv->d_tlog.alloc(2 * (size_t)(sv->splan.ntf + sv->splan.ntb) + 8 * (size_t)sv->splan.nsub + 8));
       sv->splan.V.tlog = sv->d_tlog.p;
     }
     int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_top<true>, DF_THREADS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_top<true>, DF_THREADS, DF_DYN_SMEM));
     int occ_b = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_solve_top<false>, DF_THREADS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_solve_top<false>, DF_THREADS, DF_DYN_SMEM));
     CU(cudaDeviceGetAttribute(&sv->num_sms, cudaDevAttrMultiProcessorCount, sv->dev));
     sv->df_grid = std::max(1, std::min(occ, occ_b)) * sv->num_sms;
     if (sv->opt.verbose)
@@ -620,7 +767,8 @@ static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b
 
 // enqueue the whole numeric factorisation of the values in d_vals
 static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nullptr, const int* fl_p = nullptr,
-                          bool prologue = true, const LinvPlan* linv_p = nullptr) {
+                          bool prologue = true, const LinvPlan* linv_p = nullptr, const SchurLists* sl_p = nullptr) {
+  const SchurLists& SL = sl_p ? *sl_p : sv->schur;
   Symbolic& S = sv->S;
   cudaStream_t st = sv->stream;
   DevSym& D = sv->DS;
@@ -696,20 +844,29 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaEventRecord(e, st));
         CU(cudaStreamWaitEvent(sb, e, 0));
       }
+      // Per panel p:  chain stream:  diag(p) -> next(p)      (next = TRSM of the 32 rows of the next diagonal block + that
+      //                                                     block's rank-32 update; needs the bulk update of panel p-1)
+      //               bulk stream :  trsm(p) [after diag(p)] -> update(p) [after next(p): it reads those 32 rows' L / W]
+      // so diag(p+1) waits for diag(p) + next(p) only, and trsm(p) + update(p) run under the next diagonal block.
+      cudaEvent_t e_upd_prev = nullptr;
       for (int jb = 0; jb < P.big_kmax; jb += NB) {
         k_big_diag<<<P.big_cnt, 32, 0, st>>>(D, N, bl, jb); ++L;
-        cudaEvent_t ec = sv->next_event();
-        CU(cudaEventRecord(ec, st));
-        CU(cudaStreamWaitEvent(sb, ec, 0));
+        cudaEvent_t ed = sv->next_event();
+        CU(cudaEventRecord(ed, st));
+        CU(cudaStreamWaitEvent(sb, ed, 0));
         int rows_below = P.big_fmax - jb;  // upper bound
         int nrowblk = std::max(1u, cdiv(rows_below, 128));
-        k_big_trsm<<<dim3(nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), 128, 0, sb>>>(D, N, bl, jb, nrowblk); ++L;
-        cudaEvent_t et = sv->next_event();
-        CU(cudaEventRecord(et, sb));
-        CU(cudaStreamWaitEvent(st, et, 0));      // diag(p+1) needs L/W of its own rows from trsm(p)
+        k_big_trsm<<<dim3(nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), 128, 0, sb>>>(D, N, bl, jb, nrowblk, 0); ++L;
         int rem_k = P.big_kmax - jb - NB;
         if (rem_k > 0) {
+          if (e_upd_prev) CU(cudaStreamWaitEvent(st, e_upd_prev, 0));   // rows of the next block, columns of this panel: updated through panel p-1
+          k_big_trsm<<<dim3(1, P.big_cnt), 128, 0, st>>>(D, N, bl, jb, 1, 1); ++L;
+          cudaEvent_t en = sv->next_event();
+          CU(cudaEventRecord(en, st));
+          CU(cudaStreamWaitEvent(sb, en, 0));
           k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, sb>>>(D, N, bl, jb, 0); ++L;
+          e_upd_prev = sv->next_event();
+          CU(cudaEventRecord(e_upd_prev, sb));
         }
       }
       {
@@ -718,8 +875,16 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaStreamWaitEvent(st, e, 0));
       }
       sv->mark("big-chain", l);
-      if (P.big_rmax > 0) {   // Schur complement CB -= L21 (L21 D)^T
-        k_big_schur84<<<dim3(cdiv(P.big_rmax, TM), cdiv(P.big_rmax, TM), P.big_cnt), 128, 0, st>>>(D, N, bl); ++L;
+      // Schur complements CB -= L21 (L21 D)^T: tensor cores (Ozaki int8 digits, schur_tc.cu) for the large fronts,
+      // register-blocked DFMA tiles for the rest
+      if (P.tc_t_cnt > 0) {
+        const TcFront* tf = SL.d_f.p + P.tc_f_off;
+        k_tc_slice<<<dim3(cdiv(P.tc_rmax, 8), P.tc_f_cnt), 256, 0, st>>>(D, N, tf, 0, sv->d_tc_dig.p, sv->d_tc_exp.p); ++L;
+        k_tc_slice<<<dim3(cdiv(P.tc_rmax, 8), P.tc_f_cnt), 256, 0, st>>>(D, N, tf, 1, sv->d_tc_dig.p, sv->d_tc_exp.p); ++L;
+        k_tc_schur<<<P.tc_t_cnt, 192, TC_SMEM_BYTES, st>>>(D, N, tf, SL.d_t.p + P.tc_t_off, sv->d_tc_dig.p, sv->d_tc_exp.p); ++L;
+      }
+      if (P.df_cnt > 0) {
+        k_big_schur84<<<dim3(cdiv(P.df_rmax, TM), cdiv(P.df_rmax, TM), P.df_cnt), 128, 0, st>>>(D, N, SL.d_dfl.p + P.df_off); ++L;
       }
     }
   }
@@ -847,17 +1012,17 @@ static int launch_sweep(Solver* sv, const SolvePlan& SP, bool fwd) {
   const int nt = fwd ? SP.ntf : SP.ntb;
   const int grid = std::min(sv->df_grid, std::max(nt, 1));
   if (fwd) {
-    if (SP.nsub > 0) { k_solve_sub<true><<<SP.nsub, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->d_x.p, sv->d_cbv.p); ++sv->launches; }
+    if (SP.nsub > 0) { k_solve_sub<true><<<SP.nsub, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->d_x.p, sv->d_cbv.p); ++sv->launches; }
     if (nt > 0) {
-      k_solve_top<true><<<grid, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p); ++sv->launches;
+      k_solve_top<true><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p); ++sv->launches;
       sv->ticket_f += (unsigned long long)nt + grid;
     }
   } else {
     if (nt > 0) {
-      k_solve_top<false><<<grid, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p); ++sv->launches;
+      k_solve_top<false><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p); ++sv->launches;
       sv->ticket_b += (unsigned long long)nt + grid;
     }
-    if (SP.nsub > 0) { k_solve_sub<false><<<SP.nsub, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->d_x.p, sv->d_cbv.p); ++sv->launches; }
+    if (SP.nsub > 0) { k_solve_sub<false><<<SP.nsub, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->d_x.p, sv->d_cbv.p); ++sv->launches; }
   }
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;
@@ -914,7 +1079,8 @@ static int shard_setup(Solver* sv, int rank, int world) {
   }
   for (int ph = 0; ph < 2; ++ph) {
     std::vector<int> fl;
-    build_level_plans(S, sv->opt.smem_front_max, take[ph], fl, H.plan[ph], sv->dbg.buckets);
+    build_level_plans(S, sv->opt.smem_front_max, take[ph], fl, H.plan[ph], sv->dbg.buckets, H.schur[ph], sv->tc_min_r);
+    { int rc2 = upload_schur_lists(sv, H.schur[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
     { int rc2 = build_linv_plan(sv, S, take[ph], H.linv_plan[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
     { int rc2 = build_solve_plan(sv, S, take[ph], H.splan[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
     if (fl.empty()) fl.push_back(0);
@@ -957,6 +1123,7 @@ void b200ldlt_default_options(b200ldlt_options* o) {
   o->pivtolmax = 1e-4;
   o->tiny = 1e-15;
   o->smem_front_max = 128;
+  o->tc_schur_min_r = 0;
   o->use_graph = 1;   /* 1 = CUDA-graph replay of the factorisation + dataflow solve; 0 = plain launches; 2 = level-per-launch solve */
   o->verbose = 0;
 }
@@ -968,6 +1135,7 @@ b200ldlt_handle b200ldlt_create(const b200ldlt_options* opt) {
   if (sv->opt.smem_front_max < 8) sv->opt.smem_front_max = 8;
   sv->pivtol = sv->opt.pivtol;
   sv->dbg.read();
+  sv->tc_min_r = sv->opt.tc_schur_min_r;
   memset(&sv->info, 0, sizeof(sv->info));
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1114,6 +1282,13 @@ int b200ldlt_dump_solve_timeline(b200ldlt_handle h, const char* path) {
     fprintf(fp, "%zu %d %d %d %d %d %llu %llu\n", i, i < (size_t)sv->splan.ntf ? 0 : 1, T.type, T.s, T.blk,
             s >= 0 ? sv->S.sn_level[s] : -1, t[2 * i], t[2 * i + 1]);
   }
+  // subtree records: "S pass index start loaded end nfront nlv"
+  const size_t base = 2 * (size_t)(sv->splan.ntf + sv->splan.ntb);
+  for (int pass = 0; pass < 2; ++pass)
+    for (int u = 0; u < sv->splan.nsub; ++u) {
+      const unsigned long long* r = t.data() + base + 4 * ((size_t)pass * sv->splan.nsub + u);
+      fprintf(fp, "S %d %d %llu %llu %llu %llu %llu\n", pass, u, r[0], r[1], r[2], r[3] >> 32, r[3] & 0xffffffffull);
+    }
   fclose(fp);
   return B200LDLT_SUCCESS;
 }
@@ -1168,7 +1343,7 @@ int b200ldlt_shard_factor(b200ldlt_handle h, int phase, int from_host) {
     if (from_host) CU(cudaMemcpyAsync(sv->d_vals.p, sv->h_vals, sv->nnz * sizeof(double), cudaMemcpyHostToDevice, st));
     sv->have_dev_vals = true;
   }
-  return enqueue_factor(sv, &sv->shard.plan[phase], sv->shard.d_fl[phase].p, phase == 0, &sv->shard.linv_plan[phase]);
+  return enqueue_factor(sv, &sv->shard.plan[phase], sv->shard.d_fl[phase].p, phase == 0, &sv->shard.linv_plan[phase], &sv->shard.schur[phase]);
 }
 
 /* counters_total: CNT_N ints already summed over the ranks (all-reduce of device_ptr("counters")) */

@@ -565,19 +565,23 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
   factor_front_smem<WARP>(F, ld, f, k, lp, pt, cv1, cv2, sh, N.u, N.tiny, N.dinv + c0, N.doff + c0,
                           N.ptype + c0, N.counters);
 
-  // write L panel (f x k, ld = f), unit diagonal, zero strictly-upper part of the pivot block
-  double* __restrict__ P = N.L + S.L_off[s];
+  // write L panel (f x k, ld = f), unit diagonal.  The strictly-upper part of the k x k pivot block receives L11^T
+  // (entry (i, t), i < t, = L[t][i]): the backward solve of the small fronts reads row t of L11 as the contiguous
+  // column segment P[0..t) + t*f instead of a stride-f gather (solve_dataflow.cu, w64_bwd).
   // (the pivot columns of F hold the unscaled values L*D: apply D^-1 = {cv1 = dinv, cv2 = doff} here)
+  double* __restrict__ P = N.L + S.L_off[s];
+  auto lval = [&](int row, int col) -> double {   // L[row][col], row > col
+    const int ty = pt[col];
+    if (ty == 1) return F[row + col * ld] * cv1[col];
+    if (ty == 2) return (row == col + 1) ? 0.0 : fma(F[row + col * ld], cv1[col], F[row + (col + 1) * ld] * cv2[col]);
+    return fma(F[row + (col - 1) * ld], cv2[col - 1], F[row + col * ld] * cv1[col]);
+  };
   for (int t = tid >> 5; t < k; t += (nt >> 5)) {
-    const int ty = pt[t];
     for (int i = tid & 31; i < f; i += 32) {
       double v;
-      if (i < t) v = 0.0;
+      if (i < t) v = lval(t, i);
       else if (i == t) v = 1.0;
-      else if (ty == 2 && i == t + 1) v = 0.0;
-      else if (ty == 1) v = F[i + t * ld] * cv1[t];
-      else if (ty == 2) v = fma(F[i + t * ld], cv1[t], F[i + (t + 1) * ld] * cv2[t]);
-      else v = fma(F[i + (t - 1) * ld], cv2[t - 1], F[i + t * ld] * cv1[t]);
+      else v = lval(i, t);
       P[i + (size_t)t * f] = v;
     }
   }
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const in
   for (int t = 0; t < 32; ++t) {
     if (t < k && lane < f) {
       double v;
-      if (lane < t) v = 0.0;
+      if (lane < t) v = F[order[t] * 33 + lane];   // L11^T in the upper triangle (see k_front_smem)
       else if (lane == t) v = 1.0;
       else v = F[orig * 33 + t];
       P[lane + (size_t)t * f] = v;
@@ -803,8 +807,11 @@ __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* 
 // columns per CTA.
 #define TRSM_LD 34          // even leading dimension: column t of the block starts 16-byte aligned
 #define TRSM_SWAP_COLS 32   // columns per row-swap CTA (4 warps x 8)
+// mode 1 ("next", on the CHAIN stream): ONE CTA per front handles only the rows of the NEXT diagonal block (row0 .. row0+31)
+//   and applies this panel's rank-nb update to that 32x32 block -- all the next k_big_diag depends on;
+// mode 0 (bulk stream): every other row below the block (+ the row-interchange CTAs).
 __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
-                                                  int nrowblk) {
+                                                  int nrowblk, int mode) {
   __shared__ __align__(16) double Lb[NB * TRSM_LD];
   __shared__ double Ln[NB * 33], Wn[NB * 33];   // CTA 0: L / W rows of the next diagonal block
   __shared__ double di[NB], dup[NB], dlo[NB];
@@ -817,6 +824,8 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
   const int row0 = jb + nb;
   double* P = N.L + S.L_off[s];
   const int tid = threadIdx.x;
+  const int nxt = max(0, min(NB, k - row0));   // rows of the next diagonal block (pivot rows right below this block)
+  if (mode == 1 && nxt == 0) return;
   if ((int)blockIdx.x >= nrowblk) {
     // ---- left part: rows jb..jb+nb of columns [0, jb) get the block permutation ----
     const int lane = tid & 31, warp = tid >> 5;
@@ -837,10 +846,10 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
     }
     return;
   }
-  if ((long long)blockIdx.x * blockDim.x >= f - row0 && blockIdx.x != 0) return;
+  if (mode == 0 && (long long)blockIdx.x * blockDim.x >= f - row0 - nxt) return;
   double* Wp = N.W + S.L_off[s];
-  const int i = row0 + blockIdx.x * blockDim.x + tid;
-  const bool active = i < f;
+  const int i = (mode == 1) ? row0 + tid : row0 + nxt + blockIdx.x * blockDim.x + tid;
+  const bool active = (mode == 1) ? (tid < nxt) : (i < f);
   // issue all global loads up front: the diagonal block, its D, and this thread's row (columns in pivot order)
   {
     double lb[NB * NB / 128];
@@ -870,7 +879,7 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
   __syncthreads();
   // CTA 0 owns the rows of the NEXT panel's diagonal block: it also applies this panel's rank-32 update to that
   // 32x32 block (the bulk trailing update skips it), so the next k_big_diag can start right after this kernel.
-  const int nb2 = (blockIdx.x == 0) ? max(0, min(NB, k - row0)) : 0;
+  const int nb2 = (mode == 1) ? nxt : 0;
   double x[NB];
 #pragma unroll
   for (int t = 0; t < NB; ++t) x[t] = (active && t < nb) ? P[i + (size_t)(jb + bp[t]) * f] : 0.0;

@@ -1,18 +1,23 @@
 // Supernodal triangular solve (forward L, D^-1, backward L^T): TWO kernels per sweep.
 //
 //   k_solve_sub<FWD> : the BOTTOM of the elimination tree.  The tree below the big separator fronts is cut into
-//                      subtrees of bounded size (bytes of L, number of fronts, front order <= 256); ONE CTA walks one
-//                      subtree level by level -- fronts of order <= 64 one warp each, larger ones by the whole CTA --
-//                      with CTA barriers only: no global flags, no tickets, no atomics.  Subtrees are launched largest
-//                      first (the hardware block scheduler then does LPT scheduling).
+//                      subtrees whose whole working set -- the L panels (contiguous in memory: supernodes are numbered in
+//                      postorder), right-hand side, D, permutations, row maps, front descriptors -- fits in shared memory.
+//                      ONE CTA owns one subtree: a single TMA bulk copy (cp.async.bulk + mbarrier) brings the L panels
+//                      in, then the CTA walks the subtree level by level out of shared memory -- fronts of order <= 64
+//                      one warp each, larger ones by the whole CTA -- with CTA barriers only: no global flags, no
+//                      tickets, no atomics, no dependent global loads on the critical path; update vectors between the
+//                      fronts of a subtree never leave shared memory.  Subtrees are launched largest first (the
+//                      hardware block scheduler then does LPT scheduling); two CTAs per SM overlap one subtree's bulk
+//                      load with the other's arithmetic.
 //   k_solve_top<FWD> : everything above the subtrees: a persistent task-queue kernel.  Fronts up to order 256 are one
-//                      task each; a front larger than that is cut into (64-row block) x (4-tile chunk) GEMV tasks on the
-//                      EXPLICIT inverse of its pivot block (k_linv_*), so a separator front of order 1000+ keeps ~50
-//                      CTAs busy instead of a chain of block steps.  A task waits for its producers through
-//                      ld.acquire/st.release flags; it only ever waits for tasks EARLIER in the (topologically sorted)
-//                      list and every ticket holder is resident, so the scheme cannot deadlock.  Chunk partials are
-//                      combined by the last-arriving CTA in chunk order (fence + counter), so results do not depend on
-//                      arrival order: bit-reproducible.
+//                      task each (panel staged in shared memory by a bulk copy when it fits); a front larger than that
+//                      is cut into (64-row block) x (2-tile chunk) GEMV tasks on the EXPLICIT inverse of its pivot
+//                      block (k_linv_*), so a separator front of order 1000+ keeps ~100 CTAs busy instead of a chain of
+//                      block steps.  A task waits for its producers through ld.acquire/st.release flags; it only ever
+//                      waits for tasks EARLIER in the (topologically sorted) list and every ticket holder is resident,
+//                      so the scheme cannot deadlock.  Chunk partials are combined by the last-arriving CTA in chunk
+//                      order (fence + counter), so results do not depend on arrival order: bit-reproducible.
 // Forward: sub then top; backward: top then sub (the kernel boundary is the only synchronisation between the two).
 // L is streamed exactly once per sweep (HBM-bound, SURVEY.md 8d: 2*8*nnz(L) bytes per right-hand side); children ->
 // parent data flows through per-front update vectors gathered by the parent (no atomics on the data path).
@@ -27,9 +32,11 @@ namespace b200 {
 
 #define DF_THREADS 256
 #define DF_BLK 64            // block-row / block-column size of the big-front tasks
-#define DF_CH 4              // 64x64 tiles per chunk task
+#define DF_CH 2              // 64x64 tiles per chunk task (both tiles are in flight before the task waits for its inputs)
 #define DF_MIDMAX 256        // fronts above this order are "big" (block tasks + explicit L11 inverse)
-#define DF_SMEM_DOUBLES 1600 // max(mid front: 2*256 + 32*33 = 1568, big task: 256 + 256 + 64 + 128 + 64 = 768)
+#define DF_DYN_SMEM (100 * 1024)   // dynamic shared memory of both solve kernels (2 CTAs per SM)
+#define DF_WSCR 64           // doubles of per-warp scratch (small fronts)
+#define DF_MIDSCR 512        // doubles of CTA scratch for a mid front (v[f] | w[f], f <= 256)
 
 enum { ST_SMALL = 0, ST_MID = 1, ST_FP = 2, ST_FC = 3, ST_BT = 4, ST_BX = 5 };
 
@@ -38,6 +45,21 @@ enum { ST_SMALL = 0, ST_MID = 1, ST_FP = 2, ST_FC = 3, ST_BT = 4, ST_BX = 5 };
 // ST_FP/FC/BT/BX : s = front, blk = 64-block, tiles [t0, t1) of the contraction, chunk q of nq,
 //                  pbase = first partial slot of (s, kind, blk), cidx = its arrival counter
 struct SolveTask { int type, s, blk, t0, t1, q, nq, pbase, cidx, pad; };
+
+// everything a front routine needs to know about a front, in ONE 32-byte record (two 16-byte loads from one sector)
+struct __align__(16) FrontDesc {
+  int c0;                  // first (permuted) column
+  unsigned short k, r;     // pivot columns, contribution rows
+  int ch0;                 // first entry in child_idx
+  unsigned short nch, pad;
+  long long L_off;         // panel offset in L
+  long long ro;            // offset of the row list / update vector (rows_ptr)
+};
+
+// one subtree of k_solve_sub: supernodes [s0, sR] (contiguous: postorder), its level schedule at meta[moff ...]:
+//   meta[moff] = nlv ; then nlv+1 level offsets into the front list ; then nlv counts of small (order <= 64) fronts ;
+//   then the front list itself (nfront ids, by level, small fronts first)
+struct SubDesc { int s0, sR, moff, nlv; };
 
 struct DevSolve {
   const SolveTask* tasks;      // forward list (top part)
@@ -59,14 +81,15 @@ struct DevSolve {
   unsigned long long* ticket;  // [0] fwd, [1] bwd (monotonic)
   const double* linv;          // explicit inverses of the big fronts' pivot blocks L11 (K64 x K64 each, see k_linv_*)
   const long long* linv_off;   // nsn : offset of a big front's inverse in linv, -1 = none
-  // subtrees (k_solve_sub): subtree u owns levels [sub_ptr[u], sub_ptr[u+1]) of lvl_*; level e owns the fronts
-  // sub_fronts[lvl_ptr[e] .. lvl_ptr[e+1]) -- the first lvl_nsmall[e] of them have order <= 64
-  const int* sub_ptr;
-  const int* lvl_ptr;
-  const int* lvl_nsmall;
-  const int* sub_fronts;
-  const int* sub_root;         // root front of each subtree (its done_f is published for the top kernel)
+  const FrontDesc* fdesc;      // nsn
+  const int* gmap;             // big fronts: gather map, gmap[gmap_off[s] + q*f + j] = index into cbv of the entry child q
+  const long long* gmap_off;   //   adds to (pre-pivot) local row j of the parent, or -1
+  const SubDesc* subs;         // subtrees of k_solve_sub
+  const int* sub_meta;
+  const int* subrow;           // aligned with rows: backward address of a contribution row inside its subtree:
+                               //   >= 0 : column (local index into the subtree's x slice) ; < 0 : -(1 + index into the root's rows)
   int nsub;
+  int upper_max;               // fronts up to this order carry L11^T in the upper triangle of their pivot block
   unsigned long long* tlog;    // optional (debug): 2 timestamps per top task, fwd then bwd; nullptr = off
 };
 
@@ -82,12 +105,71 @@ __device__ __forceinline__ void wait_eq(const int* p, int epoch) {
   while (ld_acquire(p) != epoch) __nanosleep(20);
 }
 
+// ---- TMA 1-D bulk copy global -> shared with mbarrier completion (sm_90+; PTX cp.async.bulk) ---------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bytes: multiple of 16, both addresses 16-byte aligned; a single request may not exceed the mbarrier tx range -> split
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned long long bytes, unsigned long long* bar) {
+  const unsigned long long CH = 64 * 1024;
+  for (unsigned long long o = 0; o < bytes; o += CH) {
+    const unsigned n = (unsigned)((bytes - o < CH) ? (bytes - o) : CH);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32((const char*)dst + o)),
+                 "l"((const char*)src + o), "r"(n), "r"(smem_u32(bar))
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// fronts of order <= 64: one warp per front, two rows per lane (lane, lane+32), L streamed straight from global
-// memory: the loads do not depend on the running vector, so 16 columns are always in flight ahead of the shuffle chain.
-// FLAGS = true : top kernel (wait for the children / the parent, publish done flags)
-// FLAGS = false: subtree kernel (ordering comes from CTA barriers)
-// smem per warp: w[64]
+// Where a front routine finds its data.  SUB = true : shared-memory slices of one subtree (supernodes [s0, sR]); children
+// outside that range (only with a sharded tree) are read from global memory.  SUB = false : the global arrays.
+// ------------------------------------------------------------------------------------------------
+struct FrontIO {
+  const double* Lbase; long long L0;     // panel of front s at Lbase + (fd.L_off - L0)
+  double* xs; int col0;                  // right-hand side / solution entry of column c at xs[c - col0]
+  double* uv; long long ro0;             // update vector of front s at uv + (fd.ro - ro0)
+  const double* dinv; const double* doff; const int* ptype; const int* lperm;   // [c - col0]
+  const int* rel;                        // [ro - ro0 + j]
+  const int* subrow; const double* rootx;   // SUB, backward: addresses of the contribution rows (see DevSolve::subrow)
+  const FrontDesc* fd; int s0, sR;       // descriptors: fd[s - s0]
+  const int* chi; int ch00;              // child lists: chi[ch - ch00]
+  // global arrays (children outside a subtree; rows of ancestors)
+  const FrontDesc* gfd; const double* gcbv; const int* grel; const int* grows; const double* gx;
+};
+
+template <bool SUB>
+__device__ __forceinline__ double ldv(const double* p) { return SUB ? *p : __ldcg(p); }
+
+__device__ __forceinline__ FrontDesc load_fd(const FrontDesc* p) {
+  const int4 a = reinterpret_cast<const int4*>(p)[0], b = reinterpret_cast<const int4*>(p)[1];
+  FrontDesc d;
+  d.c0 = a.x; d.k = (unsigned short)(a.y & 0xffff); d.r = (unsigned short)((unsigned)a.y >> 16);
+  d.ch0 = a.z; d.nch = (unsigned short)(a.w & 0xffff); d.pad = 0;
+  d.L_off = ((long long)(unsigned)b.x) | ((long long)b.y << 32);
+  d.ro = ((long long)(unsigned)b.z) | ((long long)b.w << 32);
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fronts of order <= 64: one warp per front, two rows per lane (lane, lane+32)
+// scratch per warp: w[64]
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void w64_load8(const double* __restrict__ P, int f, int k, int i0, int i1, int tb,
                                           double (&l0)[8], double (&l1)[8]) {
@@ -111,63 +193,65 @@ __device__ __forceinline__ void w64_fstep8(int k, int tb, const double (&l0)[8],
   }
 }
 
-template <bool FLAGS>
-__device__ void w64_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* w,
-                        double* __restrict__ x, double* __restrict__ cbv) {
+template <bool SUB>
+__device__ void w64_fwd(const FrontIO& io, const DevSolve& V, int s, int epoch, double* w) {
   const int lane = threadIdx.x & 31;
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const long long ro = S.rows_ptr[s];
-  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
-  const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
+  const FrontDesc fd = load_fd(io.fd + (s - io.s0));
+  const int k = fd.k, r = fd.r, f = k + r, nch = fd.nch;
+  const int cl = fd.c0 - io.col0;
+  const long long rol = fd.ro - io.ro0;
   const int i0 = lane, i1 = lane + 32;
-  const double* __restrict__ P = N.L + S.L_off[s];
+  const double* __restrict__ P = io.Lbase + (fd.L_off - io.L0);
   double a0[8], a1[8], b0[8], b1[8];
-  w64_load8(P, f, k, i0, i1, 0, a0, a1);            // in flight while the children are gathered
-  w[i0] = (i0 < k) ? x[c0 + i0] : 0.0;
-  w[i1] = (i1 < k) ? x[c0 + i1] : 0.0;
+  w64_load8(P, f, k, i0, i1, 0, a0, a1);            // (global: in flight while the children are gathered)
+  w[i0] = (i0 < k) ? io.xs[cl + i0] : 0.0;
+  w[i1] = (i1 < k) ? io.xs[cl + i1] : 0.0;
+  const int lp0 = (i0 < k) ? io.lperm[cl + i0] : i0, lp1 = (i1 < k) ? io.lperm[cl + i1] : i1;
   __syncwarp();
   for (int q0 = 0; q0 < nch; q0 += 32) {
     // child metadata lane-parallel, then the children one after the other (their targets may overlap); the
     // (index, value) pairs of child q+1 are in flight while child q is added
     const int m = min(32, nch - q0);
-    int cq = -1, rq = 0;
+    int rq = 0, inq = 1;
     long long oq = 0;
     if (lane < m) {
-      cq = S.child_idx[ch0 + q0 + lane];
-      oq = S.rows_ptr[cq];
-      rq = (int)(S.rows_ptr[cq + 1] - oq);
-      if (FLAGS) wait_eq(V.done_f + cq, epoch);
+      const int c = io.chi[fd.ch0 - io.ch00 + q0 + lane];
+      inq = (!SUB) || (c >= io.s0 && c <= io.sR);
+      const FrontDesc cd = load_fd(inq ? io.fd + (c - io.s0) : io.gfd + c);
+      oq = cd.ro; rq = cd.r;
+      if (!SUB) wait_eq(V.done_f + c, epoch);
     }
     __syncwarp();
     int nidx0 = 0, nidx1 = 0;
     double nval0 = 0.0, nval1 = 0.0;
     bool nok0 = false, nok1 = false;
-    {
-      const long long o = __shfl_sync(0xffffffffu, oq, 0);
-      const int rc = __shfl_sync(0xffffffffu, rq, 0);
+    auto fetch = [&](int q) {
+      const long long o = __shfl_sync(0xffffffffu, oq, q);
+      const int rc = __shfl_sync(0xffffffffu, rq, q);
+      const int in = __shfl_sync(0xffffffffu, inq, q);
+      const int* __restrict__ rl = (SUB && in) ? io.rel + (o - io.ro0) : io.grel + o;
+      const double* __restrict__ src = (SUB && in) ? io.uv + (o - io.ro0) : io.gcbv + o;
       nok0 = lane < rc; nok1 = lane + 32 < rc;
-      if (nok0) { nidx0 = S.rel[o + lane]; nval0 = __ldcg(cbv + o + lane); }
-      if (nok1) { nidx1 = S.rel[o + lane + 32]; nval1 = __ldcg(cbv + o + lane + 32); }
-    }
+      if (SUB && in) {
+        if (nok0) { nidx0 = rl[lane]; nval0 = src[lane]; }
+        if (nok1) { nidx1 = rl[lane + 32]; nval1 = src[lane + 32]; }
+      } else {
+        if (nok0) { nidx0 = rl[lane]; nval0 = __ldcg(src + lane); }
+        if (nok1) { nidx1 = rl[lane + 32]; nval1 = __ldcg(src + lane + 32); }
+      }
+    };
+    fetch(0);
     for (int q = 0; q < m; ++q) {
       const int idx0 = nidx0, idx1 = nidx1;
       const double val0 = nval0, val1 = nval1;
       const bool ok0 = nok0, ok1 = nok1;
-      if (q + 1 < m) {
-        const long long o = __shfl_sync(0xffffffffu, oq, q + 1);
-        const int rc = __shfl_sync(0xffffffffu, rq, q + 1);
-        nok0 = lane < rc; nok1 = lane + 32 < rc;
-        if (nok0) { nidx0 = S.rel[o + lane]; nval0 = __ldcg(cbv + o + lane); }
-        if (nok1) { nidx1 = S.rel[o + lane + 32]; nval1 = __ldcg(cbv + o + lane + 32); }
-      }
+      if (q + 1 < m) fetch(q + 1);
       if (ok0) w[idx0] += val0;   // rel is strictly increasing inside a child: no two lanes hit the same entry
       if (ok1) w[idx1] += val1;
       __syncwarp();
     }
   }
-  double v0 = 0.0, v1 = 0.0;
-  if (i0 < f) v0 = (i0 < k) ? w[N.lperm[c0 + i0]] : w[i0];
-  if (i1 < f) v1 = (i1 < k) ? w[N.lperm[c0 + i1]] : w[i1];
+  double v0 = (i0 < f) ? w[lp0] : 0.0, v1 = (i1 < f) ? w[lp1] : 0.0;
   for (int tb = 0; tb < k; tb += 16) {
     if (tb + 8 < k) w64_load8(P, f, k, i0, i1, tb + 8, b0, b1);
     w64_fstep8(k, tb, a0, a1, v0, v1);
@@ -183,16 +267,16 @@ __device__ void w64_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
     const int i = lane + 32 * h;
     const double v = h ? v1 : v0;
     if (i < k) {
-      const int ty = N.ptype[c0 + i];
+      const int ty = io.ptype[cl + i];
       double y;
-      if (ty == 1) y = v * N.dinv[c0 + i];
-      else if (ty == 2) y = v * N.dinv[c0 + i] + w[i + 1] * N.doff[c0 + i];
-      else y = w[i - 1] * N.doff[c0 + i - 1] + v * N.dinv[c0 + i];
-      x[c0 + i] = y;
-    } else if (i < f) cbv[ro + i - k] = v;
+      if (ty == 1) y = v * io.dinv[cl + i];
+      else if (ty == 2) y = v * io.dinv[cl + i] + w[i + 1] * io.doff[cl + i];
+      else y = w[i - 1] * io.doff[cl + i - 1] + v * io.dinv[cl + i];
+      io.xs[cl + i] = y;
+    } else if (i < f) io.uv[rol + i - k] = v;
   }
   __syncwarp();
-  if (FLAGS && lane == 0) st_release(V.done_f + s, epoch);
+  if (!SUB && lane == 0) st_release(V.done_f + s, epoch);
 }
 
 // sum over the 32 lanes of p[t], t = 0..31: lane t receives the total of column t (31 shuffles instead of 32 x 5)
@@ -230,25 +314,35 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&p)[32]) {
   return p[0];
 }
 
-template <bool FLAGS>
-__device__ void w64_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch,
-                        double* __restrict__ x) {
+// value of contribution row j of the front (backward): the solution entry of that (ancestor) column
+template <bool SUB>
+__device__ __forceinline__ double cb_row_x(const FrontIO& io, long long rol, long long ro, int j) {
+  if (SUB) {
+    const int a = io.subrow[rol + j];
+    return a >= 0 ? io.xs[a] : io.rootx[-a - 1];
+  }
+  return __ldcg(io.gx + io.grows[ro + j]);
+}
+
+template <bool SUB>
+__device__ void w64_bwd(const FrontIO& io, const DevSolve& V, int s, int epoch, int parent, int upper_max) {
   const int lane = threadIdx.x & 31;
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const long long ro = S.rows_ptr[s];
-  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  const FrontDesc fd = load_fd(io.fd + (s - io.s0));
+  const int k = fd.k, r = fd.r, f = k + r;
+  const int cl = fd.c0 - io.col0;
+  const long long rol = fd.ro - io.ro0;
   const int i0 = lane, i1 = lane + 32;
-  const double* __restrict__ P = N.L + S.L_off[s];
-  if (FLAGS) {
-    const int par = S.sn_parent[s];
-    if (par >= 0 && lane == 0) wait_eq(V.done_b + par, epoch);
+  const double* __restrict__ P = io.Lbase + (fd.L_off - io.L0);
+  if (!SUB) {
+    if (parent >= 0 && lane == 0) wait_eq(V.done_b + parent, epoch);
     __syncwarp();
   }
   double v0 = 0.0, v1 = 0.0;  // entries i0 / i1 of [D^-1 y ; x(rows)]
-  if (i0 < k) v0 = x[c0 + i0]; else if (i0 < f) v0 = __ldcg(x + S.rows[ro + i0 - k]);
-  if (i1 < k) v1 = x[c0 + i1]; else if (i1 < f) v1 = __ldcg(x + S.rows[ro + i1 - k]);
+  if (i0 < k) v0 = io.xs[cl + i0]; else if (i0 < f) v0 = cb_row_x<SUB>(io, rol, fd.ro, i0 - k);
+  if (i1 < k) v1 = io.xs[cl + i1]; else if (i1 < f) v1 = cb_row_x<SUB>(io, rol, fd.ro, i1 - k);
+  const int lp0 = (i0 < k) ? io.lperm[cl + i0] : 0, lp1 = (i1 < k) ? io.lperm[cl + i1] : 0;
   if (k <= 32) {
-    // (1) rectangular part  u_t = sum_{i >= k} L[i,t] v_i : no chain -- coalesced column loads (lane = row), per-lane
+    // (1) rectangular part  u_t = sum_{i >= k} L[i,t] v_i : no chain -- column loads with lane = row, per-lane
     //     products for all 32 columns, one transposing warp reduction (lane t gets u_t)
     const bool cb0 = i0 >= k && i0 < f, cb1 = i1 < f;
     const double m0 = cb0 ? v0 : 0.0, m1 = cb1 ? v1 : 0.0;
@@ -265,23 +359,30 @@ __device__ void w64_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
 #pragma unroll
       for (int q = 0; q < 8; ++q) p[tb + q] = fma(l0[q], m0, l1[q] * m1);
     }
-    // (2) triangle: lane t owns column t; its sub-diagonal entries L[ii, t] (ii > t) are 31 independent loads
-    //     (column t is contiguous: 16 consecutive ii share a 128-byte line), then a chain of k-1 shuffle+FMA steps
-    double lr[32];
-#pragma unroll
-    for (int ii = 1; ii < 32; ++ii) lr[ii] = (ii < k && lane < ii) ? P[ii + (size_t)lane * f] : 0.0;
     const double u = warp_transpose_reduce(p);
+    // (2) triangle, lane t owns column t:  z_t -= L[ii][t] x_ii for ii = k-1 .. t+1.  Row ii of L11 is read from the
+    //     UPPER triangle of the pivot block, where the factorisation stored L11^T: P[t + ii*f], t < ii -- contiguous
+    //     across the lanes (the lower triangle would be a stride-f gather).
     double z = (lane < k) ? v0 - u : 0.0;
+    for (int tb = ((k - 1) >> 3) << 3; tb >= 0; tb -= 8) {
+      double lr[8];
 #pragma unroll
-    for (int ii = 31; ii >= 1; --ii) {
-      if (ii < k) {   // warp-uniform
-        const double xi = __shfl_sync(0xffffffffu, z, ii);
-        z = fma(-lr[ii], xi, z);
+      for (int q = 0; q < 8; ++q) {
+        const int ii = tb + q;
+        lr[q] = (ii < k && lane < ii) ? (f <= upper_max ? P[lane + (size_t)ii * f] : P[ii + (size_t)lane * f]) : 0.0;
+      }
+#pragma unroll
+      for (int q = 7; q >= 0; --q) {
+        const int ii = tb + q;
+        if (ii < k && ii >= 1) {   // warp-uniform
+          const double xi = __shfl_sync(0xffffffffu, z, ii);
+          z = fma(-lr[q], xi, z);
+        }
       }
     }
-    if (lane < k) x[c0 + N.lperm[c0 + lane]] = z;
+    if (lane < k) io.xs[cl + lp0] = z;
   } else {
-    // columns from the last to the first: v_t -= sum_{i>t} L[i,t] v_i  (column read coalesced, warp-sum)
+    // columns from the last to the first: v_t -= sum_{i>t} L[i,t] v_i  (column read with lane = row, warp-sum)
     for (int tb = k - 1; tb >= 0; tb -= 8) {
       double l0[8], l1[8];
 #pragma unroll
@@ -301,53 +402,67 @@ __device__ void w64_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
         }
       }
     }
-    if (i0 < k) x[c0 + N.lperm[c0 + i0]] = v0;
-    if (i1 < k) x[c0 + N.lperm[c0 + i1]] = v1;
+    // (all lanes must have read their z entries before the permuted write-back: the reads happened at the top)
+    if (i0 < k) io.xs[cl + lp0] = v0;
+    if (i1 < k) io.xs[cl + lp1] = v1;
   }
   __syncwarp();
-  if (FLAGS && lane == 0) st_release(V.done_b + s, epoch);
+  if (!SUB && lane == 0) st_release(V.done_b + s, epoch);
 }
 
 // ------------------------------------------------------------------------------------------------
-// mid fronts (65 .. 256): one CTA, blocked by 32
-// smem: v[f] | w[f] | Lb[32*33]
+// mid fronts (65 .. 256): one CTA, blocked by 32; scratch: v[f] | w[f]
 // ------------------------------------------------------------------------------------------------
-template <bool FLAGS>
-__device__ void mid_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
-                        double* __restrict__ x, double* __restrict__ cbv) {
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]), f = k + r;
-  double* v = sm;
-  double* w = sm + f;
-  double* Lb = sm + 2 * f;
+template <bool SUB>
+__device__ void mid_fwd(const FrontIO& io, const DevSolve& V, int s, int epoch, double* scr, const double* Lp_override,
+                        unsigned long long* mbar, unsigned mphase) {
+  const FrontDesc fd = load_fd(io.fd + (s - io.s0));
+  const int k = fd.k, r = fd.r, f = k + r, nch = fd.nch;
+  const int cl = fd.c0 - io.col0;
+  const long long rol = fd.ro - io.ro0;
+  double* v = scr;
+  double* w = scr + f;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  const int ch0 = S.child_ptr[s], ch1 = S.child_ptr[s + 1];
-  if (FLAGS) for (int q = ch0 + tid; q < ch1; q += nt) wait_eq(V.done_f + S.child_idx[q], epoch);
-  for (int i = tid; i < f; i += nt) w[i] = (i < k) ? x[c0 + i] : 0.0;
+  if (!SUB) for (int q = tid; q < nch; q += nt) wait_eq(V.done_f + io.chi[fd.ch0 - io.ch00 + q], epoch);
+  for (int i = tid; i < f; i += nt) w[i] = (i < k) ? io.xs[cl + i] : 0.0;
   __syncthreads();
-  for (int q = ch0; q < ch1; ++q) {
-    const int c = S.child_idx[q];
-    const long long o = S.rows_ptr[c];
-    const int rc = (int)(S.rows_ptr[c + 1] - o);
-    for (int t = tid; t < rc; t += nt) w[S.rel[o + t]] += __ldcg(cbv + o + t);
-    __syncthreads();
-  }
-  const int* __restrict__ lp = N.lperm + c0;
-  for (int i = tid; i < f; i += nt) v[i] = (i < k) ? w[lp[i]] : w[i];
-  __syncthreads();
-  const double* __restrict__ P = N.L + S.L_off[s];
-  for (int t0 = 0; t0 < k; t0 += 32) {
-    const int nb = min(32, k - t0);
-    for (int t = tid; t < nb * nb; t += nt) {
-      int i = t % nb, q = t / nb;
-      Lb[i + q * 33] = P[(t0 + i) + (size_t)(t0 + q) * f];
+  for (int q = 0; q < nch; ++q) {
+    const int c = io.chi[fd.ch0 - io.ch00 + q];
+    const bool in = (!SUB) || (c >= io.s0 && c <= io.sR);
+    const FrontDesc cd = load_fd(in ? io.fd + (c - io.s0) : io.gfd + c);
+    const int rc = cd.r;
+    if (SUB && in) {
+      const int* __restrict__ rl = io.rel + (cd.ro - io.ro0);
+      const double* __restrict__ src = io.uv + (cd.ro - io.ro0);
+      for (int t = tid; t < rc; t += nt) w[rl[t]] += src[t];
+    } else {
+      const int* __restrict__ rl = io.grel + cd.ro;
+      const double* __restrict__ src = io.gcbv + cd.ro;
+      for (int t = tid; t < rc; t += nt) w[rl[t]] += __ldcg(src + t);
     }
     __syncthreads();
+  }
+  const int* __restrict__ lp = io.lperm + cl;
+  for (int i = tid; i < f; i += nt) v[i] = (i < k) ? w[lp[i]] : w[i];
+  __syncthreads();
+  const double* __restrict__ P = Lp_override ? Lp_override : io.Lbase + (fd.L_off - io.L0);
+  if (mbar) mbar_wait(mbar, mphase);   // the staged panel (bulk copy issued by the caller) has landed
+  for (int t0 = 0; t0 < k; t0 += 32) {
+    const int nb = min(32, k - t0);
     if (warp == 0) {
+      // the triangle of this 32-block: lane = row; the block column is read 8 entries ahead of the shuffle chain
       double yi = (lane < nb) ? v[t0 + lane] : 0.0;
-      for (int q = 0; q < nb; ++q) {
-        double yq = __shfl_sync(0xffffffffu, yi, q);
-        if (lane > q && lane < nb) yi = fma(-Lb[lane + q * 33], yq, yi);
+      for (int qb = 0; qb < nb; qb += 8) {
+        double l[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) l[q] = (qb + q < nb && lane > qb + q && lane < nb) ? P[(t0 + lane) + (size_t)(t0 + qb + q) * f] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (qb + q < nb) {
+            const double yq = __shfl_sync(0xffffffffu, yi, qb + q);
+            yi = fma(-l[q], yq, yi);
+          }
+        }
       }
       if (lane < nb) v[t0 + lane] = yi;
     }
@@ -361,43 +476,39 @@ __device__ void mid_fwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
     __syncthreads();
   }
   for (int t = tid; t < k; t += nt) {
-    const int ty = N.ptype[c0 + t];
+    const int ty = io.ptype[cl + t];
     double y;
-    if (ty == 1) y = v[t] * N.dinv[c0 + t];
-    else if (ty == 2) y = v[t] * N.dinv[c0 + t] + v[t + 1] * N.doff[c0 + t];
-    else y = v[t - 1] * N.doff[c0 + t - 1] + v[t] * N.dinv[c0 + t];
-    x[c0 + t] = y;
+    if (ty == 1) y = v[t] * io.dinv[cl + t];
+    else if (ty == 2) y = v[t] * io.dinv[cl + t] + v[t + 1] * io.doff[cl + t];
+    else y = v[t - 1] * io.doff[cl + t - 1] + v[t] * io.dinv[cl + t];
+    io.xs[cl + t] = y;
   }
-  double* __restrict__ out = cbv + S.rows_ptr[s];
+  double* __restrict__ out = io.uv + rol;
   for (int i = tid; i < r; i += nt) out[i] = v[k + i];
   __syncthreads();
-  if (FLAGS && tid == 0) st_release(V.done_f + s, epoch);
+  if (!SUB && tid == 0) st_release(V.done_f + s, epoch);
 }
 
-template <bool FLAGS>
-__device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int s, int epoch, double* sm,
-                        double* __restrict__ x) {
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const long long ro = S.rows_ptr[s];
-  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
-  double* v = sm;
-  double* Lb = sm + 2 * f;
+template <bool SUB>
+__device__ void mid_bwd(const FrontIO& io, const DevSolve& V, int s, int epoch, int parent, double* scr,
+                        const double* Lp_override, unsigned long long* mbar, unsigned mphase, int upper_max) {
+  const FrontDesc fd = load_fd(io.fd + (s - io.s0));
+  const int k = fd.k, r = fd.r, f = k + r;
+  const int cl = fd.c0 - io.col0;
+  const long long rol = fd.ro - io.ro0;
+  double* v = scr;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-  if (FLAGS) {
-    const int par = S.sn_parent[s];
-    if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
+  if (!SUB) {
+    if (parent >= 0 && tid == 0) wait_eq(V.done_b + parent, epoch);
+    __syncthreads();
   }
+  for (int i = tid; i < f; i += nt) v[i] = (i < k) ? io.xs[cl + i] : cb_row_x<SUB>(io, rol, fd.ro, i - k);
   __syncthreads();
-  for (int i = tid; i < f; i += nt) v[i] = (i < k) ? x[c0 + i] : __ldcg(x + S.rows[ro + (i - k)]);
-  __syncthreads();
-  const double* __restrict__ P = N.L + S.L_off[s];
+  const double* __restrict__ P = Lp_override ? Lp_override : io.Lbase + (fd.L_off - io.L0);
+  if (mbar) mbar_wait(mbar, mphase);
   const int nblk = (k + 31) / 32;
   for (int b = nblk - 1; b >= 0; --b) {
     const int t0 = b * 32, nb = min(32, k - t0);
-    for (int t = tid; t < nb * nb; t += nt) {
-      int i = t % nb, q = t / nb;
-      Lb[i + q * 33] = P[(t0 + i) + (size_t)(t0 + q) * f];
-    }
     for (int q = warp; q < nb; q += nwarp) {
       const double* col = P + (size_t)(t0 + q) * f;
       double acc = 0.0;
@@ -408,19 +519,34 @@ __device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
     }
     __syncthreads();
     if (warp == 0) {
+      // triangle of this block: lane t owns column t; row q of the block comes from L11^T in the upper triangle when the
+      // factorisation stored it (fronts up to order 128), else from the lower triangle (stride-f gather)
       double zi = (lane < nb) ? v[t0 + lane] : 0.0;
-      for (int q = nb - 1; q >= 0; --q) {
-        double zq = __shfl_sync(0xffffffffu, zi, q);
-        if (lane < q) zi = fma(-Lb[q + lane * 33], zq, zi);
+      const bool upper = f <= upper_max;
+      for (int qb = ((nb - 1) >> 3) << 3; qb >= 0; qb -= 8) {
+        double l[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int qq = qb + q;
+          l[q] = (qq < nb && lane < qq) ? (upper ? P[(t0 + lane) + (size_t)(t0 + qq) * f] : P[(t0 + qq) + (size_t)(t0 + lane) * f]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 7; q >= 0; --q) {
+          const int qq = qb + q;
+          if (qq < nb && qq >= 1) {   // warp-uniform
+            const double zq = __shfl_sync(0xffffffffu, zi, qq);
+            zi = fma(-l[q], zq, zi);
+          }
+        }
       }
       if (lane < nb) v[t0 + lane] = zi;
     }
     __syncthreads();
   }
-  const int* __restrict__ lp = N.lperm + c0;
-  for (int t = tid; t < k; t += nt) x[c0 + lp[t]] = v[t];
+  const int* __restrict__ lp = io.lperm + cl;
+  for (int t = tid; t < k; t += nt) io.xs[cl + lp[t]] = v[t];
   __syncthreads();
-  if (FLAGS && tid == 0) st_release(V.done_b + s, epoch);
+  if (!SUB && tid == 0) st_release(V.done_b + s, epoch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,19 +556,20 @@ __device__ void mid_bwd(const DevSym& S, const DevNum& N, const DevSolve& V, int
 //             FC: u_j   = w_j - L21[j,:] y                   (update vector handed to the parent)
 //   backward  BT: t_b   = z_b - L21[:,b]^T x(rows)           (z = D^-1 y)
 //             BX: x_b   = sum_{c>=b} Linv[c,b]^T t_c
-// Each (64-block, chunk of <= DF_CH tiles) is one task; the w entries a task needs are gathered on the fly from the
-// children's update vectors through the inverse row maps (S.einv) -- no separate gather task, no staging buffer.
+// Each (64-block, chunk of <= DF_CH tiles) is one task; ALL tiles of a chunk are in flight before the task waits for its
+// inputs, and the w entries it needs are gathered on the fly from the children's update vectors through a precomputed
+// gather map (V.gmap: parent row -> entry of each child's update vector) -- no separate gather task, no staging buffer.
 // The right-hand side of a big front stays in x[c0..c0+k) until BX overwrites it with the solution: the forward result
 // z lives in V.bigv (so FP tasks of other blocks can still read the right-hand side).
-// smem: stage[256] | part[256] | ys[64] | red[128] | colacc[64]
+// smem: stage[128] | part[256] | ys[64] | red[128] | colacc[64]
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double big_gather_row(const DevSym& S, int j, int k, int c0, int ch0, int nch,
+__device__ __forceinline__ double big_gather_row(const DevSolve& V, int s, int j, int k, int f, int c0, int nch,
                                                  const double* __restrict__ x, const double* __restrict__ cbv) {
+  const int* __restrict__ gm = V.gmap + V.gmap_off[s] + j;
   double v = (j < k) ? x[c0 + j] : 0.0;
   for (int q = 0; q < nch; ++q) {   // fixed child order: deterministic
-    const int c = S.child_idx[ch0 + q];
-    const int e = S.einv[S.einv_off[c] + j];
-    if (e >= 0) v += __ldcg(cbv + S.rows_ptr[c] + e);
+    const int e = gm[(size_t)q * f];
+    if (e >= 0) v += __ldcg(cbv + e);
   }
   return v;
 }
@@ -497,44 +624,71 @@ __device__ __forceinline__ void reduce_cols(double (&pacc)[16], double* red, dou
 __device__ void big_fp(const DevSym& S, const DevNum& N, const DevSolve& V, const SolveTask& T, int epoch, double* sm,
                        int* s_flag, const double* __restrict__ x, const double* __restrict__ cbv) {
   const int s = T.s, rb = T.blk;
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const FrontDesc fd = load_fd(V.fdesc + s);
+  const int c0 = fd.c0, k = fd.k;
   const int nkb = (k + DF_BLK - 1) / DF_BLK;
   const long long K64 = (long long)nkb * DF_BLK;
   const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
   double* stage = sm;
-  double* part = sm + 256;
+  double* part = sm + 128;
   double* ys = part + 256;
   const int r0 = rb * DF_BLK, nrow = min(DF_BLK, k - r0);
   const double* __restrict__ Li = V.linv + V.linv_off[s] + (r0 + tx);
-  // first tile in flight before the children are seen (Linv does not depend on the right-hand side)
-  double ltn[16];
+  // both tiles in flight before the children are seen (Linv does not depend on the right-hand side)
+  const int f = k + fd.r;
+  const bool two = T.t1 - T.t0 > 1;
+  double la[16], lb[16];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) ltn[q] = Li[((long long)T.t0 * DF_BLK + ty + 4 * q) * K64];
-  const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
+  for (int q = 0; q < 16; ++q) la[q] = Li[((long long)T.t0 * DF_BLK + ty + 4 * q) * K64];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) lb[q] = two ? Li[((long long)(T.t0 + 1) * DF_BLK + ty + 4 * q) * K64] : 0.0;
+  const int ch0 = fd.ch0, nch = fd.nch;
+  // gather addresses of this thread's stage entry (they do not depend on the right-hand side): pivot permutation ->
+  // per-child index into cbv; up to 4 children in registers, more through the map again
+  const int ncols = (T.t1 - T.t0) * DF_BLK;     // <= 128 <= DF_THREADS: one stage entry per thread
+  const int gi = T.t0 * DF_BLK + tid;
+  int gsrc[4] = {-1, -1, -1, -1};
+  int jrow = -1;
+  if (tid < ncols && gi < k) {
+    jrow = N.lperm[c0 + gi];
+    const int* __restrict__ gm = V.gmap + V.gmap_off[s] + jrow;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (q < nch) gsrc[q] = gm[(size_t)q * f];
+  }
+  // D of this block (finalisation) -- prefetched as well
+  int ty2 = 1;
+  double dv = 0.0, dof = 0.0, dofm = 0.0;
+  if (tid < nrow) {
+    const int i = r0 + tid;
+    ty2 = N.ptype[c0 + i]; dv = N.dinv[c0 + i]; dof = N.doff[c0 + i];
+    if (i > 0) dofm = N.doff[c0 + i - 1];
+  }
   for (int q = tid; q < nch; q += DF_THREADS) wait_eq(V.done_f + S.child_idx[ch0 + q], epoch);
   __syncthreads();
-  {
-    const int* __restrict__ lp = N.lperm + c0;
-    const int ncols = (T.t1 - T.t0) * DF_BLK;
-    for (int i = tid; i < ncols; i += DF_THREADS) {
-      const int gi = T.t0 * DF_BLK + i;
-      stage[i] = (gi < k) ? big_gather_row(S, lp[gi], k, c0, ch0, nch, x, cbv) : 0.0;
+  if (tid < ncols) {
+    double v = 0.0;
+    if (jrow >= 0) {
+      v = x[c0 + jrow];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (gsrc[q] >= 0) v += __ldcg(cbv + gsrc[q]);
+      if (nch > 4) {
+        const int* __restrict__ gm = V.gmap + V.gmap_off[s] + jrow;
+        for (int q = 4; q < nch; ++q) { const int e = gm[(size_t)q * f]; if (e >= 0) v += __ldcg(cbv + e); }
+      }
     }
+    stage[tid] = v;
   }
   __syncthreads();
   double acc = 0.0;
-  for (int c = T.t0; c < T.t1; ++c) {
-    double lt[16];
+  {
+    const double* wc = stage + ty;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-    if (c + 1 < T.t1) {
-      const double* nx = Li + (long long)(c + 1) * DF_BLK * K64;
+    for (int q = 0; q < 16; ++q) acc = fma(la[q], wc[4 * q], acc);
+    if (two) {
+      const double* wd = stage + DF_BLK + ty;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) ltn[q] = nx[(long long)(ty + 4 * q) * K64];
+      for (int q = 0; q < 16; ++q) acc = fma(lb[q], wd[4 * q], acc);
     }
-    const double* wc = stage + (c - T.t0) * DF_BLK + ty;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) acc = fma(lt[q], wc[4 * q], acc);
   }
   part[ty * 64 + tx] = acc;
   __syncthreads();
@@ -545,11 +699,10 @@ __device__ void big_fp(const DevSym& S, const DevNum& N, const DevSolve& V, cons
     const int i = r0 + tid;
     const long long o = V.bigv_off[s];
     V.bigy[o + i] = ys[tid];              // y block for the contribution rows (pivoted order)
-    const int ty2 = N.ptype[c0 + i];      // 2x2 partners never straddle a 32-column panel, so they sit in this block
-    double z;
-    if (ty2 == 1) z = ys[tid] * N.dinv[c0 + i];
-    else if (ty2 == 2) z = ys[tid] * N.dinv[c0 + i] + ys[tid + 1] * N.doff[c0 + i];
-    else z = ys[tid - 1] * N.doff[c0 + i - 1] + ys[tid] * N.dinv[c0 + i];
+    double z;                              // 2x2 partners never straddle a 32-column panel, so they sit in this block
+    if (ty2 == 1) z = ys[tid] * dv;
+    else if (ty2 == 2) z = ys[tid] * dv + ys[tid + 1] * dof;
+    else z = ys[tid - 1] * dofm + ys[tid] * dv;
     V.bigv[o + i] = z;
   }
   __syncthreads();
@@ -560,20 +713,33 @@ __device__ void big_fp(const DevSym& S, const DevNum& N, const DevSolve& V, cons
 __device__ void big_fc(const DevSym& S, const DevNum& N, const DevSolve& V, const SolveTask& T, int epoch, double* sm,
                        int* s_flag, const double* __restrict__ x, double* __restrict__ cbv) {
   const int s = T.s, j = T.blk;
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const FrontDesc fd = load_fd(V.fdesc + s);
+  const int c0 = fd.c0, k = fd.k;
+  const int f = k + fd.r;
   const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
   double* stage = sm;
-  double* part = sm + 256;
+  double* part = sm + 128;
   double* ys = part + 256;
   const int rbase = k + j * DF_BLK, nr = min(DF_BLK, f - rbase);
-  const double* __restrict__ P = N.L + S.L_off[s] + (rbase + tx);
-  double ltn[16];
+  const double* __restrict__ P = N.L + fd.L_off + (rbase + tx);
+  const bool two = T.t1 - T.t0 > 1;
+  double la[16], lb[16];
   {
     const int tc0 = T.t0 * DF_BLK, ncn = min(DF_BLK, k - tc0);
     const double* nx = P + (size_t)tc0 * f;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncn) ? nx[(size_t)t * f] : 0.0; }
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; la[q] = (tx < nr && t < ncn) ? nx[(size_t)t * f] : 0.0; }
+    const int tc1 = tc0 + DF_BLK, ncm = two ? min(DF_BLK, k - tc1) : 0;
+    const double* ny = P + (size_t)tc1 * f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; lb[q] = (tx < nr && t < ncm) ? ny[(size_t)t * f] : 0.0; }
+  }
+  // addresses of this row's assembled right-hand side entry (needed by the finalising CTA): prefetched
+  int gsrc[4] = {-1, -1, -1, -1};
+  if (tid < nr) {
+    const int* __restrict__ gm = V.gmap + V.gmap_off[s] + (rbase + tid);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (q < fd.nch) gsrc[q] = gm[(size_t)q * f];
   }
   for (int c = T.t0 + tid; c < T.t1; c += DF_THREADS) wait_eq(V.bflag_f + V.boff[s] + c, epoch);
   __syncthreads();
@@ -587,19 +753,15 @@ __device__ void big_fc(const DevSym& S, const DevNum& N, const DevSolve& V, cons
   }
   __syncthreads();
   double acc = 0.0;
-  for (int c = T.t0; c < T.t1; ++c) {
-    double lt[16];
+  {
+    const double* yc = stage + ty;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-    if (c + 1 < T.t1) {
-      const int tcn = (c + 1) * DF_BLK, ncn = min(DF_BLK, k - tcn);
-      const double* nx = P + (size_t)tcn * f;
+    for (int q = 0; q < 16; ++q) acc = fma(la[q], yc[4 * q], acc);
+    if (two) {
+      const double* yd = stage + DF_BLK + ty;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr && t < ncn) ? nx[(size_t)t * f] : 0.0; }
+      for (int q = 0; q < 16; ++q) acc = fma(lb[q], yd[4 * q], acc);
     }
-    const double* yc = stage + (c - T.t0) * DF_BLK + ty;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) acc = fma(lt[q], yc[4 * q], acc);
   }
   part[ty * 64 + tx] = acc;
   __syncthreads();
@@ -608,9 +770,14 @@ __device__ void big_fc(const DevSym& S, const DevNum& N, const DevSolve& V, cons
   if (!chunk_combine(V, T, ys, s_flag)) return;
   if (tid < nr) {
     // the children are complete (every FP task of this front waited for them before publishing the flags seen above)
-    const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
-    const double wv = big_gather_row(S, rbase + tid, k, c0, ch0, nch, x, cbv);
-    cbv[S.rows_ptr[s] + (rbase - k) + tid] = wv - ys[tid];
+    double wv = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (gsrc[q] >= 0) wv += __ldcg(cbv + gsrc[q]);
+    if (fd.nch > 4) {
+      const int* __restrict__ gm = V.gmap + V.gmap_off[s] + (rbase + tid);
+      for (int q = 4; q < fd.nch; ++q) { const int e = gm[(size_t)q * f]; if (e >= 0) wv += __ldcg(cbv + e); }
+    }
+    cbv[fd.ro + (rbase - k) + tid] = wv - ys[tid];
   }
   __syncthreads();
   if (tid == 0) {
@@ -625,53 +792,45 @@ __device__ void big_fc(const DevSym& S, const DevNum& N, const DevSolve& V, cons
 __device__ void big_bt(const DevSym& S, const DevNum& N, const DevSolve& V, const SolveTask& T, int epoch, double* sm,
                        int* s_flag, const double* __restrict__ x) {
   const int s = T.s, b = T.blk;
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  const long long ro = S.rows_ptr[s];
-  const int r = (int)(S.rows_ptr[s + 1] - ro), f = k + r;
+  const FrontDesc fd = load_fd(V.fdesc + s);
+  const int k = fd.k;
+  const long long ro = fd.ro;
+  const int r = fd.r, f = k + r;
   const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
   double* stage = sm;
-  double* red = sm + 576;
+  double* red = sm + 448;
   double* colacc = red + 128;
   const int tc0 = b * DF_BLK, ncol = min(DF_BLK, k - tc0);
-  const double* __restrict__ P = N.L + S.L_off[s] + (size_t)tc0 * f;
+  const double* __restrict__ P = N.L + fd.L_off + (size_t)tc0 * f;
   double pacc[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
-  double ltn[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) ltn[q] = 0.0;
-  if (T.t1 > T.t0) {
-    const int rb2 = k + T.t0 * DF_BLK, nr2 = min(DF_BLK, f - rb2);
+  const bool one = T.t1 - T.t0 > 0, two = T.t1 - T.t0 > 1;
+  double la[16], lb[16];
+  {
+    const int rb2 = k + T.t0 * DF_BLK, nr2 = one ? min(DF_BLK, f - rb2) : 0;
     const double* base = P + (rb2 + tx);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; la[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
+    const int rb3 = rb2 + DF_BLK, nr3 = two ? min(DF_BLK, f - rb3) : 0;
+    const double* base3 = P + (rb3 + tx);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; lb[q] = (tx < nr3 && t < ncol) ? base3[(size_t)t * f] : 0.0; }
   }
+  const int nrows = (T.t1 - T.t0) * DF_BLK;     // <= 128: one stage entry per thread
+  const int rix = T.t0 * DF_BLK + tid;
+  const int grow = (tid < nrows && rix < r) ? S.rows[ro + rix] : -1;   // row id prefetched before the wait
   {
     const int par = S.sn_parent[s];
     if (par >= 0 && tid == 0) wait_eq(V.done_b + par, epoch);
   }
   __syncthreads();
-  {
-    const int nrows = (T.t1 - T.t0) * DF_BLK;
-    for (int i = tid; i < nrows; i += DF_THREADS) {
-      const int ri = T.t0 * DF_BLK + i;
-      stage[i] = (ri < r) ? __ldcg(x + S.rows[ro + ri]) : 0.0;
-    }
-  }
+  if (tid < nrows) stage[tid] = (grow >= 0) ? __ldcg(x + grow) : 0.0;
   __syncthreads();
-  for (int ch = T.t0; ch < T.t1; ++ch) {
-    double lt[16];
+  {
+    const double xa = one ? stage[tx] : 0.0, xb = two ? stage[DF_BLK + tx] : 0.0;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-    if (ch + 1 < T.t1) {
-      const int rb2 = k + (ch + 1) * DF_BLK, nr2 = min(DF_BLK, f - rb2);
-      const double* base = P + (rb2 + tx);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { const int t = ty + 4 * q; ltn[q] = (tx < nr2 && t < ncol) ? base[(size_t)t * f] : 0.0; }
-    }
-    const double xi = stage[(ch - T.t0) * DF_BLK + tx];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], xi, pacc[q]);
+    for (int q = 0; q < 16; ++q) pacc[q] = fma(la[q], xa, lb[q] * xb);
   }
   reduce_cols(pacc, red, colacc);
   if (!chunk_combine(V, T, colacc, s_flag)) return;
@@ -687,12 +846,13 @@ __device__ void big_bt(const DevSym& S, const DevNum& N, const DevSolve& V, cons
 __device__ void big_bx(const DevSym& S, const DevNum& N, const DevSolve& V, const SolveTask& T, int epoch, double* sm,
                        int* s_flag, double* __restrict__ x) {
   const int s = T.s, b = T.blk;
-  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const FrontDesc fd = load_fd(V.fdesc + s);
+  const int c0 = fd.c0, k = fd.k;
   const int nkb = (k + DF_BLK - 1) / DF_BLK;
   const long long K64 = (long long)nkb * DF_BLK;
   const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
   double* stage = sm;
-  double* red = sm + 576;
+  double* red = sm + 448;
   double* colacc = red + 128;
   const int tc0 = b * DF_BLK, ncol = min(DF_BLK, k - tc0);
   const double* __restrict__ Li = V.linv + V.linv_off[s] + (long long)tc0 * K64 + tx;
@@ -700,9 +860,13 @@ __device__ void big_bx(const DevSym& S, const DevNum& N, const DevSolve& V, cons
   double pacc[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) pacc[q] = 0.0;
-  double ltn[16];
+  const bool two = T.t1 - T.t0 > 1;
+  double la[16], lb[16];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)T.t0 * DF_BLK + (long long)(ty + 4 * q) * K64];
+  for (int q = 0; q < 16; ++q) la[q] = Li[(long long)T.t0 * DF_BLK + (long long)(ty + 4 * q) * K64];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) lb[q] = two ? Li[(long long)(T.t0 + 1) * DF_BLK + (long long)(ty + 4 * q) * K64] : 0.0;
+  const int lpo = (tid < ncol) ? N.lperm[c0 + tc0 + tid] : 0;   // (prefetched: needed by the finalising CTA)
   for (int c = T.t0 + tid; c < T.t1; c += DF_THREADS) wait_eq(V.bflag_b + V.boff[s] + c, epoch);
   __syncthreads();
   {
@@ -713,21 +877,14 @@ __device__ void big_bx(const DevSym& S, const DevNum& N, const DevSolve& V, cons
     }
   }
   __syncthreads();
-  for (int c = T.t0; c < T.t1; ++c) {
-    double lt[16];
+  {
+    const double ta = stage[tx], tb2 = two ? stage[DF_BLK + tx] : 0.0;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) lt[q] = ltn[q];
-    if (c + 1 < T.t1) {
-#pragma unroll
-      for (int q = 0; q < 16; ++q) ltn[q] = Li[(long long)(c + 1) * DF_BLK + (long long)(ty + 4 * q) * K64];
-    }
-    const double ti = stage[(c - T.t0) * DF_BLK + tx];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) pacc[q] = fma(lt[q], ti, pacc[q]);
+    for (int q = 0; q < 16; ++q) pacc[q] = fma(la[q], ta, lb[q] * tb2);
   }
   reduce_cols(pacc, red, colacc);
   if (!chunk_combine(V, T, colacc, s_flag)) return;
-  if (tid < ncol) x[c0 + N.lperm[c0 + tc0 + tid]] = colacc[tid];   // final value (the permutation is panel-local)
+  if (tid < ncol) x[c0 + lpo] = colacc[tid];   // final value (the permutation is panel-local)
   __syncthreads();
   if (tid == 0) {
     __threadfence();                                 // this block's solution entries before the counter
@@ -861,34 +1018,122 @@ __global__ void __launch_bounds__(128) k_linv_gemm(DevSym S, DevNum N, const Lin
 }
 
 // ------------------------------------------------------------------------------------------------
-// bottom of the tree: one CTA per subtree, level by level, CTA barriers only
+// Shared-memory layout of one subtree (k_solve_sub).  The same arithmetic runs on the host when the subtrees are cut
+// (the byte count must fit DF_DYN_SMEM) and on the device when the slices are carved.
+//   doubles : Ls[nL] | xs[ncol] | uv[nrt] | rootx[rroot] | dinv[ncol] | doff[ncol] | wscr[8*DF_WSCR] | midscr[DF_MIDSCR]
+//   ints    : lperm[ncol] | ptype[ncol] | rel-or-subrow[nrt] | chi[nchi] | meta[nmeta]
+//   FrontDesc fd[nfront] ; mbarrier (8 bytes)
 // ------------------------------------------------------------------------------------------------
+struct SubLayout {
+  long long nL; int ncol, nrt, rroot, nchi, nmeta, nfront;
+  __host__ __device__ long long n_doubles() const {
+    return nL + 3LL * ncol + nrt + rroot + (DF_THREADS / 32) * DF_WSCR + DF_MIDSCR;
+  }
+  __host__ __device__ long long n_ints() const { return 2LL * ncol + nrt + nchi + nmeta; }
+  __host__ __device__ long long ints_off() const { return ((n_doubles() * 8 + 15) / 16) * 16; }   // bytes
+  __host__ __device__ long long fd_off() const { return ints_off() + ((n_ints() * 4 + 15) / 16) * 16; }
+  __host__ __device__ long long bytes() const { return fd_off() + (long long)nfront * (long long)sizeof(FrontDesc) + 16; }
+};
+
 template <bool FWD>
 __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_sub(DevSym S, DevNum N, DevSolve V, int epoch,
-                                                          double* __restrict__ x, double* __restrict__ cbv) {
-  __shared__ double sm[DF_SMEM_DOUBLES];
-  const int u = blockIdx.x;
-  const int e0 = V.sub_ptr[u], nlv = V.sub_ptr[u + 1] - e0;
-  const int warp = threadIdx.x >> 5;
-  for (int li = 0; li < nlv; ++li) {
-    const int e = e0 + (FWD ? li : nlv - 1 - li);
-    const int b = V.lvl_ptr[e], en = V.lvl_ptr[e + 1], ns = V.lvl_nsmall[e];
-    for (int q = b + warp; q < b + ns; q += DF_THREADS / 32) {
-      const int s = V.sub_fronts[q];
-      if (FWD) w64_fwd<false>(S, N, V, s, epoch, sm + warp * 64, x, cbv);
-      else w64_bwd<false>(S, N, V, s, epoch, x);
-    }
-    if (en > b + ns) {
-      __syncthreads();   // the per-warp scratch of the small fronts overlaps the mid-front buffers
-      for (int q = b + ns; q < en; ++q) {
-        const int s = V.sub_fronts[q];
-        if (FWD) mid_fwd<false>(S, N, V, s, epoch, sm, x, cbv);
-        else mid_bwd<false>(S, N, V, s, epoch, sm, x);
-      }
-    }
-    __syncthreads();     // (also orders this level's global writes before the next level's reads, CTA scope)
+                                                             double* __restrict__ x, double* __restrict__ cbv) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  unsigned long long t_a = 0, t_b = 0;
+  if (V.tlog && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
+  const SubDesc sd = V.subs[blockIdx.x];
+  const int s0 = sd.s0, sR = sd.sR, nfront = sR - s0 + 1, nlv = sd.nlv;
+  const int col0 = S.sn_start[s0], ncol = S.sn_start[sR + 1] - col0;
+  const long long L0 = S.L_off[s0], nL = S.L_off[sR + 1] - L0;
+  const long long ro0 = S.rows_ptr[s0], roR = S.rows_ptr[sR];
+  const int nrt = (int)(S.rows_ptr[sR + 1] - ro0), rroot = (int)(S.rows_ptr[sR + 1] - roR);
+  const int ch00 = S.child_ptr[s0], nchi = S.child_ptr[sR + 1] - ch00;
+  const int nmeta = 2 * nlv + 1 + nfront;
+  // carve
+  double* Ls = reinterpret_cast<double*>(smraw);
+  double* xs = Ls + nL;
+  double* uv = xs + ncol;
+  double* rootx = uv + nrt;
+  double* dinv = rootx + rroot;
+  double* doff = dinv + ncol;
+  double* wscr = doff + ncol;
+  double* midscr = wscr + (DF_THREADS / 32) * DF_WSCR;
+  SubLayout lay;
+  lay.nL = nL; lay.ncol = ncol; lay.nrt = nrt; lay.rroot = rroot; lay.nchi = nchi; lay.nmeta = nmeta; lay.nfront = nfront;
+  int* lperm = reinterpret_cast<int*>(smraw + lay.ints_off());
+  int* ptype = lperm + ncol;
+  int* relsub = ptype + ncol;
+  int* chi = relsub + nrt;
+  int* meta = chi + nchi;
+  FrontDesc* fds = reinterpret_cast<FrontDesc*>(smraw + lay.fd_off());
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(fds + nfront);
+
+  if (tid == 0) mbar_init(mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(mbar, (unsigned)(nL * 8));
+    bulk_g2s(Ls, N.L + L0, (unsigned long long)nL * 8, mbar);   // the whole subtree's panels: contiguous (postorder)
   }
-  if (FWD && threadIdx.x == 0) V.done_f[V.sub_root[u]] = epoch;   // read by the top kernel (next launch)
+  // everything else: plain coalesced loads, all in flight together with the bulk copy
+  for (int i = tid; i < ncol; i += DF_THREADS) {
+    xs[i] = x[col0 + i];
+    dinv[i] = N.dinv[col0 + i];
+    doff[i] = N.doff[col0 + i];
+    lperm[i] = N.lperm[col0 + i];
+    ptype[i] = N.ptype[col0 + i];
+  }
+  for (int i = tid; i < nrt; i += DF_THREADS) relsub[i] = FWD ? S.rel[ro0 + i] : V.subrow[ro0 + i];
+  for (int i = tid; i < nchi; i += DF_THREADS) chi[i] = S.child_idx[ch00 + i];
+  for (int i = tid; i < nmeta; i += DF_THREADS) meta[i] = V.sub_meta[sd.moff + i];
+  {
+    const int4* src = reinterpret_cast<const int4*>(V.fdesc + s0);
+    int4* dst = reinterpret_cast<int4*>(fds);
+    for (int i = tid; i < 2 * nfront; i += DF_THREADS) dst[i] = src[i];
+  }
+  if (!FWD) for (int i = tid; i < rroot; i += DF_THREADS) rootx[i] = x[S.rows[roR + i]];   // ancestors: final (earlier kernel)
+  FrontIO io;
+  io.Lbase = Ls; io.L0 = L0; io.xs = xs; io.col0 = col0; io.uv = uv; io.ro0 = ro0;
+  io.dinv = dinv; io.doff = doff; io.ptype = ptype; io.lperm = lperm;
+  io.rel = relsub; io.subrow = relsub; io.rootx = rootx;
+  io.fd = fds; io.s0 = s0; io.sR = sR; io.chi = chi; io.ch00 = ch00;
+  io.gfd = V.fdesc; io.gcbv = cbv; io.grel = S.rel; io.grows = S.rows; io.gx = x;
+  __syncthreads();
+  mbar_wait(mbar, 0);
+  if (V.tlog && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
+  const int* lvl = meta;              // nlv + 1 offsets into the front list
+  const int* nsm = meta + nlv + 1;    // nlv
+  const int* fl = meta + 2 * nlv + 1; // nfront ids
+  for (int li = 0; li < nlv; ++li) {
+    const int e = FWD ? li : nlv - 1 - li;
+    const int b = lvl[e], en = lvl[e + 1], ns = nsm[e];
+    for (int q = b + warp; q < b + ns; q += DF_THREADS / 32) {
+      const int s = fl[q];
+      if (FWD) w64_fwd<true>(io, V, s, epoch, wscr + warp * DF_WSCR);
+      else w64_bwd<true>(io, V, s, epoch, -1, V.upper_max);
+    }
+    for (int q = b + ns; q < en; ++q) {   // (mid fronts use their own scratch: no barrier needed before them)
+      const int s = fl[q];
+      if (FWD) mid_fwd<true>(io, V, s, epoch, midscr, nullptr, nullptr, 0);
+      else mid_bwd<true>(io, V, s, epoch, -1, midscr, nullptr, nullptr, 0, V.upper_max);
+    }
+    __syncthreads();
+  }
+  // results back to global memory: the x slice (forward: z = D^-1 y in pivot order; backward: the solution), the
+  // root's update vector (forward), and the done flags of every front (read by the top kernel / other plans)
+  for (int i = tid; i < ncol; i += DF_THREADS) x[col0 + i] = xs[i];
+  if (FWD) {
+    for (int i = tid; i < rroot; i += DF_THREADS) cbv[roR + i] = uv[(roR - ro0) + i];
+    for (int i = tid; i < nfront; i += DF_THREADS) V.done_f[s0 + i] = epoch;
+  } else {
+    for (int i = tid; i < nfront; i += DF_THREADS) V.done_b[s0 + i] = epoch;
+  }
+  if (V.tlog && tid == 0) {   // debug: 4 timestamps/records per subtree after the task records
+    unsigned long long t_c;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
+    unsigned long long* rec = V.tlog + 2 * ((unsigned long long)V.ntasks_fwd + V.ntasks_bwd) + 4 * ((FWD ? 0 : (unsigned long long)V.nsub) + blockIdx.x);
+    rec[0] = t_a; rec[1] = t_b; rec[2] = t_c; rec[3] = ((unsigned long long)nfront << 32) | (unsigned)nlv;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -896,13 +1141,27 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_sub(DevSym S, DevNum N,
 // ------------------------------------------------------------------------------------------------
 template <bool FWD>
 __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_top(DevSym S, DevNum N, DevSolve V, int epoch,
-                                                          unsigned long long ticket_base,
-                                                          double* __restrict__ x, double* __restrict__ cbv) {
-  __shared__ double sm[DF_SMEM_DOUBLES];
+                                                             unsigned long long ticket_base,
+                                                             double* __restrict__ x, double* __restrict__ cbv) {
+  extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ unsigned long long s_ticket;
+  __shared__ unsigned long long s_mbar;
   __shared__ int s_flag;
+  double* sm = reinterpret_cast<double*>(smraw);                // [0, 8*DF_WSCR + DF_MIDSCR) scratch, then the panel stage
+  double* midscr = sm + (DF_THREADS / 32) * DF_WSCR;
+  double* stage = midscr + DF_MIDSCR;
+  const long long stage_doubles = (DF_DYN_SMEM / 8) - ((DF_THREADS / 32) * DF_WSCR + DF_MIDSCR);
   const SolveTask* tasks = FWD ? V.tasks : V.tasks_bwd;
   const int ntasks = FWD ? V.ntasks_fwd : V.ntasks_bwd;
+  FrontIO io;
+  io.Lbase = N.L; io.L0 = 0; io.xs = x; io.col0 = 0; io.uv = cbv; io.ro0 = 0;
+  io.dinv = N.dinv; io.doff = N.doff; io.ptype = N.ptype; io.lperm = N.lperm;
+  io.rel = S.rel; io.subrow = nullptr; io.rootx = nullptr;
+  io.fd = V.fdesc; io.s0 = 0; io.sR = S.nsn - 1; io.chi = S.child_idx; io.ch00 = 0;
+  io.gfd = V.fdesc; io.gcbv = cbv; io.grel = S.rel; io.grows = S.rows; io.gx = x;
+  unsigned mphase = 0;
+  if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+  __syncthreads();
   while (true) {
     if (threadIdx.x == 0) s_ticket = atomicAdd(V.ticket + (FWD ? 0 : 1), 1ull) - ticket_base;
     __syncthreads();
@@ -916,11 +1175,28 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_top(DevSym S, DevNum N,
       const int w = threadIdx.x >> 5;
       if (w < T.blk) {
         const int s = V.bundle[T.s + w];
-        if (FWD) w64_fwd<true>(S, N, V, s, epoch, sm + w * 64, x, cbv);
-        else w64_bwd<true>(S, N, V, s, epoch, x);
+        if (FWD) w64_fwd<false>(io, V, s, epoch, sm + w * DF_WSCR);
+        else w64_bwd<false>(io, V, s, epoch, S.sn_parent[s], V.upper_max);
       }
     } else if (T.type == ST_MID) {
-      if (FWD) mid_fwd<true>(S, N, V, T.s, epoch, sm, x, cbv); else mid_bwd<true>(S, N, V, T.s, epoch, sm, x);
+      // stage the whole panel in shared memory with one bulk copy when it fits (it does not depend on the right-hand
+      // side, so it is in flight while the routine waits for / gathers its inputs)
+      const FrontDesc fd = load_fd(V.fdesc + T.s);
+      const long long pn = ((long long)(fd.k + fd.r) * fd.k + 1) & ~1LL;
+      const double* Lp = nullptr;
+      unsigned long long* mb = nullptr;
+      unsigned ph = 0;
+      if (pn <= stage_doubles) {
+        if (threadIdx.x == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage before the async write
+          mbar_expect_tx(&s_mbar, (unsigned)(pn * 8));
+          bulk_g2s(stage, N.L + fd.L_off, (unsigned long long)pn * 8, &s_mbar);
+        }
+        Lp = stage; mb = &s_mbar; ph = mphase;
+        mphase ^= 1;
+      }
+      if (FWD) mid_fwd<false>(io, V, T.s, epoch, midscr, Lp, mb, ph);
+      else mid_bwd<false>(io, V, T.s, epoch, S.sn_parent[T.s], midscr, Lp, mb, ph, V.upper_max);
     } else if (T.type == ST_FP) {
       big_fp(S, N, V, T, epoch, sm, &s_flag, x, cbv);
     } else if (T.type == ST_FC) {

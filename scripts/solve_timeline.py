@@ -6,7 +6,7 @@ from ipopt_b200 import B200Ldlt
 from ipopt_b200.kkt import mbndry_kkt
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 dim, irn, jcn, val, nc = mbndry_kkt(N, sigma_spread=3.0, seed=1)
-s = B200Ldlt()
+s = B200Ldlt(verbose=1)
 s.InitializeStructure(dim, len(irn), irn, jcn)
 s.GetValuesArrayPtr()[:] = val
 print(s.factor(True, nc))
