@@ -126,6 +126,34 @@ int b200ldlt_analyse_now(b200ldlt_handle h, const double* vals);
  * (original, unscaled values), returns max-norms. Used by tests/bench for parity checks. */
 int b200ldlt_residual(b200ldlt_handle h, const double* x, const double* b, double* r_inf, double* x_inf, double* b_inf);
 
+/* ---- device-side callers of the path ----------------------------------------------------------------
+ * What TSymLinearSolver does on the host around every MultiSolve -- fill the values array from the blocks of the augmented
+ * system (TripletHelper::FillValues, IpTripletHelper.cpp:805-873, on the CompoundSymMatrix StdAugSystemSolver builds,
+ * IpStdAugSystemSolver.cpp:232-430) and the iterative refinement of the solve (IpPDFullSpaceSolver.cpp:241-346) -- for
+ * callers that keep W, J, Sigma and the right-hand sides in device memory: no 8*nnz H2D per factorisation, one D2H of
+ * the refined solution per solve. */
+typedef struct b200ldlt_augsys {
+  int n_x, n_s, n_c, n_d;          /* block dimensions (n_d == n_s) */
+  int nnz_w, nnz_jc, nnz_jd;       /* triplet counts of W (lower triangle), J_c, J_d as delivered at analyse time */
+  const double* W;  double W_factor;   /* DEVICE pointers; NULL W = "no Hessian" (the block values are 0) */
+  const double* D_x; double delta_x;   /* diagonal of the (1,1) block: D_x + delta_x   (NULL D: delta only) */
+  const double* D_s; double delta_s;   /* (2,2): D_s + delta_s */
+  const double* J_c;                   /* (3,1) */
+  const double* D_c; double delta_c;   /* (3,3): D_c - delta_c */
+  const double* J_d;                   /* (4,1) */
+  const double* D_d; double delta_d;   /* (4,4): D_d - delta_d ; the (4,2) block is -I */
+} b200ldlt_augsys;
+/* Writes the handle's DEVICE value array in exactly the order FillValues produces for that CompoundSymMatrix:
+ *   [W_factor*W | D_x+delta_x | D_s+delta_s | J_c | D_c-delta_c | J_d | -1 (n_s times) | D_d-delta_d]
+ * (bit-identical: one multiply / one add per entry like the reference).  Follow with b200ldlt_refactor(). */
+int b200ldlt_assemble_augsys_device(b200ldlt_handle h, const b200ldlt_augsys* a);
+/* Solve with iterative refinement entirely on the device: d_rhs (dim doubles, DEVICE) holds b on entry and the refined x
+ * on exit.  After the first solve, steps of  r = b - A x ; x += solve(r)  are taken while step < min_steps or the
+ * residual ratio  ||r||_inf / (min(||x||_inf, 1e6 ||b||_inf) + ||b||_inf)  (IpPDFullSpaceSolver.cpp:795-820) exceeds tol,
+ * at most max_steps.  A is the matrix of the last factor call (its values on the device). */
+int b200ldlt_solve_refine_device(b200ldlt_handle h, double* d_rhs, int min_steps, int max_steps, double tol,
+                                 int* steps_done, double* residual_ratio);
+
 /* ---- multi-GPU elimination-tree sharding (one process / handle per GPU) -----------------
  * The exchange itself (contribution blocks of the cut -> rank 0, update vectors, top solution back) is done by the
  * caller with NCCL send/recv on the device pointers below; ipopt_b200/sharded.py is the reference orchestration. */

@@ -28,6 +28,14 @@ class Options(C.Structure):
                 ("use_graph", C.c_int), ("verbose", C.c_int), ("tc_schur_min_r", C.c_int)]
 
 
+class AugSys(C.Structure):
+    _fields_ = [("n_x", C.c_int), ("n_s", C.c_int), ("n_c", C.c_int), ("n_d", C.c_int), ("nnz_w", C.c_int),
+                ("nnz_jc", C.c_int), ("nnz_jd", C.c_int), ("W", C.c_void_p), ("W_factor", C.c_double),
+                ("D_x", C.c_void_p), ("delta_x", C.c_double), ("D_s", C.c_void_p), ("delta_s", C.c_double),
+                ("J_c", C.c_void_p), ("D_c", C.c_void_p), ("delta_c", C.c_double), ("J_d", C.c_void_p),
+                ("D_d", C.c_void_p), ("delta_d", C.c_double)]
+
+
 class Info(C.Structure):
     _fields_ = [("n", C.c_int), ("nnz_in", C.c_int64), ("nnz_unique", C.c_int64), ("nsupernodes", C.c_int),
                 ("nlevels", C.c_int), ("max_front", C.c_int), ("max_pivots", C.c_int), ("n_saddle", C.c_int),
@@ -46,7 +54,8 @@ EXPORTED = ["b200ldlt_default_options", "b200ldlt_create", "b200ldlt_destroy", "
             "b200ldlt_analyse", "b200ldlt_values_ptr", "b200ldlt_factor", "b200ldlt_factor_device",
             "b200ldlt_solve", "b200ldlt_solve_device", "b200ldlt_num_neg", "b200ldlt_increase_quality",
             "b200ldlt_refactor", "b200ldlt_get_info", "b200ldlt_symbolic_array", "b200ldlt_analyse_now",
-            "b200ldlt_residual", "b200ldlt_set_pivtol"]
+            "b200ldlt_residual", "b200ldlt_set_pivtol",
+            "b200ldlt_assemble_augsys_device", "b200ldlt_solve_refine_device"]
 
 _lib = None
 
@@ -75,6 +84,10 @@ def load_library():
     L.b200ldlt_factor.argtypes = [vp, C.c_int, C.c_int, ip]
     L.b200ldlt_factor_device.argtypes = [vp, vp, C.c_int, C.c_int, ip]
     L.b200ldlt_refactor.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.b200ldlt_assemble_augsys_device.argtypes = [vp, C.POINTER(AugSys)]
+    L.b200ldlt_solve_refine_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, ip, dp]
+    L.b200ldlt_device_ptr.argtypes = [vp, C.c_char_p]
+    L.b200ldlt_device_ptr.restype = vp
     L.b200ldlt_solve.argtypes = [vp, C.c_int, dp]
     L.b200ldlt_solve_device.argtypes = [vp, C.c_int, vp]
     L.b200ldlt_num_neg.argtypes = [vp]
@@ -226,6 +239,20 @@ class B200Ldlt:
 
     def solve_device(self, d_rhs_ptr, nrhs=1):
         return self._L.b200ldlt_solve_device(self._h, int(nrhs), C.c_void_p(d_rhs_ptr))
+
+    def assemble_augsys_device(self, n_x, n_s, n_c, nnz_w, nnz_jc, nnz_jd, W=0, W_factor=1.0, D_x=0, delta_x=0.0, D_s=0,
+                               delta_s=0.0, J_c=0, D_c=0, delta_c=0.0, J_d=0, D_d=0, delta_d=0.0):
+        """Device pointers (ints, 0 = absent) of the blocks of the augmented system -> the handle's device value array
+        (b200ldlt_assemble_augsys_device); follow with refactor()."""
+        a = AugSys(n_x, n_s, n_c, n_s, nnz_w, nnz_jc, nnz_jd, W or None, W_factor, D_x or None, delta_x, D_s or None, delta_s,
+                   J_c or None, D_c or None, delta_c, J_d or None, D_d or None, delta_d)
+        return self._L.b200ldlt_assemble_augsys_device(self._h, C.byref(a))
+
+    def solve_refine_device(self, d_rhs_ptr, min_steps=1, max_steps=10, tol=1e-10):
+        steps, ratio = C.c_int(0), C.c_double(0.0)
+        st = self._L.b200ldlt_solve_refine_device(self._h, C.c_void_p(d_rhs_ptr), int(min_steps), int(max_steps), float(tol),
+                                                  C.byref(steps), C.byref(ratio))
+        return st, steps.value, ratio.value
 
     def analyse_now(self, vals=None):
         return self._L.b200ldlt_analyse_now(self._h, None if vals is None else _dptr(np.ascontiguousarray(vals)))

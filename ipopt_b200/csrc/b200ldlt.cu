@@ -1,6 +1,7 @@
 // Host orchestration + extern "C" shim of the B200 LDL^T backend (see include/b200ldlt.h).
 // One translation unit: the kernels are included so nvcc sees launch sites and definitions together.
 #include "../../include/b200ldlt.h"
+#include "../../include/b200vec.h"
 
 #include <cuda_runtime.h>
 
@@ -122,6 +123,9 @@ struct Solver {
   int rhs_cap = 0;
   int* h_counters = nullptr;     // pinned
   bool analysed = false, factored = false, have_dev_vals = false;
+  b200vec_ctx vec = nullptr;       // vector kernels on the handle's stream (device-side refinement)
+  b200vec_tmat amat = nullptr;     // the matrix as a symmetric triplet operator (residuals)
+  DevBuf<double> d_ref_b, d_ref_r;
   int tc_min_r = 0;                // fronts with r >= this use the tensor-core Schur path (0 = off)
   bool reanalyse = false;          // set by increase_quality after forced pivots: next factor re-runs the analysis on its values
   int n_reanalysed = 0;
@@ -179,6 +183,8 @@ struct Solver {
   int fgraph_launches = 0;
 
   ~Solver() {
+    if (amat) b200vec_tmat_destroy(amat);
+    if (vec) b200vec_destroy(vec);
     if (h_vals) cudaFreeHost(h_vals);
     if (h_rhs) cudaFreeHost(h_rhs);
     if (h_counters) cudaFreeHost(h_counters);
@@ -405,7 +411,7 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
     return S.L_off[a + 1] - S.L_off[a - size[a] + 1] > S.L_off[b + 1] - S.L_off[b - size[b] + 1];
   });
   const int nsub = (int)roots.size();
-  std::vector<SubDesc> subs(std::max(nsub, 1), SubDesc{0, 0, 0, 0});
+  std::vector<SubDesc> subs(std::max(nsub, 1), SubDesc{});
   std::vector<int> meta;
   SP.sub_bytes = 0;
   for (int u = 0; u < nsub; ++u) {
@@ -427,7 +433,16 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
       lvl.push_back((int)e); nsm.push_back(ns);
       q = e;
     }
-    subs[u] = SubDesc{s0, sR, (int)meta.size(), (int)nsm.size()};
+    {
+      SubDesc d{};
+      d.s0 = s0; d.sR = sR; d.moff = (int)meta.size(); d.nlv = (int)nsm.size();
+      d.col0 = S.sn_start[s0]; d.ncol = S.sn_start[sR + 1] - S.sn_start[s0];
+      d.nrt = (int)(S.rows_ptr[sR + 1] - S.rows_ptr[s0]); d.rroot = S.r(sR);
+      d.ch00 = S.child_ptr[s0]; d.nchi = S.child_ptr[sR + 1] - S.child_ptr[s0];
+      d.parent = S.sn_parent[sR];
+      d.L0 = S.L_off[s0]; d.nL = S.L_off[sR + 1] - S.L_off[s0]; d.ro0 = S.rows_ptr[s0];
+      subs[u] = d;
+    }
     meta.insert(meta.end(), lvl.begin(), lvl.end());
     meta.insert(meta.end(), nsm.begin(), nsm.end());
     meta.insert(meta.end(), M.begin(), M.end());
@@ -724,18 +739,16 @@ static int run_analysis(Solver* sv, const double* vals) {
       rc2 = build_solve_plan(sv, S, take, sv->splan, st);
       if (rc2 != B200LDLT_SUCCESS) return rc2;
     }
-    CU(cudaFuncSetAttribute(k_solve_sub<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
-    CU(cudaFuncSetAttribute(k_solve_sub<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
-    CU(cudaFuncSetAttribute(k_solve_top<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
-    CU(cudaFuncSetAttribute(k_solve_top<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
+    CU(cudaFuncSetAttribute(k_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
+    CU(cudaFuncSetAttribute(k_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_DYN_SMEM));
     if (sv->dbg.solve_timeline) {
       CU(sv->d_tlog.alloc(2 * (size_t)(sv->splan.ntf + sv->splan.ntb) + 8 * (size_t)sv->splan.nsub + 8));
       sv->splan.V.tlog = sv->d_tlog.p;
     }
     int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_top<true>, DF_THREADS, DF_DYN_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve<true>, DF_THREADS, DF_DYN_SMEM));
     int occ_b = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_solve_top<false>, DF_THREADS, DF_DYN_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_solve<false>, DF_THREADS, DF_DYN_SMEM));
     CU(cudaDeviceGetAttribute(&sv->num_sms, cudaDevAttrMultiProcessorCount, sv->dev));
     sv->df_grid = std::max(1, std::min(occ, occ_b)) * sv->num_sms;
     if (sv->opt.verbose)
@@ -1005,25 +1018,21 @@ __global__ void k_mark_flags(int* flags, const int* __restrict__ list, int n, in
   if (i < n) flags[list[i]] = value;
 }
 
-// one sweep over the fronts of a plan: forward = subtrees then top, backward = top then subtrees
+// one sweep over the fronts of a plan: ONE persistent kernel (forward: subtrees then top tasks; backward: the reverse)
 static int launch_sweep(Solver* sv, const SolvePlan& SP, bool fwd) {
   cudaStream_t st = sv->stream;
   const DevSolve& V = SP.V;
-  const int nt = fwd ? SP.ntf : SP.ntb;
-  const int grid = std::min(sv->df_grid, std::max(nt, 1));
+  const long long nt = (long long)(fwd ? SP.ntf : SP.ntb) + SP.nsub;
+  if (nt <= 0) return B200LDLT_SUCCESS;
+  const int grid = (int)std::min<long long>(sv->df_grid, nt);
   if (fwd) {
-    if (SP.nsub > 0) { k_solve_sub<true><<<SP.nsub, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->d_x.p, sv->d_cbv.p); ++sv->launches; }
-    if (nt > 0) {
-      k_solve_top<true><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p); ++sv->launches;
-      sv->ticket_f += (unsigned long long)nt + grid;
-    }
+    k_solve<true><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p);
+    sv->ticket_f += (unsigned long long)nt + grid;
   } else {
-    if (nt > 0) {
-      k_solve_top<false><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p); ++sv->launches;
-      sv->ticket_b += (unsigned long long)nt + grid;
-    }
-    if (SP.nsub > 0) { k_solve_sub<false><<<SP.nsub, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->d_x.p, sv->d_cbv.p); ++sv->launches; }
+    k_solve<false><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p);
+    sv->ticket_b += (unsigned long long)nt + grid;
   }
+  ++sv->launches;
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;
 }
@@ -1185,6 +1194,7 @@ int b200ldlt_analyse(b200ldlt_handle h, int dim, int nonzeros, const int* irn, c
   CU(cudaHostAlloc((void**)&sv->h_vals, std::max<size_t>(nonzeros, 1) * sizeof(double), cudaHostAllocDefault));
   memset(sv->h_vals, 0, std::max<size_t>(nonzeros, 1) * sizeof(double));
   sv->analysed = false; sv->factored = false; sv->have_dev_vals = false;
+  if (sv->amat) { b200vec_tmat_destroy(sv->amat); sv->amat = nullptr; }
   if (sv->h_rhs) { cudaFreeHost(sv->h_rhs); sv->h_rhs = nullptr; }
   sv->rhs_cap = 0;   // staging buffers are sized by dim: a new structure invalidates them
   return B200LDLT_SUCCESS;
@@ -1213,7 +1223,7 @@ int b200ldlt_factor_device(b200ldlt_handle h, const double* d_vals, int check_in
 
 int b200ldlt_refactor(b200ldlt_handle h, int check_inertia, int expected_neg, int* num_neg) {
   Solver* sv = (Solver*)h;
-  if (!sv || !sv->analysed || !sv->have_dev_vals) { if (sv) sv->err = "refactor: no matrix on the device"; return B200LDLT_FATAL_ERROR; }
+  if (!sv || !sv->have_dev_vals) { if (sv) sv->err = "refactor: no matrix on the device"; return B200LDLT_FATAL_ERROR; }
   return do_factor(sv, sv->d_vals.p, false, check_inertia, expected_neg, num_neg);
 }
 
@@ -1393,6 +1403,98 @@ int b200ldlt_shard_solve(b200ldlt_handle h, int phase, double* d_rhs) {
   } else return B200LDLT_FATAL_ERROR;
   CU(cudaGetLastError());
   return rc;
+}
+
+/* ---- device-side callers ------------------------------------------------------------------------ */
+namespace b200 {
+struct AugSeg { const double* src; long long off; long long n; double scale, add; };   // out[off+i] = scale*src[i] + add (src NULL: add)
+struct AugSegs { AugSeg s[8]; };
+__global__ void __launch_bounds__(256) k_assemble_augsys(AugSegs A, double* __restrict__ out) {
+  const AugSeg g = A.s[blockIdx.y];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n; i += (long long)gridDim.x * blockDim.x) {
+    double v;
+    if (!g.src) v = g.add;
+    else {
+      v = g.src[i];
+      if (g.scale != 1.0) v = __dmul_rn(g.scale, v);   // IpBlasScal of the SumSymMatrix term (FillValues)
+      if (g.add != 0.0) v = __dadd_rn(v, g.add);       // Vector::AddScalar(delta)
+    }
+    out[g.off + i] = v;
+  }
+}
+}  // namespace b200
+
+int b200ldlt_assemble_augsys_device(b200ldlt_handle h, const b200ldlt_augsys* a) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !a) return B200LDLT_FATAL_ERROR;
+  if (sv->n <= 0 || a->n_d != a->n_s) { sv->err = "assemble_augsys: analyse first / n_d must equal n_s"; return B200LDLT_FATAL_ERROR; }
+  const long long total = (long long)a->nnz_w + a->n_x + a->n_s + a->nnz_jc + a->n_c + a->nnz_jd + a->n_s + a->n_d;
+  if (total != sv->nnz || a->n_x + a->n_s + a->n_c + a->n_d != sv->n) { sv->err = "assemble_augsys: block sizes do not match the analysed structure"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  if (!sv->analysed && !sv->d_vals.p) CU(sv->d_vals.alloc(sv->nnz));   // (the lazy analysis re-allocates and keeps the contents: see do_factor)
+  AugSegs A;
+  long long off = 0;
+  auto seg = [&](int q, const double* src, long long n, double scale, double add) { A.s[q] = AugSeg{src, off, n, scale, add}; off += n; };
+  seg(0, a->W, a->nnz_w, a->W ? a->W_factor : 1.0, 0.0);
+  seg(1, a->D_x, a->n_x, 1.0, a->delta_x);
+  seg(2, a->D_s, a->n_s, 1.0, a->delta_s);
+  seg(3, a->J_c, a->nnz_jc, 1.0, 0.0);
+  seg(4, a->D_c, a->n_c, 1.0, -a->delta_c);
+  seg(5, a->J_d, a->nnz_jd, 1.0, 0.0);
+  seg(6, nullptr, a->n_s, 1.0, -1.0);
+  seg(7, a->D_d, a->n_d, 1.0, -a->delta_d);
+  if (!a->J_c && a->nnz_jc > 0) { sv->err = "assemble_augsys: J_c missing"; return B200LDLT_FATAL_ERROR; }
+  if (!a->J_d && a->nnz_jd > 0) { sv->err = "assemble_augsys: J_d missing"; return B200LDLT_FATAL_ERROR; }
+  long long nmax = 1;
+  for (int q = 0; q < 8; ++q) nmax = std::max(nmax, A.s[q].n);
+  k_assemble_augsys<<<dim3((unsigned)std::min<long long>((nmax + 255) / 256, 1184), 8), 256, 0, sv->stream>>>(A, sv->d_vals.p);
+  CU(cudaGetLastError());
+  sv->have_dev_vals = true;
+  return B200LDLT_SUCCESS;
+}
+
+int b200ldlt_solve_refine_device(b200ldlt_handle h, double* d_rhs, int min_steps, int max_steps, double tol,
+                                 int* steps_done, double* residual_ratio) {
+  Solver* sv = (Solver*)h;
+  if (steps_done) *steps_done = 0;
+  if (!sv || !sv->factored || !sv->have_dev_vals || !d_rhs) { if (sv) sv->err = "solve_refine: factor first (values on the device)"; return B200LDLT_FATAL_ERROR; }
+  CU(cudaSetDevice(sv->dev));
+  const int n = sv->n;
+  if (!sv->vec) {
+    sv->vec = b200vec_create(sv->dev, (void*)sv->stream);
+    if (!sv->vec) { sv->err = "solve_refine: b200vec_create failed"; return B200LDLT_FATAL_ERROR; }
+  }
+  if (!sv->amat) {
+    sv->amat = b200vec_tmat_create(sv->vec, n, n, sv->nnz, sv->irn.data(), sv->jcn.data(), 1);
+    if (!sv->amat) { sv->err = "solve_refine: could not build the triplet operator"; return B200LDLT_FATAL_ERROR; }
+  }
+  if ((int)sv->d_ref_b.n < n) { CU(sv->d_ref_b.alloc(n)); CU(sv->d_ref_r.alloc(n)); }
+  cudaStream_t st = sv->stream;
+  CU(cudaMemcpyAsync(sv->d_ref_b.p, d_rhs, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  sv->launches = 0;
+  int rc = enqueue_solve(sv, d_rhs, d_rhs);
+  if (rc != B200LDLT_SUCCESS) return rc;
+  b200vec vb{sv->d_ref_b.p, n, 0, 0.0}, vx{d_rhs, n, 0, 0.0}, vr{sv->d_ref_r.p, n, 0, 0.0};
+  double nb = 0.0, ratio = 0.0;
+  if (b200vec_amax(sv->vec, &vb, &nb)) { sv->err = b200vec_last_error(sv->vec); return B200LDLT_FATAL_ERROR; }
+  int step = 0;
+  for (;;) {
+    // r = b - A x
+    vr.homogeneous = 0;
+    if (b200vec_copy(sv->vec, &vb, &vr) || b200vec_tmat_mult(sv->amat, sv->d_vals.p, -1.0, &vx, 1.0, &vr)) { sv->err = b200vec_last_error(sv->vec); return B200LDLT_FATAL_ERROR; }
+    double nr = 0.0, nx = 0.0;
+    if (b200vec_amax(sv->vec, &vr, &nr) || b200vec_amax(sv->vec, &vx, &nx)) { sv->err = b200vec_last_error(sv->vec); return B200LDLT_FATAL_ERROR; }
+    ratio = (nb + nx == 0.0) ? nr : nr / (std::min(nx, 1e6 * nb) + nb);
+    if (step >= max_steps || (step >= min_steps && ratio <= tol)) break;
+    rc = enqueue_solve(sv, sv->d_ref_r.p, sv->d_ref_r.p);     // d = A^-1 r
+    if (rc != B200LDLT_SUCCESS) return rc;
+    if (b200vec_axpy(sv->vec, 1.0, &vr, &vx)) { sv->err = b200vec_last_error(sv->vec); return B200LDLT_FATAL_ERROR; }
+    ++step;
+  }
+  CU(cudaStreamSynchronize(st));
+  if (steps_done) *steps_done = step;
+  if (residual_ratio) *residual_ratio = ratio;
+  return B200LDLT_SUCCESS;
 }
 
 int b200ldlt_num_neg(b200ldlt_handle h) { return h ? ((Solver*)h)->num_neg : -1; }

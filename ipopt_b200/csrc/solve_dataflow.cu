@@ -59,7 +59,11 @@ struct __align__(16) FrontDesc {
 // one subtree of k_solve_sub: supernodes [s0, sR] (contiguous: postorder), its level schedule at meta[moff ...]:
 //   meta[moff] = nlv ; then nlv+1 level offsets into the front list ; then nlv counts of small (order <= 64) fronts ;
 //   then the front list itself (nfront ids, by level, small fronts first)
-struct SubDesc { int s0, sR, moff, nlv; };
+struct SubDesc {
+  int s0, sR, moff, nlv;
+  int col0, ncol, nrt, rroot, ch00, nchi, parent, pad;   // first column / #columns, #rows of all fronts / of the root, child list, parent of the root
+  long long L0, nL, ro0;                                 // panel range (doubles), first row-list offset
+};
 
 struct DevSolve {
   const SolveTask* tasks;      // forward list (top part)
@@ -1035,20 +1039,17 @@ struct SubLayout {
   __host__ __device__ long long bytes() const { return fd_off() + (long long)nfront * (long long)sizeof(FrontDesc) + 16; }
 };
 
+// one subtree, by the whole CTA (see the file header).  `mbar` / `mphase`: the CTA's transaction barrier and its phase.
 template <bool FWD>
-__global__ void __launch_bounds__(DF_THREADS, 2) k_solve_sub(DevSym S, DevNum N, DevSolve V, int epoch,
-                                                             double* __restrict__ x, double* __restrict__ cbv) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+__device__ void solve_subtree(const DevSym& S, const DevNum& N, const DevSolve& V, int u, int epoch, unsigned char* smraw,
+                              unsigned long long* mbar, unsigned mphase, double* __restrict__ x, double* __restrict__ cbv) {
   const int tid = threadIdx.x, warp = tid >> 5;
   unsigned long long t_a = 0, t_b = 0;
   if (V.tlog && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
-  const SubDesc sd = V.subs[blockIdx.x];
+  const SubDesc sd = V.subs[u];
   const int s0 = sd.s0, sR = sd.sR, nfront = sR - s0 + 1, nlv = sd.nlv;
-  const int col0 = S.sn_start[s0], ncol = S.sn_start[sR + 1] - col0;
-  const long long L0 = S.L_off[s0], nL = S.L_off[sR + 1] - L0;
-  const long long ro0 = S.rows_ptr[s0], roR = S.rows_ptr[sR];
-  const int nrt = (int)(S.rows_ptr[sR + 1] - ro0), rroot = (int)(S.rows_ptr[sR + 1] - roR);
-  const int ch00 = S.child_ptr[s0], nchi = S.child_ptr[sR + 1] - ch00;
+  const int col0 = sd.col0, ncol = sd.ncol, nrt = sd.nrt, rroot = sd.rroot, ch00 = sd.ch00, nchi = sd.nchi;
+  const long long L0 = sd.L0, nL = sd.nL, ro0 = sd.ro0, roR = sd.ro0 + (sd.nrt - sd.rroot);
   const int nmeta = 2 * nlv + 1 + nfront;
   // carve
   double* Ls = reinterpret_cast<double*>(smraw);
@@ -1067,13 +1068,11 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_sub(DevSym S, DevNum N,
   int* chi = relsub + nrt;
   int* meta = chi + nchi;
   FrontDesc* fds = reinterpret_cast<FrontDesc*>(smraw + lay.fd_off());
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(fds + nfront);
 
-  if (tid == 0) mbar_init(mbar, 1);
-  __syncthreads();
   if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this shared memory before the async write
     mbar_expect_tx(mbar, (unsigned)(nL * 8));
-    bulk_g2s(Ls, N.L + L0, (unsigned long long)nL * 8, mbar);   // the whole subtree's panels: contiguous (postorder)
+    bulk_g2s(Ls, N.L + L0, (unsigned long long)nL * 8, mbar);      // the whole subtree's panels: contiguous (postorder)
   }
   // everything else: plain coalesced loads, all in flight together with the bulk copy
   for (int i = tid; i < ncol; i += DF_THREADS) {
@@ -1091,7 +1090,14 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_sub(DevSym S, DevNum N,
     int4* dst = reinterpret_cast<int4*>(fds);
     for (int i = tid; i < 2 * nfront; i += DF_THREADS) dst[i] = src[i];
   }
-  if (!FWD) for (int i = tid; i < rroot; i += DF_THREADS) rootx[i] = x[S.rows[roR + i]];   // ancestors: final (earlier kernel)
+  if (!FWD) {
+    // the root's contribution rows are columns of ancestors: final once the parent front is done
+    const int grow = (tid < rroot) ? S.rows[roR + tid] : 0;   // (first chunk's row ids in flight before the wait)
+    if (sd.parent >= 0 && tid == 0) wait_eq(V.done_b + sd.parent, epoch);
+    __syncthreads();
+    if (tid < rroot) rootx[tid] = __ldcg(x + grow);
+    for (int i = tid + DF_THREADS; i < rroot; i += DF_THREADS) rootx[i] = __ldcg(x + S.rows[roR + i]);
+  }
   FrontIO io;
   io.Lbase = Ls; io.L0 = L0; io.xs = xs; io.col0 = col0; io.uv = uv; io.ro0 = ro0;
   io.dinv = dinv; io.doff = doff; io.ptype = ptype; io.lperm = lperm;
@@ -1099,7 +1105,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_sub(DevSym S, DevNum N,
   io.fd = fds; io.s0 = s0; io.sR = sR; io.chi = chi; io.ch00 = ch00;
   io.gfd = V.fdesc; io.gcbv = cbv; io.grel = S.rel; io.grows = S.rows; io.gx = x;
   __syncthreads();
-  mbar_wait(mbar, 0);
+  mbar_wait(mbar, mphase);
   if (V.tlog && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
   const int* lvl = meta;              // nlv + 1 offsets into the front list
   const int* nsm = meta + nlv + 1;    // nlv
@@ -1120,29 +1126,32 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_sub(DevSym S, DevNum N,
     __syncthreads();
   }
   // results back to global memory: the x slice (forward: z = D^-1 y in pivot order; backward: the solution), the
-  // root's update vector (forward), and the done flags of every front (read by the top kernel / other plans)
+  // root's update vector (forward), and the done flags (the root's with release semantics: the parent waits for it)
   for (int i = tid; i < ncol; i += DF_THREADS) x[col0 + i] = xs[i];
   if (FWD) {
     for (int i = tid; i < rroot; i += DF_THREADS) cbv[roR + i] = uv[(roR - ro0) + i];
-    for (int i = tid; i < nfront; i += DF_THREADS) V.done_f[s0 + i] = epoch;
+    for (int i = tid; i < nfront - 1; i += DF_THREADS) V.done_f[s0 + i] = epoch;
   } else {
     for (int i = tid; i < nfront; i += DF_THREADS) V.done_b[s0 + i] = epoch;
   }
-  if (V.tlog && tid == 0) {   // debug: 4 timestamps/records per subtree after the task records
+  __syncthreads();
+  if (FWD && tid == 0) st_release(V.done_f + sR, epoch);
+  if (V.tlog && tid == 0) {   // debug: 4 records per subtree after the task records
     unsigned long long t_c;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
-    unsigned long long* rec = V.tlog + 2 * ((unsigned long long)V.ntasks_fwd + V.ntasks_bwd) + 4 * ((FWD ? 0 : (unsigned long long)V.nsub) + blockIdx.x);
+    unsigned long long* rec = V.tlog + 2 * ((unsigned long long)V.ntasks_fwd + V.ntasks_bwd) + 4 * ((FWD ? 0 : (unsigned long long)V.nsub) + u);
     rec[0] = t_a; rec[1] = t_b; rec[2] = t_c; rec[3] = ((unsigned long long)nfront << 32) | (unsigned)nlv;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// top of the tree: persistent task queue
+// ONE persistent kernel per sweep.  Work items are taken with an atomic ticket: forward = subtrees (largest first), then
+// the top tasks by level; backward = top tasks (levels descending), then the subtrees.
 // ------------------------------------------------------------------------------------------------
 template <bool FWD>
-__global__ void __launch_bounds__(DF_THREADS, 2) k_solve_top(DevSym S, DevNum N, DevSolve V, int epoch,
-                                                             unsigned long long ticket_base,
-                                                             double* __restrict__ x, double* __restrict__ cbv) {
+__global__ void __launch_bounds__(DF_THREADS, 2) k_solve(DevSym S, DevNum N, DevSolve V, int epoch,
+                                                         unsigned long long ticket_base,
+                                                         double* __restrict__ x, double* __restrict__ cbv) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ unsigned long long s_ticket;
   __shared__ unsigned long long s_mbar;
@@ -1153,6 +1162,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_top(DevSym S, DevNum N,
   const long long stage_doubles = (DF_DYN_SMEM / 8) - ((DF_THREADS / 32) * DF_WSCR + DF_MIDSCR);
   const SolveTask* tasks = FWD ? V.tasks : V.tasks_bwd;
   const int ntasks = FWD ? V.ntasks_fwd : V.ntasks_bwd;
+  const unsigned long long total = (unsigned long long)ntasks + V.nsub;
   FrontIO io;
   io.Lbase = N.L; io.L0 = 0; io.xs = x; io.col0 = 0; io.uv = cbv; io.ro0 = 0;
   io.dinv = N.dinv; io.doff = N.doff; io.ptype = N.ptype; io.lperm = N.lperm;
@@ -1167,8 +1177,16 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_top(DevSym S, DevNum N,
     __syncthreads();
     const unsigned long long tk = s_ticket;
     __syncthreads();
-    if (tk >= (unsigned long long)ntasks) return;
-    const SolveTask T = tasks[tk];
+    if (tk >= total) return;
+    const bool is_sub = FWD ? (tk < (unsigned long long)V.nsub) : (tk >= (unsigned long long)ntasks);
+    if (is_sub) {
+      solve_subtree<FWD>(S, N, V, (int)(FWD ? tk : tk - ntasks), epoch, smraw, &s_mbar, mphase, x, cbv);
+      mphase ^= 1;
+      __syncthreads();
+      continue;
+    }
+    const unsigned long long ti = FWD ? tk - V.nsub : tk;
+    const SolveTask T = tasks[ti];
     unsigned long long t_start = 0;
     if (V.tlog && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     if (T.type == ST_SMALL) {
@@ -1210,7 +1228,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve_top(DevSym S, DevNum N,
     if (V.tlog && threadIdx.x == 0) {
       unsigned long long t_end;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-      unsigned long long* rec = V.tlog + 2 * ((FWD ? 0 : (unsigned long long)V.ntasks_fwd) + tk);
+      unsigned long long* rec = V.tlog + 2 * ((FWD ? 0 : (unsigned long long)V.ntasks_fwd) + ti);
       rec[0] = t_start; rec[1] = t_end;
     }
   }

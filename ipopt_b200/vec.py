@@ -113,6 +113,7 @@ class DenseVector:
         assert len(x) == self._v.n
         if self._v.n:
             self._buf[: self._v.n].copy_(self.ctx._torch.from_numpy(x))
+            self.ctx._torch.cuda.current_stream().synchronize()   # the context's stream does not wait for torch's stream
         self._v.homogeneous = 0
 
     def ExpandedValues(self):
@@ -172,6 +173,7 @@ class ExpansionMatrix:
         p = np.ascontiguousarray(exp_pos, dtype=np.int32)
         assert len(p) == ncols
         self._pos = ctx._torch.from_numpy(p if ncols else np.zeros(1, np.int32)).to(ctx.device)
+        ctx._torch.cuda.current_stream().synchronize()
 
     def _pp(self):
         return C.c_void_p(self._pos.data_ptr())
@@ -210,6 +212,7 @@ class TripletMatrix:
         assert len(v) == self.nnz
         if self.nnz:
             self._vals[: self.nnz].copy_(self.ctx._torch.from_numpy(v))
+            self.ctx._torch.cuda.current_stream().synchronize()
 
     def MultVector(self, alpha, x, beta, y):
         self.ctx.check(self.ctx._L.b200vec_tmat_mult(self._h, C.c_void_p(self._vals.data_ptr()), alpha, x._p(), beta, y._p()))

@@ -8,7 +8,8 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 NF = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dim, irn, jcn, val, nc = mbndry_kkt(N, sigma_spread=3.0, seed=1)
 _, _, _, v0, _ = mbndry_kkt(N, w_zero=True)
-s = B200Ldlt(verbose=1)
+import os
+s = B200Ldlt(verbose=1, tc_schur_min_r=int(os.environ.get("B200_TC_MIN_R", "0")))
 s.InitializeStructure(dim, len(irn), irn, jcn)
 a = s.GetValuesArrayPtr()
 a[:] = v0

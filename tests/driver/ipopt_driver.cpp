@@ -162,13 +162,24 @@ int main(int argc, char** argv)
    }
    SmartPtr<CapturingTNLP> tnlp = new CapturingTNLP(inner);
 
+   // "ma97": NO custom hook at all -- the stock reference code path  linear_solver=ma97 + hsllib=<libb200ldlt.so>  (the
+   // reference dlopen()s the library and binds the seven ma97_*_d symbols of ipopt_b200/csrc/hsl_shim.cpp)
+   const bool via_hsllib = backend == "ma97";
    const LdltBackend* be = backend == "oracle" ? &oracle_backend : GetB200LdltBackend();
    SmartPtr<B200LdltSolverInterface> iface = new B200LdltSolverInterface(be);
    if( !dump_prefix.empty() ) iface->SetDump(dump_prefix, dump_which);
 
    SmartPtr<IpoptApplication> app = IpoptApplicationFactory();
    B200LdltSolverInterface::RegisterOptions(app->RegOptions());
-   app->Options()->SetStringValue("linear_solver", "custom");
+   if( via_hsllib )
+   {
+      const char* lib = getenv("B200_HSLLIB");
+      if( !lib ) { fprintf(stderr, "--backend ma97 needs B200_HSLLIB=<path to libb200ldlt.so>\n"); return 2; }
+      app->Options()->SetStringValue("linear_solver", "ma97");
+      app->Options()->SetStringValue("hsllib", lib);
+   }
+   else
+      app->Options()->SetStringValue("linear_solver", "custom");
    app->Options()->SetIntegerValue("print_level", print_level);
    if( problem == "hs071" )
    {  // the settings of reference examples/hs071_cpp/hs071_main.cpp:33-35
@@ -200,7 +211,8 @@ int main(int argc, char** argv)
    SmartPtr<NLP> nlp = new TNLPAdapter(GetRawPtr(tnlp), app->Jnlst());
 
    double t0 = wall_now();
-   st = app->OptimizeNLP(nlp, builder);
+   if( via_hsllib ) st = app->OptimizeTNLP(GetRawPtr(tnlp));
+   else st = app->OptimizeNLP(nlp, builder);
    double total = wall_now() - t0;
 
    int iters = -1;
@@ -212,7 +224,7 @@ int main(int argc, char** argv)
             "{\"backend\": \"%s\", \"problem\": \"%s\", \"N\": %d, \"status\": %d, \"iterations\": %d, \"objective\": %.17g, "
             "\"kkt_dim\": %d, \"kkt_nnz\": %d, \"n_factor\": %d, \"n_solve\": %d, \"n_rhs\": %d, \"n_singular\": %d, "
             "\"n_wrong_inertia\": %d, \"t_first_factor_s\": %.6f, \"t_factor_s\": %.6f, \"t_solve_s\": %.6f, \"t_total_s\": %.6f, \"host_threads\": %d}",
-            be->name, problem.c_str(), N, (int) st, iters, obj, S.dim, S.nonzeros, S.n_factor, S.n_solve, S.n_rhs,
+            via_hsllib ? "ma97-shim(b200-ldlt)" : be->name, problem.c_str(), N, (int) st, iters, obj, S.dim, S.nonzeros, S.n_factor, S.n_solve, S.n_rhs,
             S.n_singular, S.n_wrong_inertia, S.t_first_factor, S.t_factor, S.t_solve, total, omp_get_max_threads());
    printf("DRIVER_JSON %s\n", buf);
    if( !json_path.empty() ) { FILE* fp = fopen(json_path.c_str(), "w"); if( fp ) { fprintf(fp, "%s\n", buf); fclose(fp); } }

@@ -11,6 +11,11 @@
 #include "IpExpansionMatrix.hpp"
 #include "IpGenTMatrix.hpp"
 #include "IpSymTMatrix.hpp"
+#include "IpCompoundSymMatrix.hpp"
+#include "IpDiagMatrix.hpp"
+#include "IpIdentityMatrix.hpp"
+#include "IpSumSymMatrix.hpp"
+#include "IpTripletHelper.hpp"
 
 using namespace Ipopt;
 
@@ -144,6 +149,68 @@ int vecref_tmat(int symmetric, int trans, int nrows, int ncols, int nnz, const i
    }
    read_back(*Y, y, hy, sy);
    return 0;
+}
+
+
+// The augmented system exactly as StdAugSystemSolver composes it (reference src/Algorithm/IpStdAugSystemSolver.cpp:232-430)
+// from W (SymTMatrix), J_c, J_d (GenTMatrix) and the diagonal vectors, flattened by TripletHelper::FillRowCol / FillValues
+// (src/LinAlg/TMatrices/IpTripletHelper.cpp:805-873) -- what TSymLinearSolver hands to the linear solver.
+// D_* may be NULL (then only delta).  irn/jcn/vals: capacity nnz_w + n_x + n_s + nnz_jc + n_c + nnz_jd + n_s + n_s.
+int vecref_augsys_fill(int n_x, int n_s, int n_c,
+                       int nnz_w, const int* w_i, const int* w_j, const double* w_v, double W_factor,
+                       int nnz_jc, const int* jc_i, const int* jc_j, const double* jc_v,
+                       int nnz_jd, const int* jd_i, const int* jd_j, const double* jd_v,
+                       const double* D_x, double delta_x, const double* D_s, double delta_s,
+                       const double* D_c, double delta_c, const double* D_d, double delta_d,
+                       int* irn, int* jcn, double* vals)
+{
+   const int n_d = n_s;
+   SmartPtr<SymTMatrixSpace> wsp = new SymTMatrixSpace(n_x, nnz_w, w_i, w_j);
+   SmartPtr<SymTMatrix> W = wsp->MakeNewSymTMatrix();
+   if( nnz_w > 0 ) W->SetValues(w_v);
+   SmartPtr<GenTMatrixSpace> jcsp = new GenTMatrixSpace(n_c, n_x, nnz_jc, jc_i, jc_j);
+   SmartPtr<GenTMatrix> Jc = jcsp->MakeNewGenTMatrix();
+   if( nnz_jc > 0 ) Jc->SetValues(jc_v);
+   SmartPtr<GenTMatrixSpace> jdsp = new GenTMatrixSpace(n_d, n_x, nnz_jd, jd_i, jd_j);
+   SmartPtr<GenTMatrix> Jd = jdsp->MakeNewGenTMatrix();
+   if( nnz_jd > 0 ) Jd->SetValues(jd_v);
+   SmartPtr<DenseVectorSpace> vx = new DenseVectorSpace(n_x), vs = new DenseVectorSpace(n_s), vc = new DenseVectorSpace(n_c),
+                              vd = new DenseVectorSpace(n_d);
+   const int total = n_x + n_s + n_c + n_d;
+   SmartPtr<CompoundSymMatrixSpace> asp = new CompoundSymMatrixSpace(4, total);
+   asp->SetBlockDim(0, n_x); asp->SetBlockDim(1, n_s); asp->SetBlockDim(2, n_c); asp->SetBlockDim(3, n_d);
+   SmartPtr<DiagMatrixSpace> dx = new DiagMatrixSpace(n_x), ds = new DiagMatrixSpace(n_s), dc = new DiagMatrixSpace(n_c),
+                             dd = new DiagMatrixSpace(n_d);
+   SmartPtr<SumSymMatrixSpace> sx = new SumSymMatrixSpace(n_x, 2);
+   sx->SetTermSpace(0, *wsp); sx->SetTermSpace(1, *dx);
+   SmartPtr<IdentityMatrixSpace> isp = new IdentityMatrixSpace(n_s);
+   asp->SetCompSpace(0, 0, *sx); asp->SetCompSpace(1, 1, *ds); asp->SetCompSpace(2, 0, *jcsp); asp->SetCompSpace(2, 2, *dc);
+   asp->SetCompSpace(3, 0, *jdsp); asp->SetCompSpace(3, 1, *isp); asp->SetCompSpace(3, 3, *dd);
+   SmartPtr<CompoundSymMatrix> A = asp->MakeNewCompoundSymMatrix();
+   struct Mk {
+      static SmartPtr<Vector> diag(const DenseVectorSpace& sp, const double* D, double delta)
+      {  // the D + delta logic of CreateAugmentedSystem (:344-366)
+         SmartPtr<DenseVector> t = sp.MakeNewDenseVector();
+         if( D ) { if( sp.Dim() > 0 ) t->SetValues(D); else t->Set(0.); if( delta != 0. ) t->AddScalar(delta); }
+         else t->Set(delta);
+         return GetRawPtr(t);
+      }
+   };
+   SmartPtr<SumSymMatrix> sumx = sx->MakeNewSumSymMatrix();
+   sumx->SetTerm(0, W_factor, *W);
+   SmartPtr<DiagMatrix> mdx = dx->MakeNewDiagMatrix(); mdx->SetDiag(*Mk::diag(*vx, D_x, delta_x));
+   sumx->SetTerm(1, 1.0, *mdx);
+   A->SetComp(0, 0, *sumx);
+   SmartPtr<DiagMatrix> mds = ds->MakeNewDiagMatrix(); mds->SetDiag(*Mk::diag(*vs, D_s, delta_s)); A->SetComp(1, 1, *mds);
+   A->SetComp(2, 0, *Jc);
+   SmartPtr<DiagMatrix> mdc = dc->MakeNewDiagMatrix(); mdc->SetDiag(*Mk::diag(*vc, D_c, -delta_c)); A->SetComp(2, 2, *mdc);
+   A->SetComp(3, 0, *Jd);
+   SmartPtr<IdentityMatrix> id = isp->MakeNewIdentityMatrix(); id->SetFactor(-1.0); A->SetComp(3, 1, *id);
+   SmartPtr<DiagMatrix> mdd = dd->MakeNewDiagMatrix(); mdd->SetDiag(*Mk::diag(*vd, D_d, -delta_d)); A->SetComp(3, 3, *mdd);
+   const int nnz = TripletHelper::GetNumberEntries(*A);
+   TripletHelper::FillRowCol(nnz, *A, irn, jcn);
+   TripletHelper::FillValues(nnz, *A, vals);
+   return nnz;
 }
 
 }

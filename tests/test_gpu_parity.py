@@ -253,7 +253,8 @@ def _run_driver(backend, problem, N, tmp_path, opts=None):
     if not os.path.exists(DRIVER):
         pytest.skip("tests/driver/ipopt_driver not built (needs /root/reference at build time)")
     js, fin = str(tmp_path / "r.json"), str(tmp_path / "f.bin")
-    env = dict(os.environ, OMP_NUM_THREADS=str(min(16, os.cpu_count() or 1)))
+    env = dict(os.environ, OMP_NUM_THREADS=str(min(16, os.cpu_count() or 1)),
+               B200_HSLLIB=os.path.join(ROOT, "ipopt_b200", "lib", "libb200ldlt.so"))
     cmd = [DRIVER, "--backend", backend, "--problem", problem, "--N", str(N), "--print-level", "0", "--json", js, "--final", fin]
     for k, v in (opts or {}).items():
         cmd += ["--opt", "%s=%s" % (k, v)]
@@ -369,6 +370,23 @@ def test_ip_loop_parity_inertia_restoration_lbfgs(problem, N, opts, tag, tmp_pat
         ref = gold[key]
         scale = max(np.abs(ref).max(), 1e-300)
         assert np.abs(fin[key] - ref).max() <= RTOL * scale, key
+
+
+@pytest.mark.parametrize("problem,N", [("hs071", 0), ("MBndryCntrl1", 30), ("MDistCntrl3a", 25), ("LukVlE1", 1000)])
+def test_ma97_shim_through_stock_ipopt(problem, N, tmp_path):
+    """SURVEY.md 8b' / 8f-3: the UNMODIFIED reference code path  linear_solver=ma97 + hsllib=libb200ldlt.so  -- Ipopt's own
+    Ma97SolverInterface (IpMa97SolverInterface.cpp:303-314) dlopen()s the library and drives the GPU backend through the
+    seven ma97_*_d entry points of ipopt_b200/csrc/hsl_shim.cpp; no custom hook, no plugin.  Same iterates as the oracle
+    run behind the custom-solver hook."""
+    summ, fin = _run_driver("ma97", problem, N, tmp_path)
+    gold = np.load(os.path.join(G, "%s_%d_final.npz" % (problem, N)))
+    assert summ["status"] == 0 and summ["backend"].startswith("ma97-shim")
+    assert abs(summ["iterations"] - int(gold["iterations"])) <= 1
+    assert abs(fin["obj"] - float(gold["obj"])) <= 1e-9 * max(abs(float(gold["obj"])), 1e-12)
+    for key in ("x", "lam", "z_L", "z_U"):
+        ref = gold[key]
+        scale = max(np.abs(ref).max(), 1e-300)
+        assert np.abs(fin[key] - ref).max() <= 1e-7 * scale, key   # (another adapter: other refinement / scaling defaults)
 
 
 @pytest.mark.parametrize("world", [2, 4])
