@@ -1,21 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- KKT LDL^T factor+solve throughput of the B200 backend (contract: see the task statement).
 
-A "step" = the linear algebra of ONE interior-point iteration on the workload BASELINE.json's target is quoted
-on (MBndryCntrl1 N=400, KKT dim 321 600, 1 283 200 triplets): one numeric factorisation of a new KKT matrix
-(inertia check on) + two back-solves (step + one refinement), the call pattern measured on the reference's
-IP loop (1 factorisation + 2 back-solves per iteration).
+A "step" = the linear algebra of ONE interior-point iteration: one numeric factorisation of a new KKT matrix (inertia
+check on) + two back-solves (step + one refinement), the call pattern measured on the reference's IP loop (SURVEY.md 8c:
+1 factorisation + 2 back-solves per iteration).  Workload: --gpus 1 -> MBndryCntrl1 N=400 (KKT dim 321 600, 1 283 200
+triplets: the configuration BASELINE.json's target is quoted on); --gpus > 1 -> BASELINE config 5, MBndryCntrl1 N=800
+(dim 1 283 200), ONE system factorised + solved by all GPUs together (elimination-tree sharding, "strong" scaling), with
+the single-GPU time of the same N=800 step measured in the same run and printed in the same line.
 
   value : steps/s with the KKT values and right-hand sides already resident in HBM (b200ldlt_factor_device /
           b200ldlt_solve_device), CUDA events on the launching stream, max over ranks.
   e2e   : the same through the reference-facing C-ABI calls with HOST buffers (b200ldlt_factor reads the pinned
           values array Ipopt fills, b200ldlt_solve takes/returns host rhs) -- H2D/D2H inside the timed region.
-  roofline : the HBM-bound triangular-solve sweep (forward+backward): algorithmic bytes 2*8*nnz(L) + vector/index
-          traffic / its measured duration, against MEASURED_PEAKS.json's hbm_gbs.
-  cpu_baseline : the CPU oracle (oracle/cpu_ldlt.cpp, "port") on the host cores on the same matrix.
---impl reference times that CPU path alone (the reference's third-party MUMPS is not in /root/reference).
-Multi-GPU (N>1): independent replicas of the single-GPU workload (weak scaling, no data-path collective);
-elimination-tree sharding of the N=800 config is the next SURVEY.md 8e row.
+  roofline : the HBM-bound triangular-solve sweeps (k_solve<fwd> + k_solve<bwd>): algorithmic bytes 2*8*nnz(L) +
+          vector traffic / their measured duration, against MEASURED_PEAKS.json's hbm_gbs;
+          roofline_schur: the Schur-complement GEMM's pipe utilisation from the committed ncu export.
+  cpu_baseline : the CPU oracle (oracle/cpu_ldlt.cpp, "port") on the host cores on the same matrix.  The reference's own
+          comparator, MUMPS, is probed for at run time (ldconfig / pkg-config) and is absent from this image.
+  ip_loop : the reference's unmodified interior-point loop (tests/driver/ipopt_driver) on the same problem with the
+          B200 backend and with the CPU oracle: iterations, wall seconds, IP iterations per second.
+--impl reference times the CPU path alone, same steps / warm-up as the product arm.
 """
 import argparse
 import json
@@ -32,21 +36,59 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOAD_N = 400
+SHARDED_N = 800
 SNAP_ITERS = [2, 8, 15]
 
 
-def get_snapshots(rank):
+def probe_mumps():
+    """is the reference's CPU comparator (MUMPS) installed on this box?"""
+    found = []
+    try:
+        out = subprocess.run(["ldconfig", "-p"], capture_output=True, text=True, timeout=10).stdout
+        found += [l.split()[0] for l in out.splitlines() if "mumps" in l.lower()]
+    except Exception:
+        pass
+    try:
+        if subprocess.run(["pkg-config", "--exists", "coinmumps"], timeout=10).returncode == 0:
+            found.append("pkg-config:coinmumps")
+    except Exception:
+        pass
+    return {"found": found, "note": "MUMPS present: rebuild oracle/_ref --with-mumps for a MUMPS column" if found else
+            "no MUMPS library on this box (ldconfig -p | grep -i mumps; pkg-config --exists coinmumps): the CPU column is the oracle port"}
+
+
+def run_ip_loop(backend, N, threads):
+    """The reference's own IP loop on MBndryCntrl1(N) with the given linear-solver backend (tests/driver/ipopt_driver)."""
+    drv = os.path.join(ROOT, "tests", "driver", "ipopt_driver")
+    if not os.path.exists(drv):
+        return None
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    try:
+        out = subprocess.run([drv, "--backend", backend, "--problem", "MBndryCntrl1", "--N", str(N), "--print-level", "0"],
+                             env=env, timeout=900, capture_output=True, text=True).stdout
+        d = json.loads([l for l in out.splitlines() if l.startswith("DRIVER_JSON ")][-1][len("DRIVER_JSON "):])
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)[:200]}
+    it = d["iterations"]
+    return {"iterations": it, "status": d["status"], "total_s": d["t_total_s"], "iters_per_sec": it / d["t_total_s"],
+            "analysis_first_factor_s": d["t_first_factor_s"], "factor_ms_per_call": 1e3 * d["t_factor_s"] / max(d["n_factor"] - 1, 1),
+            "solve_ms_per_call": 1e3 * d["t_solve_s"] / max(d["n_solve"], 1), "n_factor": d["n_factor"], "n_solve": d["n_solve"],
+            "objective": d["objective"]}
+
+
+def get_snapshots(rank, N=None, backend="oracle"):
     """Real KKT systems of the reference's MBndryCntrl1(N) run, captured at the solver boundary by running the
     reference IP loop (driver binary) with the CPU oracle for a few iterations; synthetic same-pattern fallback."""
     import struct
+    N = N or WORKLOAD_N
     drv = os.path.join(ROOT, "tests", "driver", "ipopt_driver")
-    cache = os.path.join("/tmp", "b200_bench_snap_%d" % WORKLOAD_N)
+    cache = os.path.join("/tmp", "b200_bench_snap_%d" % N)
     paths = [cache + "_%d.bin" % k for k in SNAP_ITERS]
-    src = "reference IP loop (MBndryCntrl1 N=%d) KKT snapshots at factorisations %s" % (WORKLOAD_N, SNAP_ITERS)
+    src = "reference IP loop (MBndryCntrl1 N=%d) KKT snapshots at factorisations %s" % (N, SNAP_ITERS)
     if rank == 0 and not all(os.path.exists(p) for p in paths) and os.path.exists(drv):
         env = dict(os.environ, OMP_NUM_THREADS=str(min(32, os.cpu_count() or 1)))
         try:
-            subprocess.run([drv, "--backend", "oracle", "--problem", "MBndryCntrl1", "--N", str(WORKLOAD_N),
+            subprocess.run([drv, "--backend", backend, "--problem", "MBndryCntrl1", "--N", str(N),
                             "--print-level", "0", "--dump", cache, "--dump-iters", ",".join(map(str, SNAP_ITERS)),
                             "--opt", "max_iter=%d" % (max(SNAP_ITERS) + 1)], env=env, timeout=600,
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -69,7 +111,7 @@ def get_snapshots(rank):
         from ipopt_b200.kkt import mbndry_kkt
         src = "synthetic MBndryCntrl1-pattern KKT (driver binary unavailable)"
         for k, spread in zip(SNAP_ITERS, (1.0, 4.0, 8.0)):
-            dim, irn, jcn, val, nc = mbndry_kkt(WORKLOAD_N, sigma_spread=spread, seed=k)
+            dim, irn, jcn, val, nc = mbndry_kkt(N, sigma_spread=spread, seed=k)
             snaps.append(dict(dim=dim, irn=irn, jcn=jcn, val=val, rhs=np.random.default_rng(k).standard_normal(dim), neg=nc))
     return snaps, src
 
@@ -138,23 +180,25 @@ def main():
     host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cpu_threads = min(host_cores, 32)
 
-    config = {"workload": "MBndryCntrl1 N=%d KKT (dim 321600, 1283200 triplets): 1 numeric LDL^T + 2 back-solves per step" % WORKLOAD_N,
-              "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
-              "l2_policy": "working set (L 190 MB + contribution blocks 475 MB) exceeds the 126 MB L2; 3 different matrices cycled"}
+    wl_N = WORKLOAD_N if world == 1 else SHARDED_N
+    wl_dim = wl_N * wl_N * 2 + 4 * wl_N
+    config = {"workload": "MBndryCntrl1 N=%d KKT (dim %d): 1 numeric LDL^T + 2 back-solves per step" % (wl_N, wl_dim),
+              "parallelism": ("elimination-tree sharding over %d GPUs" % world) if world > 1 else "single GPU",
+              "l2_policy": "working set (L + contribution blocks: hundreds of MB) exceeds the 126 MB L2; 3 different matrices cycled"}
 
     if args.impl == "reference":
-        # CPU path of the same workload (the reference's MUMPS is a third-party library absent from /root/reference:
-        # this is the oracle port, all host threads), rank 0 only.
+        # CPU path of the same workload (the reference's MUMPS is a third-party library absent from /root/reference and
+        # from this image -- see probe_mumps(): this is the oracle port on all host threads), rank 0 only.
         if rank != 0:
             return 0
-        snaps, src = get_snapshots_nodist()
-        Kc = min(K, 20)
-        sec, st = time_oracle(snaps, Kc, min(W, 1), cpu_threads)
+        snaps, src = get_snapshots_nodist(wl_N)
+        sec, st = time_oracle(snaps, K, W, cpu_threads)
         line = {"impl": "reference", "metric": "kkt_factor_solve_iters_per_sec", "value": 1.0 / sec, "unit": "iter/s",
-                "n_gpus": args.gpus, "steps": Kc, "warmup": min(W, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": src, "config": config,
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": src, "config": config,
                 "cpu_baseline": {"value": 1.0 / sec, "unit": "iter/s", "cores": cpu_threads, "kind": "port",
-                                 "sample": "%d steps (1 factorisation + 2 solves each) of the same KKT snapshots" % Kc},
+                                 "sample": "%d steps (1 factorisation + 2 solves each) of the same KKT snapshots; CPU oracle, NOT MUMPS" % K},
+                "mumps_probe": probe_mumps(),
                 "e2e": {"value": 1.0 / sec, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -166,11 +210,14 @@ def main():
     torch.cuda.set_device(local_rank)
     from ipopt_b200 import B200Ldlt
 
+    if world > 1:
+        # config 5 (N=800): the snapshots come from the reference IP loop driven by the B200 backend itself on rank 0
+        # (the CPU oracle needs minutes per run at this size)
+        snaps, src = get_snapshots(rank, SHARDED_N, backend="b200")
+        return run_sharded(args, snaps, src, config, rank, local_rank, world, K, W, host_cores)
     snaps, src = get_snapshots(rank)
     s0 = snaps[0]
     dim, nnz = s0["dim"], len(s0["irn"])
-    if world > 1:
-        return run_sharded(args, snaps, src, config, rank, local_rank, world, K, W, host_cores)
     stream = torch.cuda.Stream(local_rank)     # a real stream (handle 0 would make the library create its own)
     torch.cuda.set_stream(stream)              # torch copies / events below run on the stream the kernels are launched on
     solver = B200Ldlt(device=local_rank, stream=stream.cuda_stream)
@@ -270,6 +317,11 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        ncu = {}
+        try:   # figures read from the committed ncu exports (profiles/r2_ncu_metrics.json, made by scripts/ncu_extract.py)
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_metrics.json")))
+        except Exception:
+            pass
         nnzL = info["nnz_L"]
         tri_bytes = 2 * 8 * nnzL + 8 * 4 * dim   # L streamed twice + 2 reads/2 writes of the vector
         ach = tri_bytes / (tri_ms * 1e-3) / 1e9
@@ -285,6 +337,11 @@ def main():
             sec_cpu = time_oracle(snaps, 3, 1, best_t)[0]
             cpu_threads = best_t
         step_ms = ms_dev / K
+        # the metric's other half: IP iterations per second of the reference's own loop, both backends
+        ip_loop = None
+        if not skip_cpu:
+            ip_loop = {"problem": "MBndryCntrl1 N=%d, default Ipopt options (reference examples/ScalableProblems)" % WORKLOAD_N,
+                       "b200": run_ip_loop("b200", WORKLOAD_N, 1), "cpu_oracle": run_ip_loop("oracle", WORKLOAD_N, cpu_threads)}
         line = {
             "metric": "kkt_factor_solve_iters_per_sec", "value": world * K / (ms_dev * 1e-3), "unit": "iter/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True,
@@ -294,18 +351,21 @@ def main():
             "gpu_launches": launches_timed,
             "kkt_factor_solve_ms_per_iter": {"device_resident": step_ms, "e2e_host_buffers": ms_e2e / K,
                                              "factor_ms": fac_ms, "solve_ms_per_rhs": tri_ms},
-            "roofline": {"kernel": "supernodal triangular solve sweeps (k_solve_dataflow<fwd> + k_solve_dataflow<bwd>, persistent task-queue kernels)",
+            "roofline": {"kernel": "supernodal triangular solve sweeps (k_solve<fwd> + k_solve<bwd>: shared-memory subtree tasks + chunked big-front GEMV tasks, one persistent kernel per sweep)",
                          "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": 488.2e6 if dim == 321600 else None,
-                         "traffic_source": "ncu --set full of k_solve_dataflow fwd+bwd (dram__bytes_read+write: 239.5+11.7+233.1+3.8 MB), profiles/r1_summary.md",
+                         "traffic": ncu.get("solve_dram_bytes_per_solve") if dim == ncu.get("dim") else None,
+                         "traffic_source": ncu.get("solve_source"),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_solve": tri_bytes},
+            "roofline_schur": ncu.get("schur"),
             "factor": {"flops_panel": info["flops_panel"], "flops_schur": info["flops_schur"],
                        "gflops_achieved": (info["flops_panel"] + info["flops_schur"]) / (fac_ms * 1e-3) / 1e9,
                        "nnz_L": nnzL, "supernodes": info["nsupernodes"], "levels": info["nlevels"], "max_front": info["max_front"]},
             "cpu_baseline": None if skip_cpu else
                             {"value": 1.0 / sec_cpu, "unit": "iter/s", "ms_per_step": sec_cpu * 1e3, "cores": cpu_threads, "kind": "port",
                              "sample": "3 steps (1 factorisation + 2 solves each) of the same KKT snapshots; CPU oracle, not MUMPS"},
+            "mumps_probe": probe_mumps(),
+            "ip_loop": ip_loop,
             "analysis_once_s": {"wall_first_factor": t_analyse, "ordering": info["t_order_s"], "symbolic": info["t_symbolic_s"]},
             "parity": {"scaled_residual": r / (xi + bi), "num_neg": info["num_neg"], "expected_neg": snaps[1]["neg"]},
             "clocks": sampler.summary(), "host_cores": host_cores,
@@ -325,6 +385,32 @@ def run_sharded(args, snaps, src, config, rank, local_rank, world, K, W, host_co
     from ipopt_b200.sharded import ShardedLdlt
     s0 = snaps[0]
     dim, nnz = s0["dim"], len(s0["irn"])
+    # like-for-like point of the scaling curve: the SAME N=800 step on one GPU (rank 0, unsharded), measured in this run
+    single = None
+    if rank == 0:
+        from ipopt_b200 import B200Ldlt
+        one = B200Ldlt(device=local_rank)
+        assert one.InitializeStructure(dim, nnz, s0["irn"], s0["jcn"]) == 0
+        one.GetValuesArrayPtr()[:] = s0["val"]
+        assert one.factor(True, s0["neg"])[0] == 0
+        dv = [torch.from_numpy(sn["val"]).cuda() for sn in snaps]
+        dr = [torch.from_numpy(sn["rhs"]).cuda() for sn in snaps]
+        dw = torch.empty(dim, dtype=torch.float64, device="cuda")
+        ks = max(3, min(K, 10))
+        tot = 0.0
+        for i in range(2 + ks):
+            q = i % len(snaps)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            assert one.factor_device(dv[q].data_ptr(), True, snaps[q]["neg"])[0] == 0
+            for _ in range(2):
+                dw.copy_(dr[q]); one.solve_device(dw.data_ptr(), 1)
+            torch.cuda.synchronize()
+            if i >= 2:
+                tot += time.perf_counter() - t1
+        single = {"ms_per_step": 1e3 * tot / ks, "steps": ks, "note": "same workload, unsharded, one GPU (rank 0), device-resident"}
+        one.close(); del dv, dr, dw
+        torch.cuda.empty_cache()
+    dist.barrier()
     t0 = time.perf_counter()
     sh = ShardedLdlt(dim, s0["irn"], s0["jcn"], s0["val"], device=local_rank)
     t_analyse = time.perf_counter() - t0
@@ -381,7 +467,8 @@ def run_sharded(args, snaps, src, config, rank, local_rank, world, K, W, host_co
                 "vs_baseline": None, "dtype": "f64", "data": src, "config": cfg,
                 "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "iter/s", "ms_per_step": ms_e2e / K,
                         "h2d_bytes_per_step": world * 8 * nnz + 2 * world * 8 * dim, "d2h_bytes_per_step": 2 * 8 * dim + 32 * world},
-                "gpu_launches": K * (sh.ranks[0].s.info()["launches_factor"] + 2 * 6), "analysis_once_s": {"wall": t_analyse},
+                "gpu_launches": K * (sh.ranks[0].s.info()["launches_factor"] + 2 * 4), "analysis_once_s": {"wall": t_analyse},
+                "single_gpu": single, "speedup_vs_single_gpu": (single["ms_per_step"] / (ms_dev / K)) if single else None,
                 "parity": {"scaled_residual": r / (xi + bi)}, "clocks": sampler.summary(), "host_cores": host_cores}
         print(json.dumps(line))
     sh.close()
@@ -389,10 +476,10 @@ def run_sharded(args, snaps, src, config, rank, local_rank, world, K, W, host_co
     return 0
 
 
-def get_snapshots_nodist():
+def get_snapshots_nodist(N=None):
     ws = os.environ.pop("WORLD_SIZE", None)
     try:
-        return get_snapshots(0)
+        return get_snapshots(0, N)
     finally:
         if ws is not None:
             os.environ["WORLD_SIZE"] = ws

@@ -684,6 +684,7 @@ static int run_analysis(Solver* sv, const double* vals) {
   CU(sv->d_front_list.upload(fl, st));
   { int rc2 = upload_schur_lists(sv, sv->schur, st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
   CU(cudaFuncSetAttribute(k_tc_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(k_big_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
   CU(cudaFuncSetAttribute(k_front_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CU(cudaFuncSetAttribute(k_front_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -857,30 +858,67 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         CU(cudaEventRecord(e, st));
         CU(cudaStreamWaitEvent(sb, e, 0));
       }
-      // Per panel p:  chain stream:  diag(p) -> next(p)      (next = TRSM of the 32 rows of the next diagonal block + that
-      //                                                     block's rank-32 update; needs the bulk update of panel p-1)
-      //               bulk stream :  trsm(p) [after diag(p)] -> update(p) [after next(p): it reads those 32 rows' L / W]
-      // so diag(p+1) waits for diag(p) + next(p) only, and trsm(p) + update(p) run under the next diagonal block.
-      cudaEvent_t e_upd_prev = nullptr;
-      for (int jb = 0; jb < P.big_kmax; jb += NB) {
-        k_big_diag<<<P.big_cnt, 32, 0, st>>>(D, N, bl, jb); ++L;
-        cudaEvent_t ed = sv->next_event();
-        CU(cudaEventRecord(ed, st));
-        CU(cudaStreamWaitEvent(sb, ed, 0));
+      // Panel pipeline on three streams (all inside the captured graph):
+      //   chain  (st): k_big_chain(p) = [update of panel p-1 on its two tiles] + panel rows of block p+1 + LDL^T of block p+1
+      //                 needs trsm(p-1) and update(p-2)
+      //   trsm   (sb): k_big_trsm(p)   needs the LDL^T of block p = chain(p-1)
+      //   update (su): k_big_update(p) needs trsm(p) and chain(p) (the panel rows of block p+1)
+      // so the trailing work of a panel has a full chain step of slack and the chain is one launch per 32 pivots.
+      cudaStream_t su = sv->dbg.one_stream ? st : sv->stream3;
+      {
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, st));
+        CU(cudaStreamWaitEvent(su, e, 0));
+      }
+      const int npan = (P.big_kmax + NB - 1) / NB;
+      std::vector<cudaEvent_t> eT(npan + 2, nullptr), eUB(npan + 2, nullptr);
+      k_big_chain<<<P.big_cnt, 128, CHAIN_SMEM, st>>>(D, N, bl, -NB); ++L;     // LDL^T of block 0
+      for (int p = 0; p < npan; ++p) {
+        const int jb = p * NB;
+        // trsm(p): needs the LDL^T of block p = chain(p-1); on sb it also follows update-A(p-1) (stream order), which
+        // brought the columns of panel p up to date
+        cudaEvent_t ec = sv->next_event();
+        CU(cudaEventRecord(ec, st));
+        CU(cudaStreamWaitEvent(sb, ec, 0));
         int rows_below = P.big_fmax - jb;  // upper bound
         int nrowblk = std::max(1u, cdiv(rows_below, 128));
-        k_big_trsm<<<dim3(nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), 128, 0, sb>>>(D, N, bl, jb, nrowblk, 0); ++L;
-        int rem_k = P.big_kmax - jb - NB;
+        k_big_trsm<<<dim3(nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), 128, 0, sb>>>(D, N, bl, jb, nrowblk); ++L;
+        eT[p] = sv->next_event();
+        CU(cudaEventRecord(eT[p], sb));
+        const int rem_k = P.big_kmax - jb - NB;
         if (rem_k > 0) {
-          if (e_upd_prev) CU(cudaStreamWaitEvent(st, e_upd_prev, 0));   // rows of the next block, columns of this panel: updated through panel p-1
-          k_big_trsm<<<dim3(1, P.big_cnt), 128, 0, st>>>(D, N, bl, jb, 1, 1); ++L;
+          // chain(p): block p+1.  Needs trsm(p-1) (rows of block p+1 at panel p-1; its tile (p+1,p) through panel p-2 is
+          // then complete too: update-A(p-2) precedes trsm(p-1) on sb) and update-B(p-2) (tile (p+1,p+1), threshold maxima)
+          if (p >= 1) CU(cudaStreamWaitEvent(st, eT[p - 1], 0));
+          if (p >= 2 && eUB[p - 2]) CU(cudaStreamWaitEvent(st, eUB[p - 2], 0));
+          k_big_chain<<<P.big_cnt, 128, CHAIN_SMEM, st>>>(D, N, bl, jb); ++L;
           cudaEvent_t en = sv->next_event();
           CU(cudaEventRecord(en, st));
+          // update(p), tile column 0 (the columns of panels p+1, p+2) on sb: needs trsm(p) (stream order) and chain(p)
           CU(cudaStreamWaitEvent(sb, en, 0));
-          k_big_update<<<dim3(cdiv(P.big_fmax - jb - NB, TM), cdiv(rem_k, TM), P.big_cnt), 256, 0, sb>>>(D, N, bl, jb, 0); ++L;
-          e_upd_prev = sv->next_event();
-          CU(cudaEventRecord(e_upd_prev, sb));
+          // ... and the rest of update(p-1): both add to the columns of block p+2 (fixed order: deterministic)
+          if (p >= 1 && eUB[p - 1]) CU(cudaStreamWaitEvent(sb, eUB[p - 1], 0));
+          const unsigned tiles_i = cdiv(P.big_fmax - jb - NB, TM), tiles_j = cdiv(rem_k, TM);
+          k_big_update<<<dim3(tiles_i, 1, P.big_cnt), 256, 0, sb>>>(D, N, bl, jb, 0, 0); ++L;
+          if (tiles_j > 1) {
+            cudaEvent_t ea = sv->next_event();
+            CU(cudaEventRecord(ea, sb));
+            CU(cudaStreamWaitEvent(su, ea, 0));
+            k_big_update<<<dim3(tiles_i, tiles_j - 1, P.big_cnt), 256, 0, su>>>(D, N, bl, jb, 0, 1); ++L;
+            eUB[p] = sv->next_event();
+            CU(cudaEventRecord(eUB[p], su));
+          }
         }
+      }
+      {
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, sb));
+        CU(cudaStreamWaitEvent(st, e, 0));
+      }
+      {
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, su));
+        CU(cudaStreamWaitEvent(st, e, 0));
       }
       {
         cudaEvent_t e = sv->next_event();

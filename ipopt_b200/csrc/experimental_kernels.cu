@@ -350,4 +350,105 @@ __global__ void __launch_bounds__(256) k_big_schur(DevSym S, DevNum N, const int
 }
 
 
+
+// stand-alone diagonal-block kernels (superseded by k_big_chain, which fuses them with the next block's panel rows)
+// factor the NB x NB diagonal block at panel offset jb (pivoting restricted to the block).
+// ONE WARP per front, block held in registers (warp_ldlt32).
+__global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
+  __shared__ double T[33 * NB];
+  __shared__ __align__(16) double colbuf[64];
+  __shared__ double dinv_s[NB], doff_s[NB];
+  __shared__ int order[NB], pt[NB];
+  const int s = front_list[blockIdx.x];
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  if (jb >= k) return;
+  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int nb = min(NB, k - jb);
+  double* __restrict__ P = N.L + S.L_off[s];
+  const int lane = threadIdx.x;
+  // lower part, coalesced per column, through a shared tile
+  {
+    double tmp[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) tmp[j] = (j < nb && lane >= j && lane < nb) ? P[(jb + lane) + (size_t)(jb + j) * f] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) T[lane * 33 + j] = tmp[j];
+  }
+  __syncwarp();
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? T[lane * 33 + c] : T[c * 33 + lane];
+  __syncwarp();
+  const double gext = (lane < nb) ? N.colmax[c0 + jb + lane] : 0.0;
+  warp_ldlt32(a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colbuf, gext, N.counters);
+  // write the block back in pivot order: L[t2][t] = Lraw[order[t2]][t]
+  const int mine = (lane < nb) ? order[lane] : 0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (j < nb && lane < nb) {
+      double v;
+      if (lane < j) v = 0.0;
+      else if (lane == j) v = 1.0;
+      else v = T[mine * 33 + j];
+      P[(jb + lane) + (size_t)(jb + j) * f] = v;
+    }
+  }
+  if (lane < nb) {
+    N.bperm[c0 + jb + lane] = mine;
+    N.lperm[c0 + jb + lane] = jb + mine;
+    N.dinv[c0 + jb + lane] = dinv_s[lane];
+    N.doff[c0 + jb + lane] = doff_s[lane];
+    N.ptype[c0 + jb + lane] = pt[lane];
+  }
+}
+
+// 4-warp version of k_big_diag (same inputs / outputs)
+__global__ void __launch_bounds__(128) k_big_diag4(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
+  __shared__ double T[33 * NB];
+  __shared__ double colA[64], colB[64];
+  __shared__ double dinv_s[NB], doff_s[NB];
+  __shared__ int order[NB], pt[NB];
+  const int s = front_list[blockIdx.x];
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  if (jb >= k) return;
+  const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int nb = min(NB, k - jb);
+  double* __restrict__ P = N.L + S.L_off[s];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  // lower part of the block, coalesced per column, into the shared tile (8 columns per warp)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int j = 8 * w + q;
+    T[lane * 33 + j] = (j < nb && lane >= j && lane < nb) ? P[(jb + lane) + (size_t)(jb + j) * f] : 0.0;
+  }
+  __syncthreads();
+  double a[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { const int c = 8 * w + q; a[q] = (c <= lane) ? T[lane * 33 + c] : T[c * 33 + lane]; }
+  const double gext = (lane < nb) ? N.colmax[c0 + jb + lane] : 0.0;
+  __syncthreads();   // T is reused as Lraw
+  cta_ldlt32(a, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colA, colB, gext, N.counters);
+  // write the block back in pivot order: L[t2][t] = Lraw[order[t2]][t]
+  const int mine = (lane < nb) ? order[lane] : 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int j = 8 * w + q;
+    if (j < nb && lane < nb) {
+      double v;
+      if (lane < j) v = 0.0;
+      else if (lane == j) v = 1.0;
+      else v = T[mine * 33 + j];
+      P[(jb + lane) + (size_t)(jb + j) * f] = v;
+    }
+  }
+  if (w == 0 && lane < nb) {
+    N.bperm[c0 + jb + lane] = mine;
+    N.lperm[c0 + jb + lane] = jb + mine;
+    N.dinv[c0 + jb + lane] = dinv_s[lane];
+    N.doff[c0 + jb + lane] = doff_s[lane];
+    N.ptype[c0 + jb + lane] = pt[lane];
+  }
+}
+
+
 }  // namespace b200

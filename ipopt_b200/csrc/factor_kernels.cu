@@ -738,7 +738,7 @@ __global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_
   const int s = front_list[blockIdx.x];
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-  const int nb = min(2 * NB, k);   // panels 0 and 1 (panel 1's values lack panel 0's update: a one-panel-stale estimate)
+  const int nb = min(3 * NB, k);   // panels 0, 1 and 2 (a later panel's values lack the earlier panels' updates: a stale estimate)
   const double* __restrict__ P = N.L + S.L_off[s];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int j = blockIdx.y * nwarp + warp; j < nb; j += gridDim.y * nwarp) {   // one column per warp, 8 CTAs per front
@@ -750,53 +750,333 @@ __global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_
   }
 }
 
-// factor the NB x NB diagonal block at panel offset jb (pivoting restricted to the block).
-// ONE WARP per front, block held in registers (warp_ldlt32).
-__global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
-  __shared__ double T[33 * NB];
-  __shared__ __align__(16) double colbuf[64];
+// --------------------------------------------------------------------------------------------
+// The same pivoted LDL^T of a symmetric block of order f <= 32 (k = f candidates) by FOUR warps -- the diagonal blocks of
+// the big fronts are the serial chain of the factorisation, so what counts is the latency of ONE pivot step.
+//   * warp w owns the 8 columns with original index 8w .. 8w+7 for the whole factorisation; lane = row.  Columns never
+//     move, so there is no register shifting / compaction at all: the pivot ORDER is tracked logically (mypos, exactly the
+//     position arithmetic of warp_ldlt32) and replicated in every warp.
+//   * per pivot step the owner warp publishes the candidate column in shared memory (double-buffered: one CTA barrier per
+//     published column); every warp then repeats the cheap search / decision on it redundantly (identical results, no
+//     second exchange) and updates its own 8 columns: 8 DFMAs instead of 32 + 62 moves.
+// Decisions, pivot order, factors and counters are IDENTICAL to warp_ldlt32 (same comparisons on the same values; the
+// per-entry arithmetic is the same fma); tests/test_gpu_parity.py checks the factors bit for bit.
+// Output as warp_ldlt32: Lraw[i*33 + t], order[t], pt[t], dinv_s[t], doff_s[t] (written by warp 0).
+// colA / colB: 2 x 32 doubles each (shared).  All 128 threads must call this.
+// --------------------------------------------------------------------------------------------
+__device__ void cta_ldlt32(double (&a)[8], const int f, const double u, const double tiny,
+                           double* __restrict__ Lraw, int* __restrict__ order, int* __restrict__ pt,
+                           double* __restrict__ dinv_s, double* __restrict__ doff_s,
+                           double* __restrict__ colA, double* __restrict__ colB,
+                           const double gext /* lane c: max |entry| of column c in rows OUTSIDE the block */, int* counters) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int k = f;
+  int mypos = lane;
+  unsigned alive = (f >= 32) ? 0xffffffffu : ((1u << f) - 1u);
+  unsigned cand = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+  int nc = k, npass = k, t = 0, progress = 0;
+  bool forced = false;
+  int c_neg = 0, c_forced = 0, c_tiny = 0, c_2x2 = 0;
+  int my_order = 0, my_pt = 1;
+  double my_dinv = 0.0, my_doff = 0.0;
+  int par = 0;
+  auto pick = [&](int q) -> double {   // a[q], q in 0..7 dynamic (warp-uniform)
+    double v = a[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) v = (q == j) ? a[j] : v;
+    return v;
+  };
+  while (nc > 0) {
+    if (npass == 0) {
+      if (progress > 0) { npass = nc; progress = 0; }
+      else { forced = true; npass = nc; }
+    }
+    const bool me_alive = (alive >> lane) & 1u;
+    const bool me_cand = (cand >> lane) & 1u;
+    int g0 = __ffs(__ballot_sync(0xffffffffu, me_alive && mypos == 0)) - 1;
+    double* cA = colA + 32 * par;
+    double* cB = colB + 32 * par;
+    par ^= 1;
+    // ---- publish column g0, then every warp searches it ----
+    if (w == (g0 >> 3)) cA[lane] = pick(g0 & 7);
+    __syncthreads();
+    const double a0 = cA[lane];                 // A[lane][g0]
+    const double v0 = fabs(a0);
+    const float v0f = __double2float_ru(v0);
+    const float lam_in = (me_cand && lane != g0) ? v0f : -1.0f;
+    const float lamf = wredux_max(lam_in);
+    const float gamf = wredux_max((me_alive && !me_cand) ? v0f : 0.0f);
+    int r = __ffs(__ballot_sync(0xffffffffu, lam_in == lamf)) - 1;
+    double lam = 0.0;
+    if (lamf < 0.0f) r = -1;
+    else lam = fabs(cA[r]);                     // exact magnitude of the selected entry
+    const double gam = fmax((double)gamf, __shfl_sync(0xffffffffu, gext, g0));
+    const double pa0 = cA[g0];                  // A[g0][g0]
+    const double ajj = fabs(pa0);
+    const bool ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
+    int type = 0;
+    bool noise = false;
+    const double colmax_f = fmax(lam, gam);
+    double a1 = 0.0;                            // A[lane][r] when the 2x2 branch looked at column r
+    bool usedB = false;
+    if (forced) { type = 1; noise = !(fmax(ajj, colmax_f) > 1e-12); }
+    else if (lam == 0.0 || r < 0) { if (ok1) type = 1; }
+    else if (ok1 && ajj >= BK_ALPHA * lam) type = 1;
+    else {
+      // (logically) bring column r to position 1
+      const int p = __shfl_sync(0xffffffffu, mypos, r);
+      if (p > 1) { if (mypos == 1) mypos = p; else if (mypos == p) mypos = 1; }
+      if (w == (r >> 3)) cB[lane] = pick(r & 7);
+      __syncthreads();
+      usedB = true;
+      a1 = cB[lane];
+      const double v1 = fabs(a1);
+      const float v1f = __double2float_ru(v1);
+      const bool other = me_alive && lane != g0 && lane != r;
+      double sig = (double)wredux_max((me_cand && lane != r) ? v1f : 0.0f);
+      double gamr = (double)wredux_max((me_alive && !me_cand) ? v1f : 0.0f);
+      double cj = (double)wredux_max(other ? v0f : 0.0f), cr = (double)wredux_max(other ? v1f : 0.0f);
+      {
+        const double ge_r = __shfl_sync(0xffffffffu, gext, r), ge_j = __shfl_sync(0xffffffffu, gext, g0);
+        gamr = fmax(gamr, ge_r); cr = fmax(cr, ge_r); cj = fmax(cj, ge_j);
+      }
+      const double crr = cB[r];                 // A[r][r]
+      const double arr = fabs(crr);
+      if (ok1 && ajj * sig >= BK_ALPHA * lam * lam) type = 1;
+      else if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, gamr)) {
+        // 1x1 on r: swap positions 0 and 1
+        if (mypos == 0) mypos = 1; else if (mypos == 1) mypos = 0;
+        g0 = r;
+        type = 4;                               // 1x1 whose pivot column is cB
+      } else {
+        const double pb = cA[r];                // A[r][g0]
+        const double det = pa0 * crr - pb * pb, adet = fabs(det);
+        if (lam > tiny && adet > 0.0 && isfinite(adet) &&
+            (fabs(crr) * cj + fabs(pb) * cr) * u <= adet && (fabs(pa0) * cr + fabs(pb) * cj) * u <= adet)
+          type = 3;
+      }
+    }
+    if (type == 0) {
+      // park the column at position 0 behind the remaining candidates (position nc-1) and try the next one
+      if (mypos == 0) mypos = nc - 1; else if (mypos < nc) mypos -= 1;
+      --npass;
+      continue;
+    }
+    if (type == 1 || type == 4) {
+      const double* __restrict__ cP = (type == 4) ? cB : cA;     // the pivot column, indexed by row
+      double dd = cP[g0];
+      if (forced) {
+        if (noise || !(fabs(dd) > tiny)) { dd = (dd < 0.0) ? -1.5e-8 : 1.5e-8; ++c_tiny; }
+        else { dd = copysign(fmax(fabs(dd), 1e-8 * colmax_f), dd); ++c_forced; }
+      }
+      const double c0v = (type == 4) ? a1 : a0;
+      const double rinv = 1.0 / dd;
+      const double l = (me_alive && lane != g0) ? c0v * rinv : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = fma(-l, cP[8 * w + q], a[q]);   // pivot row entry of column 8w+q = A[8w+q][g0]
+      if (w == 0) {
+        Lraw[lane * 33 + t] = l;
+        if (lane == t) { my_order = g0; my_pt = 1; my_dinv = rinv; my_doff = 0.0; }
+      }
+      if (dd < 0.0) ++c_neg;
+      alive &= ~(1u << g0); cand &= ~(1u << g0);
+      mypos -= 1;
+      nc -= 1; npass = max(npass - 1, 0); t += 1;
+    } else {
+      const double pa = pa0, pb = cA[r], pc2 = cB[r];
+      const double det = pa * pc2 - pb * pb;
+      const double c1 = a0, c2v = a1;
+      const bool other = me_alive && lane != g0 && lane != r;
+      const double idet = 1.0 / det;
+      const double l1 = other ? (pc2 * c1 - pb * c2v) * idet : 0.0;
+      const double l2 = other ? (pa * c2v - pb * c1) * idet : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = fma(-l2, cB[8 * w + q], fma(-l1, cA[8 * w + q], a[q]));
+      if (w == 0) {
+        Lraw[lane * 33 + t] = l1;
+        Lraw[lane * 33 + t + 1] = l2;
+        if (lane == t) { my_order = g0; my_pt = 2; my_dinv = pc2 * idet; my_doff = -pb * idet; }
+        if (lane == t + 1) { my_order = r; my_pt = 3; my_dinv = pa * idet; my_doff = 0.0; }
+      }
+      ++c_2x2;
+      if (det < 0.0) c_neg += 1; else if (pa < 0.0) c_neg += 2;
+      alive &= ~((1u << g0) | (1u << r)); cand &= ~((1u << g0) | (1u << r));
+      mypos -= 2;
+      nc -= 2; npass = max(npass - 2, 0); t += 2;
+    }
+    (void)usedB;
+    ++progress;
+  }
+  if (w == 0) {
+    if (lane < k) { order[lane] = my_order; pt[lane] = my_pt; dinv_s[lane] = my_dinv; doff_s[lane] = my_doff; }
+    if (lane == 0) {
+      if (c_neg) atomicAdd(counters + CNT_NEG, c_neg);
+      if (c_forced) atomicAdd(counters + CNT_FORCED, c_forced);
+      if (c_tiny) atomicAdd(counters + CNT_TINY, c_tiny);
+      if (c_2x2) atomicAdd(counters + CNT_2X2, c_2x2);
+    }
+  }
+  __syncthreads();
+}
+
+// --------------------------------------------------------------------------------------------
+// THE CHAIN KERNEL of the big-front panel pipeline: everything on the critical path of one panel step, in one launch.
+// Call p (jbp = first column of panel p, or -NB for the first call) produces the pivoted LDL^T of diagonal block p+1:
+//   B. (p >= 1) the rank-32 update of panel p-1 applied to the two tiles this kernel owns: rows of block p+1 x columns of
+//      panel p, and block (p+1, p+1).  Inputs: L / W rows of block p+1 at panel p-1 (bulk k_big_trsm of panel p-1) and W
+//      rows of block p at panel p-1 (written by the previous call).  The bulk k_big_update(q) skips these tiles.
+//   C. (p >= 0) the panel rows of block p+1:  X = A_perm L_bb(p)^-T (= L D),  L = X D^-1 -> written to L / W for the bulk
+//      update; then this panel's rank-32 update of block (p+1, p+1).
+//   D. pivoted LDL^T of block (p+1, p+1) by four warps (cta_ldlt32).
+// It needs the bulk k_big_trsm of panel p-1 and the bulk k_big_update of panel p-2: the bulk stream always has a full
+// chain step of slack, so the chain (one launch per 32 pivots) is never gated by the trailing updates.
+// dynamic smem: 6 tiles of 32 x 33 doubles
+// --------------------------------------------------------------------------------------------
+#define CHAIN_TILE (NB * 33)
+#define CHAIN_SMEM (6 * CHAIN_TILE * (int)sizeof(double))
+__device__ __forceinline__ void chain_tile_update(double* __restrict__ C, const double* __restrict__ A, const double* __restrict__ B,
+                                                  bool lower_only) {
+  // C[i][j] -= sum_t A[i][t] B[j][t] on 32 x 32 row-major tiles (ld 33), 2 x 4 entries per thread (128 threads)
+  const int tid = threadIdx.x, a = tid & 15, b = tid >> 4;
+  double acc[2][4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
+#pragma unroll 8
+  for (int t = 0; t < NB; ++t) {
+    const double l0 = A[a * 33 + t], l1 = A[(a + 16) * 33 + t];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const double wv = B[(b + 8 * w) * 33 + t];
+      acc[0][w] = fma(l0, wv, acc[0][w]);
+      acc[1][w] = fma(l1, wv, acc[1][w]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int ii = a + 16 * u, jj = b + 8 * w;
+      if (!lower_only || jj <= ii) C[ii * 33 + jj] -= acc[u][w];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_big_chain(DevSym S, DevNum N, const int* __restrict__ front_list, int jbp) {
+  extern __shared__ double csm[];
+  __shared__ double colA[64], colB[64];
   __shared__ double dinv_s[NB], doff_s[NB];
   __shared__ int order[NB], pt[NB];
+  __shared__ double di[NB], dup[NB], dlo[NB];
+  __shared__ int bp[NB];
+  double* A1 = csm;                    // rows of the new block x columns of panel p
+  double* A2 = csm + CHAIN_TILE;       // the new diagonal block (lower part), later the raw L of cta_ldlt32
+  double* Lr = csm + 2 * CHAIN_TILE;   // L rows of the new block at panel p-1   (later: L rows at panel p)
+  double* WrN = csm + 3 * CHAIN_TILE;  // W rows of the new block at panel p-1   (later: W rows at panel p)
+  double* WrP = csm + 4 * CHAIN_TILE;  // W rows of block p at panel p-1
+  double* Lbb = csm + 5 * CHAIN_TILE;  // L_bb(p), pivot order, strictly lower
   const int s = front_list[blockIdx.x];
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  if (jb >= k) return;
+  const int o = jbp + NB;              // first column of the block to factor
+  if (o >= k) return;
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
-  const int nb = min(NB, k - jb);
+  const int nbn = min(NB, k - o);
+  const bool has_p = jbp >= 0, has_pp = jbp >= NB;
+  const int jbq = jbp - NB;
   double* __restrict__ P = N.L + S.L_off[s];
-  const int lane = threadIdx.x;
-  // lower part, coalesced per column, through a shared tile
-  {
-    double tmp[NB];
+  double* __restrict__ Wp = N.W + S.L_off[s];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  // ---- all global loads up front ----
 #pragma unroll
-    for (int j = 0; j < NB; ++j) tmp[j] = (j < nb && lane >= j && lane < nb) ? P[(jb + lane) + (size_t)(jb + j) * f] : 0.0;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) T[lane * 33 + j] = tmp[j];
+  for (int e8 = 0; e8 < 8; ++e8) {
+    const int e = tid + 128 * e8, ii = e & 31, jj = e >> 5;     // consecutive threads -> consecutive rows (coalesced columns)
+    const bool rin = ii < nbn;
+    A2[ii * 33 + jj] = (rin && jj < nbn && ii >= jj) ? P[(o + ii) + (size_t)(o + jj) * f] : 0.0;
+    if (has_p) {
+      A1[ii * 33 + jj] = rin ? P[(o + ii) + (size_t)(jbp + jj) * f] : 0.0;
+      Lbb[ii * 33 + jj] = (ii > jj) ? P[(jbp + ii) + (size_t)(jbp + jj) * f] : 0.0;
+    }
+    if (has_pp) {
+      Lr[ii * 33 + jj] = rin ? P[(o + ii) + (size_t)(jbq + jj) * f] : 0.0;
+      WrN[ii * 33 + jj] = rin ? Wp[(o + ii) + (size_t)(jbq + jj) * f] : 0.0;
+      WrP[ii * 33 + jj] = Wp[(jbp + ii) + (size_t)(jbq + jj) * f];
+    }
   }
-  __syncwarp();
-  double a[32];
+  if (has_p && tid < NB) {
+    const double d = N.dinv[c0 + jbp + tid], od = N.doff[c0 + jbp + tid];
+    const int ty = N.ptype[c0 + jbp + tid];
+    double om = 0.0; int tym = 1;
+    if (tid > 0) { om = N.doff[c0 + jbp + tid - 1]; tym = N.ptype[c0 + jbp + tid - 1]; }
+    di[tid] = d;
+    dup[tid] = (ty == 2) ? od : 0.0;                      // first column of a 2x2 pivot: + x[t+1] * offdiag
+    dlo[tid] = (ty == 3 && tym == 2) ? om : 0.0;           // second column:              + x[t-1] * offdiag
+    bp[tid] = N.bperm[c0 + jbp + tid];
+  }
+  const double gext = (lane < nbn) ? N.colmax[c0 + o + lane] : 0.0;
+  __syncthreads();
+  if (has_pp) {
+    // B. panel p-1's update of the two tiles
+    chain_tile_update(A1, Lr, WrP, false);
+    chain_tile_update(A2, Lr, WrN, true);
+    __syncthreads();
+  }
+  if (has_p) {
+    // C. rows of the new block at panel p (warp 0, lane = row): x = A_perm L_bb^-T, l = x D^-1
+    if (w == 0) {
+      double x[NB];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? T[lane * 33 + c] : T[c * 33 + lane];
-  __syncwarp();
-  const double gext = (lane < nb) ? N.colmax[c0 + jb + lane] : 0.0;
-  warp_ldlt32(a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colbuf, gext, N.counters);
-  // write the block back in pivot order: L[t2][t] = Lraw[order[t2]][t]
-  const int mine = (lane < nb) ? order[lane] : 0;
+      for (int t = 0; t < NB; ++t) x[t] = A1[lane * 33 + bp[t]];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if (j < nb && lane < nb) {
+      for (int t = 0; t < NB - 1; ++t) {
+        const double xt = x[t];
+#pragma unroll
+        for (int q = t + 1; q < NB; ++q) x[q] = fma(-xt, Lbb[q * 33 + t], x[q]);
+      }
+      const double lim = 1.0 / N.u;
+      double lmax = 0.0;
+#pragma unroll
+      for (int t = 0; t < NB; ++t) {
+        double v = x[t] * di[t];
+        if (t + 1 < NB) v = fma(x[t + 1], dup[t], v);
+        if (t > 0) v = fma(x[t - 1], dlo[t], v);
+        lmax = fmax(lmax, fabs(v));
+        Lr[lane * 33 + t] = v;
+        WrN[lane * 33 + t] = x[t];
+        if (lane < nbn) {
+          P[(o + lane) + (size_t)(jbp + t) * f] = v;
+          Wp[(o + lane) + (size_t)(jbp + t) * f] = x[t];
+        }
+      }
+      if (lane < nbn && lmax > lim) atomicAdd(N.counters + CNT_GROWTH, 1);
+    }
+    __syncthreads();
+    chain_tile_update(A2, Lr, WrN, true);     // this panel's update of the new diagonal block
+    __syncthreads();
+  }
+  // D. pivoted LDL^T of the new diagonal block
+  double a[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { const int c = 8 * w + q; a[q] = (c <= lane) ? A2[lane * 33 + c] : A2[c * 33 + lane]; }
+  __syncthreads();   // A2 is reused as the raw L output
+  cta_ldlt32(a, nbn, N.u, N.tiny, A2, order, pt, dinv_s, doff_s, colA, colB, gext, N.counters);
+  const int mine = (lane < nbn) ? order[lane] : 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int j = 8 * w + q;
+    if (j < nbn && lane < nbn) {
       double v;
       if (lane < j) v = 0.0;
       else if (lane == j) v = 1.0;
-      else v = T[mine * 33 + j];
-      P[(jb + lane) + (size_t)(jb + j) * f] = v;
+      else v = A2[mine * 33 + j];
+      P[(o + lane) + (size_t)(o + j) * f] = v;
     }
   }
-  if (lane < nb) {
-    N.bperm[c0 + jb + lane] = mine;
-    N.lperm[c0 + jb + lane] = jb + mine;
-    N.dinv[c0 + jb + lane] = dinv_s[lane];
-    N.doff[c0 + jb + lane] = doff_s[lane];
-    N.ptype[c0 + jb + lane] = pt[lane];
+  if (w == 0 && lane < nbn) {
+    N.bperm[c0 + o + lane] = mine;
+    N.lperm[c0 + o + lane] = o + mine;
+    N.dinv[c0 + o + lane] = dinv_s[lane];
+    N.doff[c0 + o + lane] = doff_s[lane];
+    N.ptype[c0 + o + lane] = pt[lane];
   }
 }
 
@@ -807,13 +1087,11 @@ __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* 
 // columns per CTA.
 #define TRSM_LD 34          // even leading dimension: column t of the block starts 16-byte aligned
 #define TRSM_SWAP_COLS 32   // columns per row-swap CTA (4 warps x 8)
-// mode 1 ("next", on the CHAIN stream): ONE CTA per front handles only the rows of the NEXT diagonal block (row0 .. row0+31)
-//   and applies this panel's rank-nb update to that 32x32 block -- all the next k_big_diag depends on;
-// mode 0 (bulk stream): every other row below the block (+ the row-interchange CTAs).
+// The rows of the NEXT diagonal block (row0 .. row0+31) belong to the chain kernel (k_big_chain); this (bulk) kernel does
+// every other row below the block.
 __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
-                                                  int nrowblk, int mode) {
+                                                  int nrowblk) {
   __shared__ __align__(16) double Lb[NB * TRSM_LD];
-  __shared__ double Ln[NB * 33], Wn[NB * 33];   // CTA 0: L / W rows of the next diagonal block
   __shared__ double di[NB], dup[NB], dlo[NB];
   __shared__ int bp[NB];
   const int s = front_list[blockIdx.y];
@@ -825,7 +1103,6 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
   double* P = N.L + S.L_off[s];
   const int tid = threadIdx.x;
   const int nxt = max(0, min(NB, k - row0));   // rows of the next diagonal block (pivot rows right below this block)
-  if (mode == 1 && nxt == 0) return;
   if ((int)blockIdx.x >= nrowblk) {
     // ---- left part: rows jb..jb+nb of columns [0, jb) get the block permutation ----
     const int lane = tid & 31, warp = tid >> 5;
@@ -846,10 +1123,10 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
     }
     return;
   }
-  if (mode == 0 && (long long)blockIdx.x * blockDim.x >= f - row0 - nxt) return;
+  if ((long long)blockIdx.x * blockDim.x >= f - row0 - nxt) return;
   double* Wp = N.W + S.L_off[s];
-  const int i = (mode == 1) ? row0 + tid : row0 + nxt + blockIdx.x * blockDim.x + tid;
-  const bool active = (mode == 1) ? (tid < nxt) : (i < f);
+  const int i = row0 + nxt + blockIdx.x * blockDim.x + tid;
+  const bool active = i < f;
   // issue all global loads up front: the diagonal block, its D, and this thread's row (columns in pivot order)
   {
     double lb[NB * NB / 128];
@@ -877,9 +1154,6 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
     }
   }
   __syncthreads();
-  // CTA 0 owns the rows of the NEXT panel's diagonal block: it also applies this panel's rank-32 update to that
-  // 32x32 block (the bulk trailing update skips it), so the next k_big_diag can start right after this kernel.
-  const int nb2 = (mode == 1) ? nxt : 0;
   double x[NB];
 #pragma unroll
   for (int t = 0; t < NB; ++t) x[t] = (active && t < nb) ? P[i + (size_t)(jb + bp[t]) * f] : 0.0;
@@ -911,37 +1185,6 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
     for (int t = 0; t < NB; ++t)
       if (t < nb) { Wp[i + (size_t)(jb + t) * f] = x[t]; P[i + (size_t)(jb + t) * f] = l[t]; }
   }
-  if (nb2 > 0) {
-    if (tid < nb2) {
-#pragma unroll
-      for (int t = 0; t < NB; ++t) { Ln[tid * 33 + t] = l[t]; Wn[tid * 33 + t] = x[t]; }
-    }
-    __syncthreads();
-    // 32x32 block update, 2x4 entries per thread: rows a, a+16; columns b, b+8, b+16, b+24
-    const int a = tid & 15, b = tid >> 4;
-    double acc[2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-      for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
-#pragma unroll 8
-    for (int t = 0; t < NB; ++t) {
-      const double l0 = Ln[a * 33 + t], l1 = Ln[(a + 16) * 33 + t];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const double wv = Wn[(b + 8 * w) * 33 + t];
-        acc[0][w] = fma(l0, wv, acc[0][w]);
-        acc[1][w] = fma(l1, wv, acc[1][w]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const int ii = a + 16 * u, jj = b + 8 * w;
-        if (ii < nb2 && jj <= ii) P[(row0 + ii) + (size_t)(row0 + jj) * f] -= acc[u][w];
-      }
-  }
   if (active && lmax > lim) atomicAdd(N.counters + CNT_GROWTH, 1);
 }
 
@@ -955,8 +1198,10 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
 // with_cb != 0: the same launch also applies the panel's rank-nb update to the contribution block (columns >= k of the
 // trailing matrix live in N.CB), so the Schur complement is complete when the last panel is done and rides in the
 // shadow of the diag/trsm chain instead of a separate GEMM at the end of the level.
+// jt_off: first tile column of this launch (the update of a panel is issued as tile column 0 -- the columns the next
+// k_big_trsm reads -- and then the rest).
 __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
-                                                    int with_cb) {
+                                                    int with_cb, int jt_off) {
   __shared__ double As[NB][TM + 1];
   __shared__ double Bs[NB][TM + 1];
   const int s = front_list[blockIdx.z];
@@ -970,7 +1215,7 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
   const int Nn = with_cb ? M : Nk;            // columns covered by this launch
   // with_cb == 2: contribution-block columns only (tile grid anchored at the 64-aligned column below k)
   const int jbase = (with_cb == 2) ? (Nk / TM) * TM : 0;
-  const int i0 = jbase + blockIdx.x * TM, j0 = jbase + blockIdx.y * TM;
+  const int i0 = jbase + blockIdx.x * TM, j0 = jbase + ((int)blockIdx.y + jt_off) * TM;
   if (i0 >= M || j0 >= Nn || i0 + TM - 1 < j0) return;
   const int jlo = (with_cb == 2) ? Nk : 0;    // first column this launch owns
   const long long ld = f;
@@ -1024,15 +1269,15 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
     for (int q = 0; q < 4; ++q) {
       const int gi = i0 + tx + 16 * q;
       if (gi < M && gj < Nn && gi >= gj && gj >= jlo) {
-        if (gi < min(NB, Nk) && gj < NB) continue;   // next diagonal block: updated by k_big_trsm (a partial last panel has < 32 columns)
+        if (gi < min(2 * NB, Nk) && gj < 2 * NB) continue;   // the tiles the chain kernel owns: blocks (p+1,p+1), (p+2,p+1), (p+2,p+2)
         if (gj < Nk) C[gi + (long long)gj * ld] = c[q][p];
         else CBp[(gi - Nk) + (long long)(gj - Nk) * r] = c[q][p];
-        if (gi >= 2 * NB) m = fmaxf(m, __double2float_ru(fabs(c[q][p])));
+        if (gi >= 3 * NB) m = fmaxf(m, __double2float_ru(fabs(c[q][p])));
       }
     }
-    // columns [NB, 2NB) of the trailing matrix are the panel AFTER next: the next panel's chain kernels run
-    // concurrently with this update, so they use the maxima recorded one panel earlier.
-    if (j0 == 0 && p >= 2 && with_cb != 2) {   // (warp-uniform) columns 32..63 of the first tile column
+    // columns [2NB, 3NB) of the trailing matrix are the diagonal block TWO chain steps ahead: the chain runs up to two
+    // panels ahead of this update, so a block's threshold maxima are the ones recorded two panels earlier.
+    if (j0 == TM && p < 2 && with_cb != 2) {   // (warp-uniform) columns 64..95 = the first 32 columns of the second tile column
       const float m_lo = wredux_max((lane < 16) ? m : 0.0f), m_hi = wredux_max((lane >= 16) ? m : 0.0f);
       if ((lane == 0 || lane == 16) && gj < Nk) {
         const float mm = (lane == 0) ? m_lo : m_hi;

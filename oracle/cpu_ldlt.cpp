@@ -30,6 +30,14 @@
 #include <omp.h>
 #endif
 
+// BLAS-3 contribution-block update (ORACLE_BLAS3=1; bench.py's CPU-baseline legs): dgemm of the host BLAS the reference
+// library itself is linked against (OpenBLAS, see oracle/refhost/Makefile), so the CPU column is not handicapped by
+// rank-1 loops on the separator fronts.  Off by default: the parity fixtures were produced with the plain loops.
+extern "C" void dgemm_(const char*, const char*, const int*, const int*, const int*, const double*, const double*, const int*,
+                       const double*, const int*, const double*, double*, const int*);
+extern "C" void openblas_set_num_threads(int);
+static const bool g_blas3 = getenv("ORACLE_BLAS3") && atoi(getenv("ORACLE_BLAS3")) != 0;
+
 extern "C" int METIS_NodeND(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* options,
                             int64_t* perm, int64_t* iperm);
 
@@ -402,7 +410,11 @@ int factor_front(std::vector<double>& F, int f, int p, double u, std::vector<int
     ++progress;
   }
   // deferred update of the contribution block: column m, pivots in elimination order
-  if (q > 0 && npiv > 0) {
+  if (g_blas3 && q > 0 && npiv > 0 && (int64_t)q * q * npiv > 200000) {
+    // C(q x q, ld f) -= L21 (q x npiv, ld f) * Wcb^T  (Wcb is npiv rows of q: column-major q x npiv with ld q)
+    const double one = 1.0, mone = -1.0;
+    dgemm_("N", "T", &q, &q, &npiv, &mone, &F[p], &f, Wcb.data(), &q, &one, &F[(size_t)p * f + p], &f);
+  } else if (q > 0 && npiv > 0) {
 #pragma omp parallel for schedule(dynamic, 4) if ((int64_t)q * q * npiv > 2000000)
     for (int m = p; m < f; ++m) {
       double* col = &F[(size_t)m * f];
@@ -536,6 +548,7 @@ int factor(Oracle& O) {
   for (int l = 0; l < nlev; ++l) {
     const double tl0 = wall();
     const std::vector<int>& fl = by_level[l];
+    if (g_blas3) openblas_set_num_threads((nthreads > 1 && (int)fl.size() >= std::max(2, nthreads / 4)) ? 1 : nthreads);
     if (nthreads > 1 && (int)fl.size() >= std::max(2, nthreads / 4)) {
 #pragma omp parallel for schedule(dynamic, 1)
       for (int q = 0; q < (int)fl.size(); ++q) {

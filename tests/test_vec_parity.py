@@ -165,12 +165,38 @@ def test_v5_add_two_vectors(ctx, n):
                             all_dense = (ky == "d" or c == 0.0) and (k1 == "d" or a == 0.0) and (k2 == "d" or b == 0.0)
                             if n == 0:
                                 continue
-                            if all_dense or y.h:
+                            if a == 0.0 and b == 1.0 and c == 1.0 and ky == "d" and k2 == "d":
+                                # REFERENCE DEFECT, not reproduced: IpDenseVector.cpp:1027-1033 wraps the daxpy of this case
+                                # in a `for i < Dim()` loop, so the reference computes y + Dim()*v2 (in Dim() roundings and
+                                # O(n^2) time).  The kernel implements the documented operation y = v2 + y; see
+                                # test_v5_reference_defect_documented.
+                                continue
+                            if all_dense and c == 1.0 and (a == 0.0 or b == 0.0) and not (a == 0.0 and b == 0.0):
+                                # the reference delegates these to BLAS daxpy (IpDenseVector.cpp:965-1072): FMA or not is
+                                # the BLAS build's choice -> one rounding of slack
+                                got, ref = yd.ExpandedValues(), y.expanded()
+                                mag = np.abs(ref) + np.abs(a * v1.expanded()) + np.abs(b * v2.expanded())
+                                assert not yd.IsHomogeneous() and np.all(np.abs(got - ref) <= 2.3e-16 * mag)
+                            elif all_dense or y.h:
                                 same_state(yd, y)
                             else:
                                 mag = np.abs(c * 1.0) + np.abs(a * v1.expanded()) + np.abs(b * v2.expanded()) + np.abs(y.expanded())
                                 assert yd.IsHomogeneous() == bool(y.h)
                                 assert np.all(np.abs(yd.ExpandedValues() - y.expanded()) <= 1e-15 * (mag + 1.0))
+
+
+def test_v5_reference_defect_documented(ctx):
+    """AddTwoVectors(0, v1, 1, v2, 1) on dense vectors: the reference (IpDenseVector.cpp:1027-1033) runs its daxpy inside a
+    loop over Dim() and returns y + Dim()*v2; the kernel returns y + v2 (the documented semantics, IpVector.hpp AddTwoVectors:
+    "y = a*v1 + b*v2 + c*y").  This test pins BOTH facts so the deviation is explicit."""
+    n = 5
+    y0, v2 = np.arange(1.0, n + 1), np.array([0.5, -1.0, 2.0, 0.25, 3.0])
+    y = R.HostVec(n, values=y0.copy()); h2 = R.HostVec(n, values=v2); h1 = R.HostVec(n, values=np.zeros(n))
+    R.op("add_two_vectors", y, x1=h1, x2=h2, a=0.0, b=1.0, c=1.0)
+    assert np.array_equal(y.expanded(), y0 + n * v2)            # what the reference does
+    yd = dev(ctx, R.HostVec(n, values=y0.copy()))
+    yd.AddTwoVectors(0.0, dev(ctx, h1), 1.0, dev(ctx, h2), 1.0)
+    assert np.array_equal(yd.ExpandedValues(), y0 + v2)         # what the kernel does
 
 
 @pytest.mark.parametrize("n", SIZES)
