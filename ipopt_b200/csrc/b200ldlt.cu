@@ -93,11 +93,15 @@ struct DebugSwitches {
   bool factor_sections = false;   // B200_FACTOR_SECTIONS=1 (with use_graph=0): timed section marks
   bool one_stream = false;        // B200_ONE_STREAM=1: big-front pipeline on a single stream
   bool solve_timeline = false;    // B200_SOLVE_TIMELINE=1: per-task %globaltimer log of the top solve kernel
+  bool cb_at_end = false;         // B200_CB_AT_END=1: Schur complements as one GEMM per level (k_big_schur84) instead of per-panel updates
+  bool factor_timeline = false;   // B200_FACTOR_TIMELINE=1: %globaltimer records of the factorisation kernels (b200ldlt_dump_factor_timeline)
   std::vector<int> buckets;       // B200_BUCKETS=a,b,c: soft split points of the shared-memory front classes
   void read() {
     factor_sections = getenv("B200_FACTOR_SECTIONS") != nullptr;
     one_stream = getenv("B200_ONE_STREAM") != nullptr;
     solve_timeline = getenv("B200_SOLVE_TIMELINE") != nullptr;
+    factor_timeline = getenv("B200_FACTOR_TIMELINE") != nullptr;
+    cb_at_end = getenv("B200_CB_AT_END") != nullptr;
     if (const char* e = getenv("B200_BUCKETS"))
       for (const char* p = e; *p;) { buckets.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
   }
@@ -110,7 +114,8 @@ struct Solver {
   int dev = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;      // bulk (trsm / trailing update) stream of the big-front pipeline
-  cudaStream_t stream3 = nullptr;      // contribution-block updates of the big fronts (trail behind the chain)
+  cudaStream_t stream3 = nullptr;      // explicit L11 inverses of a level's big fronts (trail behind the chain)
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // the shared-memory front classes of a level run side by side
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   bool own_stream = false;
@@ -156,12 +161,13 @@ struct Solver {
   DevBuf<int> d_done_f, d_done_b, d_bflag_f, d_bflag_b, d_bcnt, d_bcnt_b, d_boff;
   DevBuf<long long> d_bigv_off;
   DevBuf<double> d_bigv, d_bigy;
-  DevBuf<unsigned long long> d_ticket, d_tlog;
+  DevBuf<unsigned long long> d_ticket, d_tlog, d_flog;
   DevBuf<double> d_linv;
   DevBuf<long long> d_linv_off, d_gmap_off;
   DevBuf<FrontDesc> d_fdesc;
   DevBuf<int> d_gmap;
   LinvPlan linv_plan;               // explicit inverses of the big fronts' pivot blocks (all fronts)
+  std::vector<std::unique_ptr<LinvPlan>> linv_level;   // the same work, split by tree level (issued behind each level's chain)
   std::vector<SolveTask> h_tasks;   // fwd then bwd (debug timeline)
   SolvePlan splan;                  // all fronts
   int solve_epoch = 0, df_grid = 0;
@@ -195,6 +201,7 @@ struct Solver {
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (stream2) cudaStreamDestroy(stream2);
     if (stream3) cudaStreamDestroy(stream3);
+    for (auto& q : side) if (q) cudaStreamDestroy(q);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
   // debug (B200_FACTOR_SECTIONS=1 with use_graph=0): timed section marks of the last factorisation
@@ -363,7 +370,7 @@ static int build_linv_plan(Solver* sv, const Symbolic& S, const std::vector<char
   return B200LDLT_SUCCESS;
 }
 
-static int enqueue_linv(Solver* sv, const LinvPlan& LP);
+static int enqueue_linv(Solver* sv, const LinvPlan& LP, cudaStream_t st);
 
 // Triangular-solve plan of the fronts in take[] (see solve_dataflow.cu).
 //  * Subtrees: maximal subtrees whose fronts are all taken, of order <= DF_MIDMAX, and whose whole working set (SubLayout)
@@ -655,6 +662,14 @@ static int run_analysis(Solver* sv, const double* vals) {
   N.L = sv->d_L.p; N.W = sv->d_W.p; N.CB = sv->d_CB.p; N.uval = sv->d_uval.p;
   N.dinv = sv->d_dinv.p; N.doff = sv->d_doff.p; N.ptype = sv->d_ptype.p;
   N.lperm = sv->d_lperm.p; N.bperm = sv->d_bperm.p; N.counters = sv->d_counters.p; N.colmax = sv->d_colmax.p;
+  N.flog = nullptr;
+  if (sv->dbg.factor_timeline) {
+    const unsigned long long cap = 1ull << 16;
+    CU(sv->d_flog.alloc(2 + cap * FLOG_WORDS));
+    const unsigned long long hdr[2] = {0ull, cap};
+    CU(cudaMemcpy(sv->d_flog.p, hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+    N.flog = sv->d_flog.p;
+  }
 
   // inverse row maps of the children of the (factorisation-)big fronts, for the one-launch extend-add
   {
@@ -684,7 +699,7 @@ static int run_analysis(Solver* sv, const double* vals) {
   CU(sv->d_front_list.upload(fl, st));
   { int rc2 = upload_schur_lists(sv, sv->schur, st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
   CU(cudaFuncSetAttribute(k_tc_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(k_big_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
+  CU(cudaFuncSetAttribute(k_big_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
   CU(cudaFuncSetAttribute(k_front_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CU(cudaFuncSetAttribute(k_front_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -717,6 +732,14 @@ static int run_analysis(Solver* sv, const double* vals) {
       std::vector<char> take(S.nsn, 1);
       int rc2 = build_linv_plan(sv, S, take, sv->linv_plan, st);
       if (rc2 != B200LDLT_SUCCESS) return rc2;
+      sv->linv_level.clear();
+      for (int l = 0; l < S.nlevels; ++l) {
+        std::vector<char> tl(S.nsn, 0);
+        bool any = false;
+        for (int q = 0; q < S.nsn; ++q) if (S.sn_level[q] == l && S.f(q) > kSolveMidMax) { tl[q] = 1; any = true; }
+        sv->linv_level.emplace_back(new LinvPlan());
+        if (any) { rc2 = build_linv_plan(sv, S, tl, *sv->linv_level.back(), st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
+      }
     }
     CU(sv->d_boff.upload(boff, st));
     CU(sv->d_bigv_off.upload(bigv_off, st));
@@ -799,6 +822,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
   sv->ev_next = 0;
   CU(cudaMemsetAsync(sv->d_counters.p, 0, CNT_N * sizeof(int), st));
   CU(cudaMemsetAsync(sv->d_colmax.p, 0, (size_t)n * sizeof(double), st));
+  if (sv->DN.flog) CU(cudaMemsetAsync(sv->DN.flog, 0, sizeof(unsigned long long), st));
   k_sum_dups<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_useg_ptr.p, sv->d_useg_src.p, sv->d_vals.p, sv->d_uval.p); ++L;
   k_fill<<<cdiv(n, 256), 256, 0, st>>>(n, sv->d_scale.p, 1.0); ++L;
   for (int sw = 0; sw < sv->opt.scaling; ++sw) {
@@ -821,111 +845,116 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       const LevelPlan& P = plan[l];
       if (!P.big_cnt) continue;
       k_big_zero<<<dim3(std::min<unsigned>(cdiv(P.big_zero_max, 1024), 592), P.big_cnt), 256, 0, sz>>>(D, N, fl + P.big_off); ++L;
+      // ... and the original entries scattered in (they do not depend on the children either)
+      k_big_assemble<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_entmax, 256), 64)), P.big_cnt), 256, 0, sz>>>(D, N, fl + P.big_off); ++L;
     }
     sv->ev_zero = sv->next_event();
     CU(cudaEventRecord(sv->ev_zero, sz));
   }
-  bool zero_waited = false;
+  bool zero_waited = false, linv_forked = false;
   sv->mark("prologue", -1);
   for (int l = 0; l < S.nlevels; ++l) {
     const LevelPlan& P = plan[l];
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
       if (!zero_waited) { CU(cudaStreamWaitEvent(st, sv->ev_zero, 0)); zero_waited = true; }
-      k_big_assemble<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_entmax, 256), 64)), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
       if (P.big_chmax > 0) {
         k_big_extend_all<<<dim3(cdiv(P.big_fmax, 8), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
       }
     }
     if (P.big_cnt) sv->mark("big-assemble", l);
-    for (const auto& bk : P.small) {
-      if (bk.fmax <= 32) {  // one warp per front (registers), 4 fronts per CTA
-        k_front_warp<<<cdiv(bk.cnt, 4), 128, 4 * XS_SMEM_PER_WARP, st>>>(D, N, fl + bk.off, bk.cnt); ++L;
-      } else {
-        k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, st>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
+    {
+      // the front classes of a level are independent: issue them side by side (forked from / joined to the main stream)
+      const bool fork = !sv->dbg.one_stream && (P.small.size() + (P.big_cnt ? 1 : 0)) > 1;
+      cudaEvent_t e_lvl = nullptr;
+      if (fork) { e_lvl = sv->next_event(); CU(cudaEventRecord(e_lvl, st)); }
+      int slot = P.big_cnt ? 1 : 0;          // slot 0 = the main stream (busy with the big fronts' assembly if there are any)
+      unsigned used = 0;
+      for (const auto& bk : P.small) {
+        cudaStream_t sq = st;
+        if (fork && slot > 0) {
+          const int q = (slot - 1) % 4;
+          sq = sv->side[q];
+          if (!(used & (1u << q))) { CU(cudaStreamWaitEvent(sq, e_lvl, 0)); used |= 1u << q; }
+        }
+        ++slot;
+        if (fork && slot > 4) slot = 0;
+        if (bk.fmax <= 32) {  // one warp per front (registers), 4 fronts per CTA
+          k_front_warp<<<cdiv(bk.cnt, 4), 128, 4 * XS_SMEM_PER_WARP, sq>>>(D, N, fl + bk.off, bk.cnt); ++L;
+        } else {
+          k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, sq>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
+        }
+      }
+      for (int q = 0; q < 4; ++q) if (used & (1u << q)) {
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, sv->side[q]));
+        CU(cudaStreamWaitEvent(st, e, 0));
       }
     }
     sv->mark("small-fronts", l);
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
-      k_big_colmax0<<<dim3(P.big_cnt, 8), 256, 0, st>>>(D, N, bl); ++L;
-      // Panel pipeline on two streams (both inside the captured graph): the CHAIN  diag(p) -> trsm(p) -> diag(p+1)
-      // is the critical path; the trailing update of panel p runs on the bulk stream concurrently with diag(p+1),
-      // which applies panel p's rank-32 update to its own 32x32 block itself.
-      cudaStream_t sb = sv->dbg.one_stream ? st : sv->stream2;
-      {
-        cudaEvent_t e = sv->next_event();
-        CU(cudaEventRecord(e, st));
-        CU(cudaStreamWaitEvent(sb, e, 0));
+      if (P.big_chmax <= 0) {   // (with children the extend-add kernel has recorded the column maxima of the first panels)
+        k_big_colmax0<<<dim3(P.big_cnt, 8), 256, 0, st>>>(D, N, bl); ++L;
       }
-      // Panel pipeline on three streams (all inside the captured graph):
-      //   chain  (st): k_big_chain(p) = [update of panel p-1 on its two tiles] + panel rows of block p+1 + LDL^T of block p+1
-      //                 needs trsm(p-1) and update(p-2)
-      //   trsm   (sb): k_big_trsm(p)   needs the LDL^T of block p = chain(p-1)
-      //   update (su): k_big_update(p) needs trsm(p) and chain(p) (the panel rows of block p+1)
-      // so the trailing work of a panel has a full chain step of slack and the chain is one launch per 32 pivots.
-      cudaStream_t su = sv->dbg.one_stream ? st : sv->stream3;
+      // Panel pipeline on two streams (both inside the captured graph):
+      //   chain  (st): k_big_panel(p) = LDL^T of block p+1 (one CTA) + the panel rows below it, which apply the update of
+      //                panel p-1 to their own columns first (left-looking by one panel).  Needs k_big_panel(p-1) (stream
+      //                order) and k_big_update(p-2).
+      //   bulk   (su): k_big_update(p) = rank-32 update of the columns from panel p+2 on.  Needs k_big_panel(p).
+      // So the critical path is ONE launch per 32 pivots and the bulk update of a panel has a whole chain step of slack.
+      cudaStream_t su = sv->dbg.one_stream ? st : sv->stream2;
       {
         cudaEvent_t e = sv->next_event();
         CU(cudaEventRecord(e, st));
         CU(cudaStreamWaitEvent(su, e, 0));
       }
       const int npan = (P.big_kmax + NB - 1) / NB;
-      std::vector<cudaEvent_t> eT(npan + 2, nullptr), eUB(npan + 2, nullptr);
-      k_big_chain<<<P.big_cnt, 128, CHAIN_SMEM, st>>>(D, N, bl, -NB); ++L;     // LDL^T of block 0
+      std::vector<cudaEvent_t> eUB(npan + 2, nullptr);
+      // contribution blocks: one rank-32 update per panel, behind that panel's bulk update on the same stream (a second
+      // dependent stream per panel measurably delays the launch of the next chain step).  Only when every front of the level
+      // takes the DFMA route; with tensor-core Schur fronts in the level the complements are formed at the end of the level.
+      const bool cb_panel = !sv->dbg.cb_at_end && !sv->dbg.one_stream && P.tc_t_cnt == 0 && P.df_cnt > 0;
+      k_big_panel<<<dim3(1, P.big_cnt), 128, CHAIN_SMEM, st>>>(D, N, bl, -NB, 0); ++L;     // LDL^T of block 0
       for (int p = 0; p < npan; ++p) {
         const int jb = p * NB;
-        // trsm(p): needs the LDL^T of block p = chain(p-1); on sb it also follows update-A(p-1) (stream order), which
-        // brought the columns of panel p up to date
-        cudaEvent_t ec = sv->next_event();
-        CU(cudaEventRecord(ec, st));
-        CU(cudaStreamWaitEvent(sb, ec, 0));
-        int rows_below = P.big_fmax - jb;  // upper bound
-        int nrowblk = std::max(1u, cdiv(rows_below, 128));
-        k_big_trsm<<<dim3(nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), 128, 0, sb>>>(D, N, bl, jb, nrowblk); ++L;
-        eT[p] = sv->next_event();
-        CU(cudaEventRecord(eT[p], sb));
-        const int rem_k = P.big_kmax - jb - NB;
-        if (rem_k > 0) {
-          // chain(p): block p+1.  Needs trsm(p-1) (rows of block p+1 at panel p-1; its tile (p+1,p) through panel p-2 is
-          // then complete too: update-A(p-2) precedes trsm(p-1) on sb) and update-B(p-2) (tile (p+1,p+1), threshold maxima)
-          if (p >= 1) CU(cudaStreamWaitEvent(st, eT[p - 1], 0));
-          if (p >= 2 && eUB[p - 2]) CU(cudaStreamWaitEvent(st, eUB[p - 2], 0));
-          k_big_chain<<<P.big_cnt, 128, CHAIN_SMEM, st>>>(D, N, bl, jb); ++L;
+        if (p >= 2 && eUB[p - 2]) CU(cudaStreamWaitEvent(st, eUB[p - 2], 0));
+        const int rows_below = P.big_fmax - jb;  // upper bound
+        const int nrowblk = std::max(1u, cdiv(rows_below, 128));
+        k_big_panel<<<dim3(1 + nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), 128, CHAIN_SMEM, st>>>(D, N, bl, jb, nrowblk); ++L;
+        const int rem_k = P.big_kmax - jb - 2 * NB;
+        if (rem_k > 0 || cb_panel) {
           cudaEvent_t en = sv->next_event();
           CU(cudaEventRecord(en, st));
-          // update(p), tile column 0 (the columns of panels p+1, p+2) on sb: needs trsm(p) (stream order) and chain(p)
-          CU(cudaStreamWaitEvent(sb, en, 0));
-          // ... and the rest of update(p-1): both add to the columns of block p+2 (fixed order: deterministic)
-          if (p >= 1 && eUB[p - 1]) CU(cudaStreamWaitEvent(sb, eUB[p - 1], 0));
-          const unsigned tiles_i = cdiv(P.big_fmax - jb - NB, TM), tiles_j = cdiv(rem_k, TM);
-          k_big_update<<<dim3(tiles_i, 1, P.big_cnt), 256, 0, sb>>>(D, N, bl, jb, 0, 0); ++L;
-          if (tiles_j > 1) {
-            cudaEvent_t ea = sv->next_event();
-            CU(cudaEventRecord(ea, sb));
-            CU(cudaStreamWaitEvent(su, ea, 0));
-            k_big_update<<<dim3(tiles_i, tiles_j - 1, P.big_cnt), 256, 0, su>>>(D, N, bl, jb, 0, 1); ++L;
-            eUB[p] = sv->next_event();
-            CU(cudaEventRecord(eUB[p], su));
-          }
+          CU(cudaStreamWaitEvent(su, en, 0));
         }
-      }
-      {
-        cudaEvent_t e = sv->next_event();
-        CU(cudaEventRecord(e, sb));
-        CU(cudaStreamWaitEvent(st, e, 0));
+        if (rem_k > 0) {
+          const unsigned tiles_i = cdiv(P.big_fmax - jb - 2 * NB, TM), tiles_j = cdiv(rem_k, TM);
+          k_big_update<<<dim3(tiles_i, tiles_j, P.big_cnt), 256, 0, su>>>(D, N, bl, jb); ++L;
+          eUB[p] = sv->next_event();
+          CU(cudaEventRecord(eUB[p], su));
+        }
+        if (cb_panel) {
+          k_big_update_cb<<<dim3(cdiv(P.df_rmax, TM), cdiv(P.df_rmax, TM), P.big_cnt), 256, 0, su>>>(D, N, bl, jb); ++L;
+        }
       }
       {
         cudaEvent_t e = sv->next_event();
         CU(cudaEventRecord(e, su));
         CU(cudaStreamWaitEvent(st, e, 0));
       }
-      {
-        cudaEvent_t e = sv->next_event();
-        CU(cudaEventRecord(e, sb));
-        CU(cudaStreamWaitEvent(st, e, 0));
-      }
       sv->mark("big-chain", l);
+      if (!linv_p && !sv->dbg.one_stream && l < (int)sv->linv_level.size() && sv->linv_level[l]->ndiag > 0) {
+        // explicit L11 inverses of this level's fronts: behind the chain on their own stream, concurrent with the Schur
+        // complements and the levels above (they only read the finished pivot blocks; k_linv_gemm<1> uses the top k x k
+        // part of W as scratch, which nothing reads after the chain)
+        cudaEvent_t e = sv->next_event();
+        CU(cudaEventRecord(e, st));
+        CU(cudaStreamWaitEvent(sv->stream3, e, 0));
+        int rc = enqueue_linv(sv, *sv->linv_level[l], sv->stream3);
+        if (rc != B200LDLT_SUCCESS) return rc;
+        linv_forked = true;
+      }
       // Schur complements CB -= L21 (L21 D)^T: tensor cores (Ozaki int8 digits, schur_tc.cu) for the large fronts,
       // register-blocked DFMA tiles for the rest
       if (P.tc_t_cnt > 0) {
@@ -934,14 +963,18 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         k_tc_slice<<<dim3(cdiv(P.tc_rmax, 8), P.tc_f_cnt), 256, 0, st>>>(D, N, tf, 1, sv->d_tc_dig.p, sv->d_tc_exp.p); ++L;
         k_tc_schur<<<P.tc_t_cnt, 192, TC_SMEM_BYTES, st>>>(D, N, tf, SL.d_t.p + P.tc_t_off, sv->d_tc_dig.p, sv->d_tc_exp.p); ++L;
       }
-      if (P.df_cnt > 0) {
+      if (!cb_panel && P.df_cnt > 0) {
         k_big_schur84<<<dim3(cdiv(P.df_rmax, TM), cdiv(P.df_rmax, TM), P.df_cnt), 128, 0, st>>>(D, N, SL.d_dfl.p + P.df_off); ++L;
       }
     }
   }
   sv->mark("big-schur(last)", S.nlevels);
-  {
-    int rc = enqueue_linv(sv, linv_p ? *linv_p : sv->linv_plan);
+  if (linv_forked) {
+    cudaEvent_t e = sv->next_event();
+    CU(cudaEventRecord(e, sv->stream3));
+    CU(cudaStreamWaitEvent(st, e, 0));
+  } else {
+    int rc = enqueue_linv(sv, linv_p ? *linv_p : sv->linv_plan, st);
     if (rc != B200LDLT_SUCCESS) return rc;
   }
   sv->mark("linv", S.nlevels);
@@ -951,9 +984,8 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
 
 // explicit inverses of the pivot blocks of the big fronts in LP (after their numeric factorisation): level 0 for all
 // 64x64 diagonal blocks in one launch, then two tile-GEMM launches per doubling level (all fronts and pairs batched)
-static int enqueue_linv(Solver* sv, const LinvPlan& LP) {
+static int enqueue_linv(Solver* sv, const LinvPlan& LP, cudaStream_t st) {
   if (LP.ndiag <= 0) return B200LDLT_SUCCESS;
-  cudaStream_t st = sv->stream;
   int& L = sv->launches;
   k_linv_diag<<<LP.ndiag, 64, 0, st>>>(sv->DS, sv->DN, LP.d_diag.p, sv->d_linv_off.p, sv->d_linv.p); ++L;
   for (size_t l = 0; l < LP.ng.size(); ++l) {
@@ -1198,10 +1230,15 @@ b200ldlt_handle b200ldlt_create(const b200ldlt_options* opt) {
     delete sv;
     return nullptr;
   }
+  // stream priorities: the chain of the big fronts (main stream) is the critical path of a factorisation; the bulk
+  // updates that trail it must never delay one of its launches
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (sv->opt.stream) sv->stream = (cudaStream_t)sv->opt.stream;
-  else { cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking); sv->own_stream = true; }
-  cudaStreamCreateWithFlags(&sv->stream2, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&sv->stream3, cudaStreamNonBlocking);
+  else { cudaStreamCreateWithPriority(&sv->stream, cudaStreamNonBlocking, prio_hi); sv->own_stream = true; }
+  cudaStreamCreateWithPriority(&sv->stream2, cudaStreamNonBlocking, std::min(prio_lo, prio_hi + 1));
+  cudaStreamCreateWithPriority(&sv->stream3, cudaStreamNonBlocking, prio_lo);
+  for (auto& q : sv->side) cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, prio_lo);
   cudaEventCreate(&sv->ev0);
   cudaEventCreate(&sv->ev1);
   cudaHostAlloc((void**)&sv->h_counters, CNT_N * sizeof(int), cudaHostAllocDefault);
@@ -1316,6 +1353,30 @@ int b200ldlt_solve(b200ldlt_handle h, int nrhs, double* rhs) {
   return B200LDLT_SUCCESS;
 }
 
+/* debug: write the kernel timeline of the last factorisation (needs env B200_FACTOR_TIMELINE=1 at create time):
+ * one line per record: kind s jb level k f t0 t1 ...  (kind: 1 chain role, 2 panel rows, 3 bulk update, 4 front (smem),
+ * 5 front (warp), 6 Schur, 7 extend-add, 10-12 L11 inverse; times in ns of %globaltimer) */
+int b200ldlt_dump_factor_timeline(b200ldlt_handle h, const char* path) {
+  Solver* sv = (Solver*)h;
+  if (!sv || !sv->DN.flog) return B200LDLT_FATAL_ERROR;
+  std::vector<unsigned long long> t(sv->d_flog.n);
+  CU(cudaMemcpy(t.data(), sv->d_flog.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  FILE* fp = fopen(path, "w");
+  if (!fp) return B200LDLT_FATAL_ERROR;
+  const unsigned long long nrec = std::min(t[0], t[1]);
+  for (unsigned long long i = 0; i < nrec; ++i) {
+    const unsigned long long* r = t.data() + 2 + i * FLOG_WORDS;
+    const int s = (int)(long long)r[1];
+    const int k = sv->S.sn_start[s + 1] - sv->S.sn_start[s];
+    const int f = k + (int)(sv->S.rows_ptr[s + 1] - sv->S.rows_ptr[s]);
+    fprintf(fp, "%d %d %d %d %d %d", (int)r[0], s, (int)(long long)r[2], sv->S.sn_level[s], k, f);
+    for (unsigned long long q = 0; q < r[3] && q < FLOG_WORDS - 4; ++q) fprintf(fp, " %llu", r[4 + q]);
+    fprintf(fp, "\n");
+  }
+  fclose(fp);
+  return B200LDLT_SUCCESS;
+}
+
 /* debug: write the per-task timeline of the last solve (needs env B200_SOLVE_TIMELINE=1 at analyse time) */
 int b200ldlt_dump_solve_timeline(b200ldlt_handle h, const char* path) {
   Solver* sv = (Solver*)h;
@@ -1369,13 +1430,14 @@ int64_t b200ldlt_shard_array(b200ldlt_handle h, const char* name, int64_t* out, 
 
 void* b200ldlt_device_ptr(b200ldlt_handle h, const char* name) {
   Solver* sv = (Solver*)h;
-  if (!sv || !sv->analysed || !name) return nullptr;
+  if (!sv || !name) return nullptr;
   std::string nm(name);
+  if (nm == "vals") return sv->d_vals.p;        // exists before the (lazy) analysis: assemble_augsys_device fills it
+  if (!sv->analysed) return nullptr;
   if (nm == "CB") return sv->d_CB.p;
   if (nm == "cbv") return sv->d_cbv.p;
   if (nm == "x") return sv->d_x.p;
   if (nm == "counters") return sv->d_counters.p;
-  if (nm == "vals") return sv->d_vals.p;
   return nullptr;
 }
 

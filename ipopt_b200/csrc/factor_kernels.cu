@@ -536,6 +536,9 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
   int* pt = lp + k;
   int* sh = pt + k;
   const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nt = WARP ? 32 : blockDim.x;
+  unsigned long long ts[4];
+  const bool tlog = N.flog != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+  if (tlog) ts[0] = flog_now();
 
   for (int t = tid; t < ld * f; t += nt) F[t] = 0.0;
   gsync<WARP>();
@@ -562,8 +565,10 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
     gsync<WARP>();
   }
 
+  if (tlog) ts[1] = flog_now();
   factor_front_smem<WARP>(F, ld, f, k, lp, pt, cv1, cv2, sh, N.u, N.tiny, N.dinv + c0, N.doff + c0,
                           N.ptype + c0, N.counters);
+  if (tlog) ts[2] = flog_now();
 
   // write L panel (f x k, ld = f), unit diagonal.  The strictly-upper part of the k x k pivot block receives L11^T
   // (entry (i, t), i < t, = L[t][i]): the backward solve of the small fronts reads row t of L11 as the contiguous
@@ -590,6 +595,7 @@ __global__ void k_front_smem(DevSym S, DevNum N, const int* __restrict__ front_l
   double* __restrict__ cbo = N.CB + S.cb_off[s];
   for (int m = tid >> 5; m < r; m += (nt >> 5))
     for (int i = m + (tid & 31); i < r; i += 32) cbo[i + (size_t)m * r] = F[(k + i) + (k + m) * ld];
+  if (tlog) { ts[3] = flog_now(); flog_put(N, 4, s, f, ts, 4); }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -602,6 +608,7 @@ __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const in
   const int group = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (group >= nfronts) return;
   const int s = front_list[group];
+  FlogScope fs(N, 5, s, 0);
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const int f = k + r;
@@ -668,6 +675,7 @@ __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const in
 #pragma unroll
   for (int c = 0; c < 32; ++c)
     if (lane >= k && lane < f && c <= lane - k) cbo[(lane - k) + (size_t)c * r] = a[c];
+  fs.done();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -700,12 +708,16 @@ __global__ void k_big_assemble(DevSym S, DevNum N, const int* __restrict__ front
 // einv built at analysis; per-child metadata is fetched lane-parallel (one child per lane) and broadcast.
 __global__ void __launch_bounds__(256) k_big_extend_all(DevSym S, DevNum N, const int* __restrict__ front_list) {
   const int p = front_list[blockIdx.y];
-  const int kp = S.sn_start[p + 1] - S.sn_start[p];
+  const int c0p = S.sn_start[p];
+  const int kp = S.sn_start[p + 1] - c0p;
   const int rp = (int)(S.rows_ptr[p + 1] - S.rows_ptr[p]);
   const int fp = kp + rp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lj = blockIdx.x * 8 + warp;
   if (lj >= fp) return;
+  unsigned long long ts[2];
+  const bool tlog = N.flog != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || (blockIdx.x + 1) * 8 >= fp);
+  if (tlog) ts[0] = flog_now();
   // destination column indexed by the parent row li >= lj
   double* __restrict__ dst = (lj < kp) ? N.L + S.L_off[p] + (size_t)lj * fp
                                        : N.CB + S.cb_off[p] + (size_t)(lj - kp) * rp - kp;
@@ -728,9 +740,28 @@ __global__ void __launch_bounds__(256) k_big_extend_all(DevSym S, DevNum N, cons
       const long long roq = __shfl_sync(0xffffffffu, ro, src), coq = __shfl_sync(0xffffffffu, co, src);
       const double* __restrict__ cbcol = N.CB + coq + (size_t)jq * rq;
       const int* __restrict__ rl = S.rel + roq;
-      for (int ii = jq + lane; ii < rq; ii += 32) dst[rl[ii]] += cbcol[ii];
+      // four independent gather / add / scatter groups in flight (the rows of one child column are distinct)
+      int ii = jq + lane;
+      for (; ii + 96 < rq; ii += 128) {
+        const int r0 = rl[ii], r1 = rl[ii + 32], r2 = rl[ii + 64], r3 = rl[ii + 96];
+        const double v0 = cbcol[ii], v1 = cbcol[ii + 32], v2 = cbcol[ii + 64], v3 = cbcol[ii + 96];
+        const double d0 = dst[r0], d1 = dst[r1], d2 = dst[r2], d3 = dst[r3];
+        dst[r0] = d0 + v0; dst[r1] = d1 + v1; dst[r2] = d2 + v2; dst[r3] = d3 + v3;
+      }
+      for (; ii < rq; ii += 32) dst[rl[ii]] += cbcol[ii];
+      __syncwarp();   // the next child may add to the same parent entries from other lanes
     }
   }
+  // the column is final now: max |entry| below its 32x32 diagonal block for the first three panels (the threshold test of
+  // the first chain steps; later panels get theirs from k_big_update)
+  if (lj < min(3 * NB, kp)) {
+    const int below = (lj / NB + 1) * NB;
+    double m = 0.0;
+    for (int i = below + lane; i < fp; i += 32) m = fmax(m, fabs(dst[i]));
+    m = warp_max(m);
+    if (lane == 0) N.colmax[c0p + lj] = m;
+  }
+  if (tlog) { ts[1] = flog_now(); flog_put(N, 7, p, 0, ts, 2); }
 }
 
 // column maxima of the first panel below its diagonal block (later panels get theirs from k_big_update)
@@ -751,164 +782,151 @@ __global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_
 }
 
 // --------------------------------------------------------------------------------------------
-// The same pivoted LDL^T of a symmetric block of order f <= 32 (k = f candidates) by FOUR warps -- the diagonal blocks of
-// the big fronts are the serial chain of the factorisation, so what counts is the latency of ONE pivot step.
-//   * warp w owns the 8 columns with original index 8w .. 8w+7 for the whole factorisation; lane = row.  Columns never
-//     move, so there is no register shifting / compaction at all: the pivot ORDER is tracked logically (mypos, exactly the
-//     position arithmetic of warp_ldlt32) and replicated in every warp.
-//   * per pivot step the owner warp publishes the candidate column in shared memory (double-buffered: one CTA barrier per
-//     published column); every warp then repeats the cheap search / decision on it redundantly (identical results, no
-//     second exchange) and updates its own 8 columns: 8 DFMAs instead of 32 + 62 moves.
-// Decisions, pivot order, factors and counters are IDENTICAL to warp_ldlt32 (same comparisons on the same values; the
-// per-entry arithmetic is the same fma); tests/test_gpu_parity.py checks the factors bit for bit.
-// Output as warp_ldlt32: Lraw[i*33 + t], order[t], pt[t], dinv_s[t], doff_s[t] (written by warp 0).
-// colA / colB: 2 x 32 doubles each (shared).  All 128 threads must call this.
+// cta_ldlt32s: pivoted LDL^T of a symmetric block of order f <= 32 (all f columns are candidates) by FOUR warps -- the
+// diagonal blocks of the big fronts are the serial chain of the factorisation, so what counts is the latency of ONE pivot
+// step.  Same pivoting rules as warp_ldlt32 (Bunch-Kaufman 1x1 / 2x2 with the threshold test against the whole front
+// column, failed columns retried after the others, forced pivots at the end), organised as follows:
+//   * the block lives in shared memory As[c * 33 + i] = A[i][c] (full symmetric storage) NEXT to the owners' registers
+//     (warp w: columns 8w..8w+7, lane = row): after every update the owners store their live columns back, so any
+//     column -- the candidate AND a 2x2 partner -- is one conflict-free shared-memory read away: ONE barrier per pivot
+//     step, no publishing, no register select;
+//   * a 1x1 pivot is first tried against the float-rounded-UP column maximum (one redux, no arg-max, no exact re-read):
+//     that test is conservative, so whenever it passes the exact test passes too;
+//   * candidates are taken in index order from a bit mask (parked columns wait for the next pass) -- all bookkeeping is
+//     warp-uniform integer work.
+// Output as warp_ldlt32: Lraw[i*33 + t] (must not alias As), order[t], pt[t], dinv_s[t], doff_s[t] (written by warp 0).
+// All 128 threads must call this.
+// gext_s: 32 doubles of shared memory holding max |entry| of column c in rows OUTSIDE the block.
 // --------------------------------------------------------------------------------------------
-__device__ void cta_ldlt32(double (&a)[8], const int f, const double u, const double tiny,
-                           double* __restrict__ Lraw, int* __restrict__ order, int* __restrict__ pt,
-                           double* __restrict__ dinv_s, double* __restrict__ doff_s,
-                           double* __restrict__ colA, double* __restrict__ colB,
-                           const double gext /* lane c: max |entry| of column c in rows OUTSIDE the block */, int* counters) {
+__device__ void cta_ldlt32s(double (&a)[8], const int f, const double u, const double tiny,
+                            double* __restrict__ As, double* __restrict__ Lraw, int* __restrict__ order, int* __restrict__ pt,
+                            double* __restrict__ dinv_s, double* __restrict__ doff_s, const double* __restrict__ gext_s,
+                            int* counters) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int k = f;
-  int mypos = lane;
-  unsigned alive = (f >= 32) ? 0xffffffffu : ((1u << f) - 1u);
-  unsigned cand = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
-  int nc = k, npass = k, t = 0, progress = 0;
+  unsigned cand = (f >= 32) ? 0xffffffffu : ((1u << f) - 1u);
+  unsigned parked = 0;
+  int t = 0, progress = 0;
   bool forced = false;
   int c_neg = 0, c_forced = 0, c_tiny = 0, c_2x2 = 0;
   int my_order = 0, my_pt = 1;
   double my_dinv = 0.0, my_doff = 0.0;
-  int par = 0;
-  auto pick = [&](int q) -> double {   // a[q], q in 0..7 dynamic (warp-uniform)
-    double v = a[0];
+  const unsigned lbit = 1u << lane;
+  // 1x1 pivot: pivot column values pc (lane = row), pivot dd with reciprocal rinv, column g, pr[q] = A[8w+q][g]
+  auto apply1 = [&](const double pc, const double dd, const double rinv, const int g, const double (&pr)[8]) {
+    const double l = ((cand & lbit) && lane != g) ? pc * rinv : 0.0;
+    cand &= ~(1u << g);
 #pragma unroll
-    for (int j = 1; j < 8; ++j) v = (q == j) ? a[j] : v;
-    return v;
-  };
-  while (nc > 0) {
-    if (npass == 0) {
-      if (progress > 0) { npass = nc; progress = 0; }
-      else { forced = true; npass = nc; }
+    for (int q = 0; q < 8; ++q) a[q] = fma(-l, pr[q], a[q]);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if ((cand >> (8 * w + q)) & 1u) As[(8 * w + q) * 33 + lane] = a[q];
+    if (w == 0) {
+      Lraw[lane * 33 + t] = l;
+      if (lane == t) { my_order = g; my_pt = 1; my_dinv = rinv; my_doff = 0.0; }
     }
-    const bool me_alive = (alive >> lane) & 1u;
-    const bool me_cand = (cand >> lane) & 1u;
-    int g0 = __ffs(__ballot_sync(0xffffffffu, me_alive && mypos == 0)) - 1;
-    double* cA = colA + 32 * par;
-    double* cB = colB + 32 * par;
-    par ^= 1;
-    // ---- publish column g0, then every warp searches it ----
-    if (w == (g0 >> 3)) cA[lane] = pick(g0 & 7);
-    __syncthreads();
-    const double a0 = cA[lane];                 // A[lane][g0]
-    const double v0 = fabs(a0);
-    const float v0f = __double2float_ru(v0);
+    if (dd < 0.0) ++c_neg;
+    t += 1;
+    ++progress;
+  };
+  while (cand != 0u) {
+    unsigned avail = cand & ~parked;
+    if (avail == 0u) {
+      if (progress > 0) progress = 0; else forced = true;
+      parked = 0u;
+      avail = cand;
+    }
+    const int g0 = __ffs(avail) - 1;
+    __syncthreads();                                   // the previous step's column stores are visible
+    const double* __restrict__ cA = As + g0 * 33;
+    // everything a 1x1 pivot on g0 needs is loaded (and its reciprocal started) before the search: the loads and the
+    // division overlap the reduction instead of following the decision
+    const double a0 = cA[lane];                        // A[lane][g0]
+    const double pa0 = cA[g0];
+    const double gam = gext_s[g0];
+    double pr0[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) pr0[q] = cA[8 * w + q];   // A[8w+q][g0]
+    const bool me_cand = (cand & lbit) != 0u;
+    const float v0f = __double2float_ru(fabs(a0));
     const float lam_in = (me_cand && lane != g0) ? v0f : -1.0f;
     const float lamf = wredux_max(lam_in);
-    const float gamf = wredux_max((me_alive && !me_cand) ? v0f : 0.0f);
-    int r = __ffs(__ballot_sync(0xffffffffu, lam_in == lamf)) - 1;
-    double lam = 0.0;
-    if (lamf < 0.0f) r = -1;
-    else lam = fabs(cA[r]);                     // exact magnitude of the selected entry
-    const double gam = fmax((double)gamf, __shfl_sync(0xffffffffu, gext, g0));
-    const double pa0 = cA[g0];                  // A[g0][g0]
+    const double rinv0 = 1.0 / pa0;                    // (issued behind the reduction: its latency overlaps the division)
     const double ajj = fabs(pa0);
-    const bool ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
-    int type = 0;
-    bool noise = false;
-    const double colmax_f = fmax(lam, gam);
-    double a1 = 0.0;                            // A[lane][r] when the 2x2 branch looked at column r
-    bool usedB = false;
-    if (forced) { type = 1; noise = !(fmax(ajj, colmax_f) > 1e-12); }
-    else if (lam == 0.0 || r < 0) { if (ok1) type = 1; }
-    else if (ok1 && ajj >= BK_ALPHA * lam) type = 1;
-    else {
-      // (logically) bring column r to position 1
-      const int p = __shfl_sync(0xffffffffu, mypos, r);
-      if (p > 1) { if (mypos == 1) mypos = p; else if (mypos == p) mypos = 1; }
-      if (w == (r >> 3)) cB[lane] = pick(r & 7);
-      __syncthreads();
-      usedB = true;
-      a1 = cB[lane];
-      const double v1 = fabs(a1);
-      const float v1f = __double2float_ru(v1);
-      const bool other = me_alive && lane != g0 && lane != r;
-      double sig = (double)wredux_max((me_cand && lane != r) ? v1f : 0.0f);
-      double gamr = (double)wredux_max((me_alive && !me_cand) ? v1f : 0.0f);
-      double cj = (double)wredux_max(other ? v0f : 0.0f), cr = (double)wredux_max(other ? v1f : 0.0f);
-      {
-        const double ge_r = __shfl_sync(0xffffffffu, gext, r), ge_j = __shfl_sync(0xffffffffu, gext, g0);
-        gamr = fmax(gamr, ge_r); cr = fmax(cr, ge_r); cj = fmax(cj, ge_j);
-      }
-      const double crr = cB[r];                 // A[r][r]
-      const double arr = fabs(crr);
-      if (ok1 && ajj * sig >= BK_ALPHA * lam * lam) type = 1;
-      else if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, gamr)) {
-        // 1x1 on r: swap positions 0 and 1
-        if (mypos == 0) mypos = 1; else if (mypos == 1) mypos = 0;
-        g0 = r;
-        type = 4;                               // 1x1 whose pivot column is cB
-      } else {
-        const double pb = cA[r];                // A[r][g0]
-        const double det = pa0 * crr - pb * pb, adet = fabs(det);
-        if (lam > tiny && adet > 0.0 && isfinite(adet) &&
-            (fabs(crr) * cj + fabs(pb) * cr) * u <= adet && (fabs(pa0) * cr + fabs(pb) * cj) * u <= adet)
-          type = 3;
-      }
-    }
-    if (type == 0) {
-      // park the column at position 0 behind the remaining candidates (position nc-1) and try the next one
-      if (mypos == 0) mypos = nc - 1; else if (mypos < nc) mypos -= 1;
-      --npass;
+    const double lamd = (lamf < 0.0f) ? 0.0 : (double)lamf;     // >= the exact maximum
+    if (!forced && (ajj > tiny) && (ajj >= u * fmax(lamd, gam)) && (ajj >= BK_ALPHA * lamd)) {
+      apply1(a0, pa0, rinv0, g0, pr0);
       continue;
     }
-    if (type == 1 || type == 4) {
-      const double* __restrict__ cP = (type == 4) ? cB : cA;     // the pivot column, indexed by row
-      double dd = cP[g0];
-      if (forced) {
-        if (noise || !(fabs(dd) > tiny)) { dd = (dd < 0.0) ? -1.5e-8 : 1.5e-8; ++c_tiny; }
-        else { dd = copysign(fmax(fabs(dd), 1e-8 * colmax_f), dd); ++c_forced; }
-      }
-      const double c0v = (type == 4) ? a1 : a0;
-      const double rinv = 1.0 / dd;
-      const double l = (me_alive && lane != g0) ? c0v * rinv : 0.0;
+    int r = -1;
+    double lam = 0.0;
+    if (lamf >= 0.0f) {
+      r = __ffs(__ballot_sync(0xffffffffu, lam_in == lamf)) - 1;
+      lam = fabs(cA[r]);                               // exact magnitude of the selected entry
+    }
+    const bool ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
+    const double colmax_f = fmax(lam, gam);
+    if (forced) {
+      double dd = pa0;
+      const bool noise = !(fmax(ajj, colmax_f) > 1e-12);
+      if (noise || !(fabs(dd) > tiny)) { dd = (dd < 0.0) ? -1.5e-8 : 1.5e-8; ++c_tiny; }
+      else { dd = copysign(fmax(fabs(dd), 1e-8 * colmax_f), dd); ++c_forced; }
+      apply1(a0, dd, 1.0 / dd, g0, pr0);
+      continue;
+    }
+    if (lam == 0.0 || r < 0) {
+      if (ok1) apply1(a0, pa0, rinv0, g0, pr0);
+      else parked |= 1u << g0;
+      continue;
+    }
+    if (ok1 && ajj >= BK_ALPHA * lam) { apply1(a0, pa0, rinv0, g0, pr0); continue; }
+    // ---- second column: the arg-max partner r ----
+    const double* __restrict__ cB = As + r * 33;
+    const double a1 = cB[lane];                        // A[lane][r]
+    const double crr = cB[r];
+    const double ge_r = gext_s[r];
+    double pr1[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) a[q] = fma(-l, cP[8 * w + q], a[q]);   // pivot row entry of column 8w+q = A[8w+q][g0]
-      if (w == 0) {
-        Lraw[lane * 33 + t] = l;
-        if (lane == t) { my_order = g0; my_pt = 1; my_dinv = rinv; my_doff = 0.0; }
-      }
-      if (dd < 0.0) ++c_neg;
-      alive &= ~(1u << g0); cand &= ~(1u << g0);
-      mypos -= 1;
-      nc -= 1; npass = max(npass - 1, 0); t += 1;
-    } else {
-      const double pa = pa0, pb = cA[r], pc2 = cB[r];
-      const double det = pa * pc2 - pb * pb;
-      const double c1 = a0, c2v = a1;
-      const bool other = me_alive && lane != g0 && lane != r;
-      const double idet = 1.0 / det;
-      const double l1 = other ? (pc2 * c1 - pb * c2v) * idet : 0.0;
-      const double l2 = other ? (pa * c2v - pb * c1) * idet : 0.0;
+    for (int q = 0; q < 8; ++q) pr1[q] = cB[8 * w + q];   // A[8w+q][r]
+    const float v1f = __double2float_ru(fabs(a1));
+    const bool other = me_cand && lane != g0 && lane != r;
+    const double sig = (double)wredux_max((me_cand && lane != r) ? v1f : 0.0f);
+    double cjm = (double)wredux_max(other ? v0f : 0.0f), cr = (double)wredux_max(other ? v1f : 0.0f);
+    cr = fmax(cr, ge_r); cjm = fmax(cjm, gam);
+    const double arr = fabs(crr);
+    const double pb = cA[r];                           // A[r][g0]
+    // Of the two columns read in this step one may stay alive (1x1 on g0 or on r) and is then rewritten by its owner:
+    // every warp must have finished reading before any store.  (The paths above only read column g0, which dies.)
+    __syncthreads();
+    const double det = pa0 * crr - pb * pb, adet = fabs(det);
+    const double idet = 1.0 / det;                     // (started before the tests that decide whether it is used)
+    if (ok1 && ajj * sig >= BK_ALPHA * lam * lam) { apply1(a0, pa0, rinv0, g0, pr0); continue; }
+    if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, ge_r)) { apply1(a1, crr, 1.0 / crr, r, pr1); continue; }   // 1x1 on r
+    if (lam > tiny && adet > 0.0 && isfinite(adet) &&
+        (arr * cjm + fabs(pb) * cr) * u <= adet && (ajj * cr + fabs(pb) * cjm) * u <= adet) {
+      const double l1 = other ? (crr * a0 - pb * a1) * idet : 0.0;
+      const double l2 = other ? (pa0 * a1 - pb * a0) * idet : 0.0;
+      cand &= ~((1u << g0) | (1u << r));
 #pragma unroll
-      for (int q = 0; q < 8; ++q) a[q] = fma(-l2, cB[8 * w + q], fma(-l1, cA[8 * w + q], a[q]));
+      for (int q = 0; q < 8; ++q) a[q] = fma(-l2, pr1[q], fma(-l1, pr0[q], a[q]));
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if ((cand >> (8 * w + q)) & 1u) As[(8 * w + q) * 33 + lane] = a[q];
       if (w == 0) {
         Lraw[lane * 33 + t] = l1;
         Lraw[lane * 33 + t + 1] = l2;
-        if (lane == t) { my_order = g0; my_pt = 2; my_dinv = pc2 * idet; my_doff = -pb * idet; }
-        if (lane == t + 1) { my_order = r; my_pt = 3; my_dinv = pa * idet; my_doff = 0.0; }
+        if (lane == t) { my_order = g0; my_pt = 2; my_dinv = crr * idet; my_doff = -pb * idet; }
+        if (lane == t + 1) { my_order = r; my_pt = 3; my_dinv = pa0 * idet; my_doff = 0.0; }
       }
       ++c_2x2;
-      if (det < 0.0) c_neg += 1; else if (pa < 0.0) c_neg += 2;
-      alive &= ~((1u << g0) | (1u << r)); cand &= ~((1u << g0) | (1u << r));
-      mypos -= 2;
-      nc -= 2; npass = max(npass - 2, 0); t += 2;
+      if (det < 0.0) c_neg += 1; else if (pa0 < 0.0) c_neg += 2;
+      t += 2;
+      ++progress;
+      continue;
     }
-    (void)usedB;
-    ++progress;
+    parked |= 1u << g0;                                // nothing acceptable now: retry after the other candidates
   }
   if (w == 0) {
-    if (lane < k) { order[lane] = my_order; pt[lane] = my_pt; dinv_s[lane] = my_dinv; doff_s[lane] = my_doff; }
+    if (lane < f) { order[lane] = my_order; pt[lane] = my_pt; dinv_s[lane] = my_dinv; doff_s[lane] = my_doff; }
     if (lane == 0) {
       if (c_neg) atomicAdd(counters + CNT_NEG, c_neg);
       if (c_forced) atomicAdd(counters + CNT_FORCED, c_forced);
@@ -920,62 +938,67 @@ __device__ void cta_ldlt32(double (&a)[8], const int f, const double u, const do
 }
 
 // --------------------------------------------------------------------------------------------
-// THE CHAIN KERNEL of the big-front panel pipeline: everything on the critical path of one panel step, in one launch.
-// Call p (jbp = first column of panel p, or -NB for the first call) produces the pivoted LDL^T of diagonal block p+1:
-//   B. (p >= 1) the rank-32 update of panel p-1 applied to the two tiles this kernel owns: rows of block p+1 x columns of
-//      panel p, and block (p+1, p+1).  Inputs: L / W rows of block p+1 at panel p-1 (bulk k_big_trsm of panel p-1) and W
-//      rows of block p at panel p-1 (written by the previous call).  The bulk k_big_update(q) skips these tiles.
-//   C. (p >= 0) the panel rows of block p+1:  X = A_perm L_bb(p)^-T (= L D),  L = X D^-1 -> written to L / W for the bulk
-//      update; then this panel's rank-32 update of block (p+1, p+1).
-//   D. pivoted LDL^T of block (p+1, p+1) by four warps (cta_ldlt32).
-// It needs the bulk k_big_trsm of panel p-1 and the bulk k_big_update of panel p-2: the bulk stream always has a full
-// chain step of slack, so the chain (one launch per 32 pivots) is never gated by the trailing updates.
-// dynamic smem: 6 tiles of 32 x 33 doubles
+// THE CHAIN ROLE of the big-front panel pipeline (CTA 0 of k_big_panel): everything on the critical path of one panel
+// step.  Call p (jbp = first column of panel p, or -NB for the first call) produces the pivoted LDL^T of block p+1:
+//   A. all operand tiles fetched with asynchronous copies (in flight together, zero-filled where masked);
+//   B. (p >= 1) the rank-32 update of panel p-1 applied to the two tiles the chain owns: rows of block p+1 x columns of
+//      panel p, and block (p+1, p+1).  Inputs: L / W rows of block p+1 at panel p-1 (rows role of the previous launch) and
+//      W rows of block p at panel p-1 (chain role of the previous launch).  The bulk k_big_update(q) skips these tiles.
+//   C. (p >= 0) the panel rows of block p+1:  X = A_perm L_bb(p)^-T (= L D),  L = X D^-1 (four warps, shuffles) -> L / W
+//      for the bulk update; then this panel's rank-32 update of block (p+1, p+1).
+//   D. pivoted LDL^T of block (p+1, p+1) by four warps (cta_ldlt32s).
+// It needs the previous k_big_panel and the bulk k_big_update of panel p-2: the bulk stream always has a full chain step
+// of slack, so the chain (one launch per 32 pivots) is never gated by the trailing updates.
+// dynamic smem: 8 tiles of 32 x 33 doubles
 // --------------------------------------------------------------------------------------------
 #define CHAIN_TILE (NB * 33)
-#define CHAIN_SMEM (6 * CHAIN_TILE * (int)sizeof(double))
-__device__ __forceinline__ void chain_tile_update(double* __restrict__ C, const double* __restrict__ A, const double* __restrict__ B,
-                                                  bool lower_only) {
-  // C[i][j] -= sum_t A[i][t] B[j][t] on 32 x 32 row-major tiles (ld 33), 2 x 4 entries per thread (128 threads)
+#define CHAIN_SMEM (8 * CHAIN_TILE * (int)sizeof(double))
+// C[i][j] -= sum_t A[i][t] B[j][t] on 32 x 32 row-major tiles (ld 33), 2 x 4 entries per thread (128 threads: rows a, a+16;
+// columns b + 8w).  LOWER: only the lower triangle is needed -- the quadrant rows < 16 x columns >= 16 is skipped.
+template <bool LOWER>
+__device__ __forceinline__ void chain_tile_update(double* __restrict__ C, const double* __restrict__ A, const double* __restrict__ B) {
   const int tid = threadIdx.x, a = tid & 15, b = tid >> 4;
-  double acc[2][4];
+  double acc0[4], acc1[4];
 #pragma unroll
-  for (int u = 0; u < 2; ++u)
-#pragma unroll
-    for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
+  for (int w = 0; w < 4; ++w) { acc0[w] = 0.0; acc1[w] = 0.0; }
 #pragma unroll 8
   for (int t = 0; t < NB; ++t) {
     const double l0 = A[a * 33 + t], l1 = A[(a + 16) * 33 + t];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const double wv = B[(b + 8 * w) * 33 + t];
-      acc[0][w] = fma(l0, wv, acc[0][w]);
-      acc[1][w] = fma(l1, wv, acc[1][w]);
+      if (!LOWER || w < 2) acc0[w] = fma(l0, wv, acc0[w]);
+      acc1[w] = fma(l1, wv, acc1[w]);
     }
   }
 #pragma unroll
-  for (int u = 0; u < 2; ++u)
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int ii = a + 16 * u, jj = b + 8 * w;
-      if (!lower_only || jj <= ii) C[ii * 33 + jj] -= acc[u][w];
-    }
+  for (int w = 0; w < 4; ++w) {
+    const int jj = b + 8 * w;
+    if (!LOWER || (w < 2 && jj <= a)) C[a * 33 + jj] -= acc0[w];
+    if (!LOWER || jj <= a + 16) C[(a + 16) * 33 + jj] -= acc1[w];
+  }
 }
 
-__global__ void __launch_bounds__(128) k_big_chain(DevSym S, DevNum N, const int* __restrict__ front_list, int jbp) {
-  extern __shared__ double csm[];
-  __shared__ double colA[64], colB[64];
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 8 : 0;      // src-size 0: the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+__device__ void chain_role(const DevSym& S, const DevNum& N, const int s, const int jbp, double* __restrict__ csm) {
+  __shared__ double gext_s[NB];
   __shared__ double dinv_s[NB], doff_s[NB];
   __shared__ int order[NB], pt[NB];
   __shared__ double di[NB], dup[NB], dlo[NB];
   __shared__ int bp[NB];
   double* A1 = csm;                    // rows of the new block x columns of panel p
-  double* A2 = csm + CHAIN_TILE;       // the new diagonal block (lower part), later the raw L of cta_ldlt32
-  double* Lr = csm + 2 * CHAIN_TILE;   // L rows of the new block at panel p-1   (later: L rows at panel p)
-  double* WrN = csm + 3 * CHAIN_TILE;  // W rows of the new block at panel p-1   (later: W rows at panel p)
+  double* A2 = csm + CHAIN_TILE;       // the new diagonal block (lower part), then the symmetric working copy of cta_ldlt32s
+  double* Lr = csm + 2 * CHAIN_TILE;   // L rows of the new block at panel p-1
+  double* WrN = csm + 3 * CHAIN_TILE;  // W rows of the new block at panel p-1
   double* WrP = csm + 4 * CHAIN_TILE;  // W rows of block p at panel p-1
   double* Lbb = csm + 5 * CHAIN_TILE;  // L_bb(p), pivot order, strictly lower
-  const int s = front_list[blockIdx.x];
+  double* Ln = csm + 6 * CHAIN_TILE;   // L rows of the new block at panel p (computed here)
+  double* Wn = csm + 7 * CHAIN_TILE;   // W rows of the new block at panel p (computed here)
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   const int o = jbp + NB;              // first column of the block to factor
   if (o >= k) return;
@@ -986,22 +1009,26 @@ __global__ void __launch_bounds__(128) k_big_chain(DevSym S, DevNum N, const int
   double* __restrict__ P = N.L + S.L_off[s];
   double* __restrict__ Wp = N.W + S.L_off[s];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  // ---- all global loads up front ----
+  unsigned long long ts[6];
+  const bool tlog = N.flog != nullptr && tid == 0;
+  if (tlog) ts[0] = flog_now();
+  // ---- all global loads in flight at once (asynchronous copies straight into the tiles, zero-filled where masked) ----
 #pragma unroll
   for (int e8 = 0; e8 < 8; ++e8) {
     const int e = tid + 128 * e8, ii = e & 31, jj = e >> 5;     // consecutive threads -> consecutive rows (coalesced columns)
     const bool rin = ii < nbn;
-    A2[ii * 33 + jj] = (rin && jj < nbn && ii >= jj) ? P[(o + ii) + (size_t)(o + jj) * f] : 0.0;
+    cp_async8(A2 + ii * 33 + jj, P + (o + ii) + (size_t)(o + jj) * f, rin && jj < nbn && ii >= jj);
     if (has_p) {
-      A1[ii * 33 + jj] = rin ? P[(o + ii) + (size_t)(jbp + jj) * f] : 0.0;
-      Lbb[ii * 33 + jj] = (ii > jj) ? P[(jbp + ii) + (size_t)(jbp + jj) * f] : 0.0;
+      cp_async8(A1 + ii * 33 + jj, P + (o + ii) + (size_t)(jbp + jj) * f, rin);
+      cp_async8(Lbb + ii * 33 + jj, P + (jbp + ii) + (size_t)(jbp + jj) * f, ii > jj);
     }
     if (has_pp) {
-      Lr[ii * 33 + jj] = rin ? P[(o + ii) + (size_t)(jbq + jj) * f] : 0.0;
-      WrN[ii * 33 + jj] = rin ? Wp[(o + ii) + (size_t)(jbq + jj) * f] : 0.0;
-      WrP[ii * 33 + jj] = Wp[(jbp + ii) + (size_t)(jbq + jj) * f];
+      cp_async8(Lr + ii * 33 + jj, P + (o + ii) + (size_t)(jbq + jj) * f, rin);
+      cp_async8(WrN + ii * 33 + jj, Wp + (o + ii) + (size_t)(jbq + jj) * f, rin);
+      cp_async8(WrP + ii * 33 + jj, Wp + (jbp + ii) + (size_t)(jbq + jj) * f, true);
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   if (has_p && tid < NB) {
     const double d = N.dinv[c0 + jbp + tid], od = N.doff[c0 + jbp + tid];
     const int ty = N.ptype[c0 + jbp + tid];
@@ -1013,52 +1040,73 @@ __global__ void __launch_bounds__(128) k_big_chain(DevSym S, DevNum N, const int
     bp[tid] = N.bperm[c0 + jbp + tid];
   }
   const double gext = (lane < nbn) ? N.colmax[c0 + o + lane] : 0.0;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (tlog) ts[1] = flog_now();
   if (has_pp) {
-    // B. panel p-1's update of the two tiles
-    chain_tile_update(A1, Lr, WrP, false);
-    chain_tile_update(A2, Lr, WrN, true);
+    // B. panel p-1's update of the two tiles (independent of each other: no barrier in between)
+    chain_tile_update<false>(A1, Lr, WrP);
+    chain_tile_update<true>(A2, Lr, WrN);
     __syncthreads();
   }
+  if (tlog) ts[2] = flog_now();
   if (has_p) {
-    // C. rows of the new block at panel p (warp 0, lane = row): x = A_perm L_bb^-T, l = x D^-1
-    if (w == 0) {
-      double x[NB];
+    // C. rows of the new block at panel p: X = A_perm L_bb^-T (= L D), L = X D^-1.  Warp w solves rows 8w..8w+7; lane q
+    // holds entry q of each row and row q of L_bb, the pivot entry x[t] travels by shuffle (31 steps of 8 independent
+    // shuffle + FMA pairs).
+    double lq[NB];
 #pragma unroll
-      for (int t = 0; t < NB; ++t) x[t] = A1[lane * 33 + bp[t]];
+    for (int t = 0; t < NB; ++t) lq[t] = Lbb[lane * 33 + t];     // strictly lower: lq[t] = 0 for t >= lane
+    double x[8];
+    const int bpl = bp[lane];
 #pragma unroll
-      for (int t = 0; t < NB - 1; ++t) {
-        const double xt = x[t];
+    for (int i = 0; i < 8; ++i) x[i] = A1[(8 * w + i) * 33 + bpl];
 #pragma unroll
-        for (int q = t + 1; q < NB; ++q) x[q] = fma(-xt, Lbb[q * 33 + t], x[q]);
+    for (int t = 0; t < NB - 1; ++t) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double xt = __shfl_sync(0xffffffffu, x[i], t);
+        x[i] = fma(-xt, lq[t], x[i]);                            // (lq[t] = 0 leaves the finished entries alone)
       }
-      const double lim = 1.0 / N.u;
-      double lmax = 0.0;
-#pragma unroll
-      for (int t = 0; t < NB; ++t) {
-        double v = x[t] * di[t];
-        if (t + 1 < NB) v = fma(x[t + 1], dup[t], v);
-        if (t > 0) v = fma(x[t - 1], dlo[t], v);
-        lmax = fmax(lmax, fabs(v));
-        Lr[lane * 33 + t] = v;
-        WrN[lane * 33 + t] = x[t];
-        if (lane < nbn) {
-          P[(o + lane) + (size_t)(jbp + t) * f] = v;
-          Wp[(o + lane) + (size_t)(jbp + t) * f] = x[t];
-        }
-      }
-      if (lane < nbn && lmax > lim) atomicAdd(N.counters + CNT_GROWTH, 1);
     }
+    const double dq = di[lane], duq = dup[lane], dlq = dlo[lane];
+    const double lim = 1.0 / N.u;
+    double lmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double xn = __shfl_down_sync(0xffffffffu, x[i], 1), xp = __shfl_up_sync(0xffffffffu, x[i], 1);
+      double v = x[i] * dq;
+      v = fma(xn, duq, v);             // (dup = 0 in the last column, dlo = 0 in the first: the wrapped lanes do not count)
+      v = fma(xp, dlq, v);
+      if (8 * w + i < nbn) lmax = fmax(lmax, fabs(v));
+      Ln[(8 * w + i) * 33 + lane] = v;
+      Wn[(8 * w + i) * 33 + lane] = x[i];
+    }
+    if (lmax > lim) atomicAdd(N.counters + CNT_GROWTH, 1);
     __syncthreads();
-    chain_tile_update(A2, Lr, WrN, true);     // this panel's update of the new diagonal block
+    chain_tile_update<true>(A2, Ln, Wn);      // this panel's update of the new diagonal block
+    // the new rows go to L / W for the bulk update (coalesced: consecutive threads -> consecutive rows of a column)
+#pragma unroll
+    for (int e8 = 0; e8 < 8; ++e8) {
+      const int e = tid + 128 * e8, ii = e & 31, jj = e >> 5;
+      if (ii < nbn) {
+        P[(o + ii) + (size_t)(jbp + jj) * f] = Ln[ii * 33 + jj];
+        Wp[(o + ii) + (size_t)(jbp + jj) * f] = Wn[ii * 33 + jj];
+      }
+    }
     __syncthreads();
   }
   // D. pivoted LDL^T of the new diagonal block
+  if (tlog) ts[3] = flog_now();
   double a[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) { const int c = 8 * w + q; a[q] = (c <= lane) ? A2[lane * 33 + c] : A2[c * 33 + lane]; }
-  __syncthreads();   // A2 is reused as the raw L output
-  cta_ldlt32(a, nbn, N.u, N.tiny, A2, order, pt, dinv_s, doff_s, colA, colB, gext, N.counters);
+  if (w == 0) gext_s[lane] = gext;
+  __syncthreads();   // A2 becomes the full symmetric working copy of cta_ldlt32s: A2[c * 33 + i] = A[i][c]
+#pragma unroll
+  for (int q = 0; q < 8; ++q) A2[(8 * w + q) * 33 + lane] = a[q];
+  cta_ldlt32s(a, nbn, N.u, N.tiny, A2, Ln, order, pt, dinv_s, doff_s, gext_s, N.counters);
+  if (tlog) ts[4] = flog_now();
   const int mine = (lane < nbn) ? order[lane] : 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -1067,7 +1115,7 @@ __global__ void __launch_bounds__(128) k_big_chain(DevSym S, DevNum N, const int
       double v;
       if (lane < j) v = 0.0;
       else if (lane == j) v = 1.0;
-      else v = A2[mine * 33 + j];
+      else v = Ln[mine * 33 + j];
       P[(o + lane) + (size_t)(o + j) * f] = v;
     }
   }
@@ -1078,23 +1126,35 @@ __global__ void __launch_bounds__(128) k_big_chain(DevSym S, DevNum N, const int
     N.doff[c0 + o + lane] = doff_s[lane];
     N.ptype[c0 + o + lane] = pt[lane];
   }
+  if (tlog) { ts[5] = flog_now(); flog_put(N, 1, s, jbp, ts, 6); }
 }
 
-// rows below the diagonal block: W = A_perm * L_bb^-T (= L*D), L = W * D^-1.  One row per thread, the triangular
-// solve runs right-looking (x[q] -= x[t] L[q][t] for all q > t: independent FMAs, the block column read as double2).
-// CTAs with blockIdx.x >= nrowblk apply the block's row interchanges to the L columns on the left: one WARP per
-// column (the 32 rows of a column are one 256-byte segment; the permutation is a warp shuffle), TRSM_SWAP_COLS
-// columns per CTA.
+// --------------------------------------------------------------------------------------------
+// ONE launch per panel of the big fronts: k_big_panel(p), jb = first column of panel p.  Three CTA roles:
+//   blockIdx.x == 0               the chain role (chain_role above): LDL^T of diagonal block p+1
+//   1 .. nrowblk                  the rows below block p+1 (one row per thread), LEFT-LOOKING by one panel:
+//                                   a   = A[i, panel p] - L[i, panel p-1] * W[block p, panel p-1]^T     (the update of panel p-1)
+//                                   W   = a_perm * L_bb(p)^-T  (= L*D),   L = W * D^-1
+//                                 (right-looking triangular solve: x[q] -= x[t] L[q][t] for all q > t, independent FMAs)
+//   > nrowblk                     row interchanges of block p applied to the L columns on the left: one WARP per column
+//                                 (the 32 rows of a column are one 256-byte segment; the permutation is a warp shuffle)
+// All roles depend on the same two things -- the previous k_big_panel and the bulk update of panel p-2 -- and not on each
+// other, so the critical path of a front is ONE kernel per 32 pivots; the bulk rank-32 update (k_big_update) of a panel
+// has a whole chain step to complete.  k_big_panel(-NB) (chain role only) factors block 0.
+// --------------------------------------------------------------------------------------------
 #define TRSM_LD 34          // even leading dimension: column t of the block starts 16-byte aligned
 #define TRSM_SWAP_COLS 32   // columns per row-swap CTA (4 warps x 8)
-// The rows of the NEXT diagonal block (row0 .. row0+31) belong to the chain kernel (k_big_chain); this (bulk) kernel does
-// every other row below the block.
-__global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
-                                                  int nrowblk) {
+__global__ void __launch_bounds__(128) k_big_panel(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
+                                                   int nrowblk) {
+  extern __shared__ double csm[];
+  const int s = front_list[blockIdx.y];
+  if (blockIdx.x == 0) { chain_role(S, N, s, jb, csm); return; }
+  if (jb < 0) return;
   __shared__ __align__(16) double Lb[NB * TRSM_LD];
+  __shared__ __align__(16) double Wb[NB * TRSM_LD];   // Wb[t' * LD + t] = W[jb + bperm[t]][jbq + t']
   __shared__ double di[NB], dup[NB], dlo[NB];
   __shared__ int bp[NB];
-  const int s = front_list[blockIdx.y];
+  const int bx = (int)blockIdx.x - 1;
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
   if (jb >= k) return;
   const int f = k + (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
@@ -1102,11 +1162,11 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
   const int row0 = jb + nb;
   double* P = N.L + S.L_off[s];
   const int tid = threadIdx.x;
-  const int nxt = max(0, min(NB, k - row0));   // rows of the next diagonal block (pivot rows right below this block)
-  if ((int)blockIdx.x >= nrowblk) {
+  const int nxt = max(0, min(NB, k - row0));   // rows of the next diagonal block: the chain role's
+  if (bx >= nrowblk) {
     // ---- left part: rows jb..jb+nb of columns [0, jb) get the block permutation ----
     const int lane = tid & 31, warp = tid >> 5;
-    const int cbeg = ((int)blockIdx.x - nrowblk) * TRSM_SWAP_COLS;
+    const int cbeg = (bx - nrowblk) * TRSM_SWAP_COLS;
     if (cbeg >= jb) return;
     const int src = (lane < nb) ? N.bperm[c0 + jb + lane] : lane;
     double v[TRSM_SWAP_COLS / 4];
@@ -1123,11 +1183,29 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
     }
     return;
   }
-  if ((long long)blockIdx.x * blockDim.x >= f - row0 - nxt) return;
+  if ((long long)bx * blockDim.x >= f - row0 - nxt) return;
   double* Wp = N.W + S.L_off[s];
-  const int i = row0 + nxt + blockIdx.x * blockDim.x + tid;
+  const int i = row0 + nxt + bx * blockDim.x + tid;
   const bool active = i < f;
-  // issue all global loads up front: the diagonal block, its D, and this thread's row (columns in pivot order)
+  const bool has_q = jb >= NB;                 // there is a panel p-1 whose update this kernel applies
+  const int jbq = jb - NB;
+  unsigned long long ts[2];
+  const bool tlog = N.flog != nullptr && tid == 0 && (bx == 0 || (long long)(bx + 1) * blockDim.x >= f - row0 - nxt);
+  if (tlog) ts[0] = flog_now();
+  // issue all global loads up front: the diagonal block, its D, the W rows of this block at panel p-1 (permuted), and this
+  // thread's rows (panel p-1: L; panel p: A, columns in pivot order)
+  if (tid < NB) {
+    double d = 0.0, o = 0.0, om = 0.0;
+    int ty = 1, tym = 1, b = tid;
+    if (tid < nb) {
+      d = N.dinv[c0 + jb + tid]; o = N.doff[c0 + jb + tid]; ty = N.ptype[c0 + jb + tid]; b = N.bperm[c0 + jb + tid];
+      if (tid > 0) { om = N.doff[c0 + jb + tid - 1]; tym = N.ptype[c0 + jb + tid - 1]; }
+    }
+    di[tid] = d;
+    dup[tid] = (ty == 2) ? o : 0.0;                  // first column of a 2x2 pivot: + x[t+1] * offdiag
+    dlo[tid] = (ty == 3 && tym == 2) ? om : 0.0;      // second column:              + x[t-1] * offdiag
+    bp[tid] = b;
+  }
   {
     double lb[NB * NB / 128];
 #pragma unroll
@@ -1135,28 +1213,49 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
       const int t = tid + 128 * q, ii = t & (NB - 1), jj = t / NB;
       lb[q] = (ii < nb && jj < nb && ii > jj) ? P[(jb + ii) + (size_t)(jb + jj) * f] : 0.0;
     }
-    if (tid < NB) {
-      double d = 0.0, o = 0.0, om = 0.0;
-      int ty = 1, tym = 1, b = tid;
-      if (tid < nb) {
-        d = N.dinv[c0 + jb + tid]; o = N.doff[c0 + jb + tid]; ty = N.ptype[c0 + jb + tid]; b = N.bperm[c0 + jb + tid];
-        if (tid > 0) { om = N.doff[c0 + jb + tid - 1]; tym = N.ptype[c0 + jb + tid - 1]; }
-      }
-      di[tid] = d;
-      dup[tid] = (ty == 2) ? o : 0.0;                  // first column of a 2x2 pivot: + x[t+1] * offdiag
-      dlo[tid] = (ty == 3 && tym == 2) ? om : 0.0;      // second column:              + x[t-1] * offdiag
-      bp[tid] = b;
-    }
 #pragma unroll
     for (int q = 0; q < NB * NB / 128; ++q) {
       const int t = tid + 128 * q, ii = t & (NB - 1), jj = t / NB;
       Lb[ii + jj * TRSM_LD] = lb[q];
     }
   }
-  __syncthreads();
+  __syncthreads();   // bp
+  if (has_q) {
+    double wb[NB * NB / 128];
+#pragma unroll
+    for (int q = 0; q < NB * NB / 128; ++q) {
+      const int t = tid + 128 * q, ii = t & (NB - 1), jj = t / NB;     // ii = position in the block (pivot order), jj = t'
+      wb[q] = (ii < nb) ? Wp[(jb + bp[ii]) + (size_t)(jbq + jj) * f] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < NB * NB / 128; ++q) {
+      const int t = tid + 128 * q, ii = t & (NB - 1), jj = t / NB;
+      Wb[ii + jj * TRSM_LD] = wb[q];
+    }
+  }
   double x[NB];
 #pragma unroll
   for (int t = 0; t < NB; ++t) x[t] = (active && t < nb) ? P[i + (size_t)(jb + bp[t]) * f] : 0.0;
+  __syncthreads();
+  if (has_q) {
+    // the rank-32 update of panel p-1 on this row (fixed summation order t' = 0..31)
+#pragma unroll
+    for (int t8 = 0; t8 < NB; t8 += 8) {
+      double lq[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) lq[u] = active ? P[i + (size_t)(jbq + t8 + u) * f] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double* __restrict__ wr = Wb + (t8 + u) * TRSM_LD;
+#pragma unroll
+        for (int t = 0; t < NB; t += 2) {
+          const double2 w2 = *reinterpret_cast<const double2*>(wr + t);
+          x[t] = fma(-lq[u], w2.x, x[t]);
+          x[t + 1] = fma(-lq[u], w2.y, x[t + 1]);
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int t = 0; t < NB - 1; ++t) {
     const double xt = x[t];
@@ -1186,41 +1285,34 @@ __global__ void __launch_bounds__(128) k_big_trsm(DevSym S, DevNum N, const int*
       if (t < nb) { Wp[i + (size_t)(jb + t) * f] = x[t]; P[i + (size_t)(jb + t) * f] = l[t]; }
   }
   if (active && lmax > lim) atomicAdd(N.counters + CNT_GROWTH, 1);
+  if (tlog) { ts[1] = flog_now(); flog_put(N, 2, s, jb, ts, 2); }
 }
 
 #define TM 64
 #define TK 16
-// trailing update of the remaining pivot columns after panel jb: C -= L_panel * W_panel^T (rank NB), 64x64 tiles.
-// One k-step (the whole rank-32 slab of both operands in shared memory); the C tile is prefetched before the
-// contraction so its latency overlaps the FMAs.  Skips the next diagonal block (k_big_trsm's CTA 0 updates it) and
-// records the column maxima of the panel AFTER next below its diagonal block (reduced per warp: one atomic per
-// column and warp instead of one per entry).
-// with_cb != 0: the same launch also applies the panel's rank-nb update to the contribution block (columns >= k of the
-// trailing matrix live in N.CB), so the Schur complement is complete when the last panel is done and rides in the
-// shadow of the diag/trsm chain instead of a separate GEMM at the end of the level.
-// jt_off: first tile column of this launch (the update of a panel is issued as tile column 0 -- the columns the next
-// k_big_trsm reads -- and then the rest).
-__global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const int* __restrict__ front_list, int jb,
-                                                    int with_cb, int jt_off) {
+// Bulk trailing update of panel jb (= panel p): C -= L_panel * W_panel^T (rank NB) on the pivot columns from panel p+2 on
+// (the columns of panel p+1 get this update inside k_big_panel(p+1), left-looking), lower 64x64 tiles.  One k-step (the
+// whole rank-32 slab of both operands in shared memory); the C tile is prefetched before the contraction so its latency
+// overlaps the FMAs.  Skips diagonal block (p+2, p+2) (the chain role of k_big_panel(p+1) updates it) and records the
+// column maxima of panel p+3 below its diagonal block for the threshold test of chain step p+2 (reduced per warp: one
+// atomic per column and warp instead of one per entry).
+__global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
   __shared__ double As[NB][TM + 1];
   __shared__ double Bs[NB][TM + 1];
   const int s = front_list[blockIdx.z];
   const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
-  if (jb >= k) return;
+  const int o = jb + 2 * NB;                  // first row / column of the region
+  if (o >= k) return;
   const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const int f = k + r;
-  const int nb = min(NB, k - jb);
-  const int o = jb + nb;
-  const int M = f - o, Nk = k - o;            // trailing rows; remaining pivot columns (0 after the last panel)
-  const int Nn = with_cb ? M : Nk;            // columns covered by this launch
-  // with_cb == 2: contribution-block columns only (tile grid anchored at the 64-aligned column below k)
-  const int jbase = (with_cb == 2) ? (Nk / TM) * TM : 0;
-  const int i0 = jbase + blockIdx.x * TM, j0 = jbase + ((int)blockIdx.y + jt_off) * TM;
-  if (i0 >= M || j0 >= Nn || i0 + TM - 1 < j0) return;
-  const int jlo = (with_cb == 2) ? Nk : 0;    // first column this launch owns
+  const int M = f - o, Nk = k - o;            // rows below; remaining pivot columns
+  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TM;
+  if (i0 >= M || j0 >= Nk || i0 + TM - 1 < j0) return;
+  unsigned long long ts[2];
+  const bool tlog = N.flog != nullptr && threadIdx.x == 0 && j0 == 0 && (i0 == 0 || i0 + TM >= M);
+  if (tlog) ts[0] = flog_now();
   const long long ld = f;
   double* __restrict__ C = N.L + S.L_off[s] + o + (long long)o * ld;
-  double* __restrict__ CBp = N.CB + S.cb_off[s];
   const double* __restrict__ A = N.L + S.L_off[s] + o + (long long)jb * ld;
   const double* __restrict__ Bm = N.W + S.L_off[s] + o + (long long)jb * ld;
   double* colmax_next = N.colmax + c0 + o;
@@ -1230,8 +1322,8 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int t = tid + 256 * q, ii = t & (TM - 1), kk = t / TM;
-      av[q] = (i0 + ii < M && kk < nb) ? A[i0 + ii + (long long)kk * ld] : 0.0;
-      bv[q] = (j0 + ii < Nn && kk < nb) ? Bm[j0 + ii + (long long)kk * ld] : 0.0;
+      av[q] = (i0 + ii < M) ? A[i0 + ii + (long long)kk * ld] : 0.0;
+      bv[q] = (j0 + ii < Nk) ? Bm[j0 + ii + (long long)kk * ld] : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -1245,9 +1337,7 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int gi = i0 + tx + 16 * q, gj = j0 + ty + 16 * p;
-      double v = 0.0;
-      if (gi < M && gj < Nn && gi >= gj && gj >= jlo) v = (gj < Nk) ? C[gi + (long long)gj * ld] : CBp[(gi - Nk) + (long long)(gj - Nk) * r];
-      c[q][p] = v;
+      c[q][p] = (gi < M && gj < Nk && gi >= gj) ? C[gi + (long long)gj * ld] : 0.0;
     }
   __syncthreads();
 #pragma unroll 8
@@ -1268,16 +1358,15 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int gi = i0 + tx + 16 * q;
-      if (gi < M && gj < Nn && gi >= gj && gj >= jlo) {
-        if (gi < min(2 * NB, Nk) && gj < 2 * NB) continue;   // the tiles the chain kernel owns: blocks (p+1,p+1), (p+2,p+1), (p+2,p+2)
-        if (gj < Nk) C[gi + (long long)gj * ld] = c[q][p];
-        else CBp[(gi - Nk) + (long long)(gj - Nk) * r] = c[q][p];
-        if (gi >= 3 * NB) m = fmaxf(m, __double2float_ru(fabs(c[q][p])));
+      if (gi < M && gj < Nk && gi >= gj) {
+        if (gi < min(NB, Nk) && gj < NB) continue; // diagonal block (p+2, p+2): the chain role's
+        C[gi + (long long)gj * ld] = c[q][p];
+        if (gi >= 2 * NB) m = fmaxf(m, __double2float_ru(fabs(c[q][p])));
       }
     }
-    // columns [2NB, 3NB) of the trailing matrix are the diagonal block TWO chain steps ahead: the chain runs up to two
-    // panels ahead of this update, so a block's threshold maxima are the ones recorded two panels earlier.
-    if (j0 == TM && p < 2 && with_cb != 2) {   // (warp-uniform) columns 64..95 = the first 32 columns of the second tile column
+    // columns [NB, 2NB) of the region are diagonal block p+3: the chain runs up to two panels ahead of this update, so a
+    // block's threshold maxima are the ones recorded two panels earlier
+    if (j0 == 0 && p >= 2) {   // (warp-uniform)
       const float m_lo = wredux_max((lane < 16) ? m : 0.0f), m_hi = wredux_max((lane >= 16) ? m : 0.0f);
       if ((lane == 0 || lane == 16) && gj < Nk) {
         const float mm = (lane == 0) ? m_lo : m_hi;
@@ -1286,6 +1375,72 @@ __global__ void __launch_bounds__(256) k_big_update(DevSym S, DevNum N, const in
       }
     }
   }
+  if (tlog) { ts[1] = flog_now(); flog_put(N, 3, s, jb, ts, 2); }
+}
+
+// Contribution-block share of a panel's update: CB -= L21[:, panel] * W21[:, panel]^T (rank nb) on the lower 64x64 tiles of
+// the r x r contribution block.  Issued once per panel behind k_big_panel on its own stream, so the Schur complement of a
+// front is finished a few microseconds after its last panel instead of costing a GEMM at the end of the level (the chain
+// is latency-bound and leaves the SMs idle).  Panels are applied in stream order => deterministic.
+__global__ void __launch_bounds__(256) k_big_update_cb(DevSym S, DevNum N, const int* __restrict__ front_list, int jb) {
+  __shared__ double As[NB][TM + 1];
+  __shared__ double Bs[NB][TM + 1];
+  const int s = front_list[blockIdx.z];
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  if (jb >= k) return;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TM;
+  if (i0 >= r || j0 >= r || i0 + TM - 1 < j0) return;
+  const long long ld = k + r;
+  const int nb = min(NB, k - jb);
+  double* __restrict__ C = N.CB + S.cb_off[s];
+  const double* __restrict__ A = N.L + S.L_off[s] + k + (long long)jb * ld;
+  const double* __restrict__ Bm = N.W + S.L_off[s] + k + (long long)jb * ld;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  unsigned long long ts[2];
+  const bool tlog = N.flog != nullptr && tid == 0 && j0 == 0 && (i0 == 0 || i0 + TM >= r);
+  if (tlog) ts[0] = flog_now();
+  {
+    double av[8], bv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tid + 256 * q, ii = t & (TM - 1), kk = t / TM;
+      av[q] = (i0 + ii < r && kk < nb) ? A[i0 + ii + (long long)kk * ld] : 0.0;
+      bv[q] = (j0 + ii < r && kk < nb) ? Bm[j0 + ii + (long long)kk * ld] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tid + 256 * q, ii = t & (TM - 1), kk = t / TM;
+      As[kk][ii] = av[q]; Bs[kk][ii] = bv[q];
+    }
+  }
+  double c[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int gi = i0 + tx + 16 * q, gj = j0 + ty + 16 * p;
+      c[q][p] = (gi < r && gj < r && gi >= gj) ? C[gi + (long long)gj * r] : 0.0;
+    }
+  __syncthreads();
+#pragma unroll 8
+  for (int kk = 0; kk < NB; ++kk) {
+    double a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { a[q] = As[kk][tx + 16 * q]; b[q] = Bs[kk][ty + 16 * q]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) c[q][p] = fma(-a[q], b[p], c[q][p]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int gi = i0 + tx + 16 * q, gj = j0 + ty + 16 * p;
+      if (gi < r && gj < r && gi >= gj) C[gi + (long long)gj * r] = c[q][p];
+    }
+  if (tlog) { ts[1] = flog_now(); flog_put(N, 8, s, jb, ts, 2); }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1302,6 +1457,9 @@ __global__ void __launch_bounds__(128) k_big_schur84(DevSym S, DevNum N, const i
   const long long f = k + r;
   const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TM;
   if (i0 >= r || j0 >= r || i0 + TM - 1 < j0) return;
+  unsigned long long ts[2];
+  const bool tlog = N.flog != nullptr && threadIdx.x == 0 && j0 == 0 && (i0 == 0 || i0 + TM >= r);
+  if (tlog) ts[0] = flog_now();
   double* __restrict__ C = N.CB + S.cb_off[s];
   const double* __restrict__ A = N.L + S.L_off[s] + k;
   const double* __restrict__ Bm = N.W + S.L_off[s] + k;
@@ -1348,6 +1506,7 @@ __global__ void __launch_bounds__(128) k_big_schur84(DevSym S, DevNum N, const i
       const int gi = i0 + tx + 8 * q, gj = j0 + ty + 16 * p2;
       if (gi < r && gj < r && gi >= gj) C[gi + (long long)gj * r] -= acc[q][p2];
     }
+  if (tlog) { ts[1] = flog_now(); flog_put(N, 6, s, 0, ts, 2); }
 }
 
 }  // namespace b200

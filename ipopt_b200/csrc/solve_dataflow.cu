@@ -917,6 +917,7 @@ __global__ void __launch_bounds__(64) k_linv_diag(DevSym S, DevNum N, const int*
   const int r0 = b * 64, nd = min(64, k - r0);
   const double* __restrict__ P = N.L + S.L_off[s];
   const int tid = threadIdx.x;
+  FlogScope fs(N, 10, s, b);
   for (int t = tid; t < 64 * 64; t += 64) {
     const int i = t & 63, q = t >> 6;
     Ls[i + q * LI_LD] = (i < nd && q < nd && i > q) ? P[(r0 + i) + (size_t)(r0 + q) * f] : 0.0;
@@ -947,6 +948,7 @@ __global__ void __launch_bounds__(64) k_linv_diag(DevSym S, DevNum N, const int*
     const int i = t & 63, q = t >> 6;
     E[i + (long long)q * K64] = Ls[i + q * LI_LD];
   }
+  fs.done();
 }
 
 // 64x64 tile per CTA of 128 threads, 8x4 register blocking (rows tx+8q, columns ty+16p), k-slabs of 16 prefetched
@@ -958,6 +960,7 @@ __global__ void __launch_bounds__(128) k_linv_gemm(DevSym S, DevNum N, const Lin
   __shared__ double Bs[16][65];
   const LinvItem it = items[blockIdx.x];
   const int s = it.s;
+  FlogScope fs(N, 10 + PHASE, s, it.ib);
   const int k = S.sn_start[s + 1] - S.sn_start[s];
   const long long f = k + (S.rows_ptr[s + 1] - S.rows_ptr[s]);
   const long long K64 = (long long)((k + 63) / 64) * 64;
@@ -1019,6 +1022,7 @@ __global__ void __launch_bounds__(128) k_linv_gemm(DevSym S, DevNum N, const Lin
       if (PHASE == 1) { if (row < k && col < k) Wp[row + col * f] = acc[q][p]; }
       else Li[row + col * K64] = -acc[q][p];
     }
+  fs.done();
 }
 
 // ------------------------------------------------------------------------------------------------

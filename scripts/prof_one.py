@@ -1,7 +1,10 @@
 """One analyse + NF factorisations + NS solves of a synthetic MBndryCntrl1-shaped KKT (profiling target)."""
-import sys, time
+import sys, time, os
 import numpy as np
 sys.path.insert(0, ".")
+import ipopt_b200.capi as _capi
+if os.environ.get("B200_LIBDIR"):      # experiments: a differently configured build of the library
+    _capi.lib_path = lambda: os.path.join(os.environ["B200_LIBDIR"], "libb200ldlt.so")
 from ipopt_b200 import B200Ldlt
 from ipopt_b200.kkt import mbndry_kkt
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 400

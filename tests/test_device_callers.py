@@ -99,7 +99,7 @@ def test_assemble_matches_reference_fillvalues_and_refines(n_x, n_s, n_c, mode):
     x = db.cpu().numpy()
     r = b - A @ x
     rr = np.abs(r).max() / (min(np.abs(x).max(), 1e6 * np.abs(b).max()) + np.abs(b).max())
-    assert rr <= 1e-10 and abs(rr - ratio) <= 1e-3 * max(rr, 1e-16) + 1e-18
+    assert rr <= 1e-10 and abs(rr - ratio) <= 1e-3 * rr + 1e-15   # (at round-off level the two differ in the last digits)
     # host path on the same values: one solve + one numpy refinement step agrees
     xh = b.copy(); s.solve(xh)
     rh = b - A @ xh; s.solve(rh); xh += rh
