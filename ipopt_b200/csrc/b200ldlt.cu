@@ -51,7 +51,8 @@ struct LinvPlan {
   int ndiag = 0;
   std::vector<std::unique_ptr<DevBuf<LinvItem>>> d_g;   // per recursion level: the tile items (same list for both passes ...
   std::vector<std::unique_ptr<DevBuf<LinvItem>>> d_g2;  // ... up to the k-range)
-  std::vector<int> ng;
+  std::vector<int> ng, ng2;                // items per level (pass 1, pass 2: the chunking differs)
+  long long part_tiles = 0;                // scratch tiles (= counters) the chunked items of one launch need (max over launches)
 };
 
 // triangular-solve work of a set of fronts (solve_dataflow.cu): subtrees for k_solve_sub + task lists for k_solve_top
@@ -102,8 +103,11 @@ struct DebugSwitches {
     solve_timeline = getenv("B200_SOLVE_TIMELINE") != nullptr;
     factor_timeline = getenv("B200_FACTOR_TIMELINE") != nullptr;
     cb_at_end = getenv("B200_CB_AT_END") != nullptr;
-    if (const char* e = getenv("B200_BUCKETS"))
+    if (const char* e = getenv("B200_BUCKETS")) {
       for (const char* p = e; *p;) { buckets.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
+    } else {
+      buckets = {48, 96};   // the classes of a level run side by side, so a finer split costs no serial launches (measured: -0.1 ms at N=400)
+    }
   }
 };
 
@@ -163,6 +167,8 @@ struct Solver {
   DevBuf<double> d_bigv, d_bigy;
   DevBuf<unsigned long long> d_ticket, d_tlog, d_flog;
   DevBuf<double> d_linv;
+  DevBuf<double> d_linv_part;       // partial tiles of the chunked k_linv_gemm items (one launch at a time uses it)
+  DevBuf<int> d_linv_cnt;           // their arrival counters (self-resetting)
   DevBuf<long long> d_linv_off, d_gmap_off;
   DevBuf<FrontDesc> d_fdesc;
   DevBuf<int> d_gmap;
@@ -295,7 +301,7 @@ static void build_level_plans(const Symbolic& S, int smax, const std::vector<cha
     // fronts are split again at the soft limits below (shared memory per CTA follows the largest front of a launch,
     // so finer buckets raise the number of resident CTAs per SM); a soft split only happens once the current bucket
     // holds enough fronts to fill the GPU.
-    // (soft: measured at N=400 every extra launch costs more than the occupancy gains - no soft splits by default)
+    // (soft: splits at 48 and 96 by default, DebugSwitches::buckets)
     const int kMinBucket = 296;
     auto threads_of = [](int f) { return f > 64 ? 256 : (f > 32 ? 128 : 64); };
     LevelPlan::Bucket cur{(int)fl.size(), 0, 0, 0, 256, 0};
@@ -342,7 +348,7 @@ static int build_linv_plan(Solver* sv, const Symbolic& S, const std::vector<char
   LP.ndiag = (int)pairs.size() / 2;
   if (pairs.empty()) pairs.push_back(0);
   CU(LP.d_diag.upload(pairs, st));
-  LP.d_g.clear(); LP.d_g2.clear(); LP.ng.clear();
+  LP.d_g.clear(); LP.d_g2.clear(); LP.ng.clear(); LP.ng2.clear(); LP.part_tiles = 0;
   for (int Bt = 1; Bt < maxkb; Bt *= 2) {   // merge neighbouring blocks of Bt tiles
     std::vector<LinvItem> g1, g2;
     for (int s = 0; s < S.nsn; ++s) if (take[s] && S.f(s) > kSolveMidMax) {
@@ -351,21 +357,40 @@ static int build_linv_plan(Solver* sv, const Symbolic& S, const std::vector<char
         const int a1 = a0 + Bt, b1 = std::min(a1 + Bt, nkb);   // first block [a0,a1), second [a1,b1)
         for (int ib = a1; ib < b1; ++ib)
           for (int jb = a0; jb < a1; ++jb) {
-            g1.push_back(LinvItem{s, ib, jb, jb, a1});        // T[ib,jb]    =  sum_{m=jb..a1-1} L[ib,m] Inv11[m,jb]
-            g2.push_back(LinvItem{s, ib, jb, a1, ib + 1});    // Linv[ib,jb] = -sum_{m=a1..ib}   Inv22[ib,m] T[m,jb]
+            g1.push_back(LinvItem{s, ib, jb, jb, a1, 1, 0, 0});        // T[ib,jb]    =  sum_{m=jb..a1-1} L[ib,m] Inv11[m,jb]
+            g2.push_back(LinvItem{s, ib, jb, a1, ib + 1, 1, 0, 0});    // Linv[ib,jb] = -sum_{m=a1..ib}   Inv22[ib,m] T[m,jb]
           }
       }
     }
-    // longest items first (the launch ends with its slowest tile)
-    auto longer = [](const LinvItem& x, const LinvItem& y) { return (x.m1 - x.m0) > (y.m1 - y.m0); };
-    std::stable_sort(g1.begin(), g1.end(), longer);
-    std::stable_sort(g2.begin(), g2.end(), longer);
+    // long k-ranges -> chunks of LINV_KCHUNK tiles (partial sums combined by the last chunk to arrive, in chunk order)
+    auto split = [&](std::vector<LinvItem>& g) {
+      std::vector<LinvItem> out;
+      int base = 0;                          // first scratch tile (and counter index) of the item being cut
+      for (const LinvItem& it : g) {
+        const int K = it.m1 - it.m0, nch = (K + LINV_KCHUNK - 1) / LINV_KCHUNK;
+        if (nch <= 1) { out.push_back(it); continue; }
+        for (int c = 0; c < nch; ++c)
+          out.push_back(LinvItem{it.s, it.ib, it.jb, it.m0 + c * LINV_KCHUNK, std::min(it.m1, it.m0 + (c + 1) * LINV_KCHUNK), nch, c, base});
+        base += nch;
+      }
+      LP.part_tiles = std::max<long long>(LP.part_tiles, base);
+      g.swap(out);
+    };
+    split(g1);
+    split(g2);
     LP.ng.push_back((int)g1.size());
-    if (g1.empty()) { g1.push_back(LinvItem{0, 0, 0, 0, 0}); g2.push_back(LinvItem{0, 0, 0, 0, 0}); }
+    if (g1.empty()) { g1.push_back(LinvItem{0, 0, 0, 0, 0, 1, 0, 0}); g2.push_back(LinvItem{0, 0, 0, 0, 0, 1, 0, 0}); }
+    LP.ng2.push_back((int)g2.size());
     LP.d_g.emplace_back(new DevBuf<LinvItem>());
     LP.d_g2.emplace_back(new DevBuf<LinvItem>());
     CU(LP.d_g.back()->upload(g1, st));
     CU(LP.d_g2.back()->upload(g2, st));
+  }
+  if ((size_t)LP.part_tiles > sv->d_linv_cnt.n) {     // (analysis time: never inside a captured graph)
+    CU(cudaStreamSynchronize(st));
+    CU(sv->d_linv_part.alloc((size_t)LP.part_tiles * 4096));
+    CU(sv->d_linv_cnt.alloc((size_t)LP.part_tiles));
+    CU(cudaMemset(sv->d_linv_cnt.p, 0, sv->d_linv_cnt.n * sizeof(int)));
   }
   return B200LDLT_SUCCESS;
 }
@@ -990,8 +1015,8 @@ static int enqueue_linv(Solver* sv, const LinvPlan& LP, cudaStream_t st) {
   k_linv_diag<<<LP.ndiag, 64, 0, st>>>(sv->DS, sv->DN, LP.d_diag.p, sv->d_linv_off.p, sv->d_linv.p); ++L;
   for (size_t l = 0; l < LP.ng.size(); ++l) {
     if (LP.ng[l] <= 0) continue;
-    k_linv_gemm<1><<<LP.ng[l], 128, 0, st>>>(sv->DS, sv->DN, LP.d_g[l]->p, sv->d_linv_off.p, sv->d_linv.p); ++L;
-    k_linv_gemm<2><<<LP.ng[l], 128, 0, st>>>(sv->DS, sv->DN, LP.d_g2[l]->p, sv->d_linv_off.p, sv->d_linv.p); ++L;
+    k_linv_gemm<1><<<LP.ng[l], 128, 0, st>>>(sv->DS, sv->DN, LP.d_g[l]->p, sv->d_linv_off.p, sv->d_linv.p, sv->d_linv_part.p, sv->d_linv_cnt.p); ++L;
+    k_linv_gemm<2><<<LP.ng2[l], 128, 0, st>>>(sv->DS, sv->DN, LP.d_g2[l]->p, sv->d_linv_off.p, sv->d_linv.p, sv->d_linv_part.p, sv->d_linv_cnt.p); ++L;
   }
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;

@@ -781,6 +781,16 @@ __global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_
   }
 }
 
+// Reciprocal on the pivot chain: MUFU.RCP64H seed (>= 20 bits) + one cubically convergent correction = 3 dependent FMAs
+// instead of the 5 (+ range checks) of the correctly rounded 1.0 / d; the result is within ~1 ulp.  d must be a normal number.
+__device__ __forceinline__ double fast_rcp(const double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  e = fma(e, e, e);
+  return fma(r, e, r);
+}
+
 // --------------------------------------------------------------------------------------------
 // cta_ldlt32s: pivoted LDL^T of a symmetric block of order f <= 32 (all f columns are candidates) by FOUR warps -- the
 // diagonal blocks of the big fronts are the serial chain of the factorisation, so what counts is the latency of ONE pivot
@@ -801,7 +811,8 @@ __global__ void k_big_colmax0(DevSym S, DevNum N, const int* __restrict__ front_
 __device__ void cta_ldlt32s(double (&a)[8], const int f, const double u, const double tiny,
                             double* __restrict__ As, double* __restrict__ Lraw, int* __restrict__ order, int* __restrict__ pt,
                             double* __restrict__ dinv_s, double* __restrict__ doff_s, const double* __restrict__ gext_s,
-                            int* counters) {
+                            int* counters, unsigned long long* prof = nullptr /* debug: [0] fast steps<<40|cycles, [1] other steps<<40|cycles */) {
+  unsigned long long pf_fast = 0, pf_slow = 0; long long pf_t0 = 0; bool pf_pending = false;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned cand = (f >= 32) ? 0xffffffffu : ((1u << f) - 1u);
   unsigned parked = 0;
@@ -811,6 +822,11 @@ __device__ void cta_ldlt32s(double (&a)[8], const int f, const double u, const d
   int my_order = 0, my_pt = 1;
   double my_dinv = 0.0, my_doff = 0.0;
   const unsigned lbit = 1u << lane;
+  // The pivot TESTS run in float arithmetic first, with every rounding on the safe side (a double-precision operation has
+  // ~10x the latency of a float one on this part, and a step is a chain of dependent operations): a float test can PROVE an
+  // inequality of the exact test true or false; whenever it cannot, the exact double-precision sequence decides.
+  const float tiny_up = __double2float_ru(tiny), u_up = __double2float_ru(u);
+  const float alpha_up = __double2float_ru(BK_ALPHA), alpha_dn = __double2float_rd(BK_ALPHA);
   // 1x1 pivot: pivot column values pc (lane = row), pivot dd with reciprocal rinv, column g, pr[q] = A[8w+q][g]
   auto apply1 = [&](const double pc, const double dd, const double rinv, const int g, const double (&pr)[8]) {
     const double l = ((cand & lbit) && lane != g) ? pc * rinv : 0.0;
@@ -836,10 +852,14 @@ __device__ void cta_ldlt32s(double (&a)[8], const int f, const double u, const d
       avail = cand;
     }
     const int g0 = __ffs(avail) - 1;
+    if (prof) {
+      const long long now = clock64();
+      if (pf_pending) pf_slow += (1ull << 40) + (unsigned long long)(now - pf_t0);
+      pf_t0 = now; pf_pending = true;
+    }
     __syncthreads();                                   // the previous step's column stores are visible
     const double* __restrict__ cA = As + g0 * 33;
-    // everything a 1x1 pivot on g0 needs is loaded (and its reciprocal started) before the search: the loads and the
-    // division overlap the reduction instead of following the decision
+    // everything a 1x1 pivot on g0 needs is loaded (and its reciprocal started) before the search
     const double a0 = cA[lane];                        // A[lane][g0]
     const double pa0 = cA[g0];
     const double gam = gext_s[g0];
@@ -849,62 +869,86 @@ __device__ void cta_ldlt32s(double (&a)[8], const int f, const double u, const d
     const bool me_cand = (cand & lbit) != 0u;
     const float v0f = __double2float_ru(fabs(a0));
     const float lam_in = (me_cand && lane != g0) ? v0f : -1.0f;
-    const float lamf = wredux_max(lam_in);
-    const double rinv0 = 1.0 / pa0;                    // (issued behind the reduction: its latency overlaps the division)
+    const float lamf = wredux_max(lam_in);             // >= the exact maximum lam
+    const double rinv0 = fast_rcp(pa0);                // (issued behind the reduction: the two latencies overlap)
     const double ajj = fabs(pa0);
-    const double lamd = (lamf < 0.0f) ? 0.0 : (double)lamf;     // >= the exact maximum
-    if (!forced && (ajj > tiny) && (ajj >= u * fmax(lamd, gam)) && (ajj >= BK_ALPHA * lamd)) {
-      apply1(a0, pa0, rinv0, g0, pr0);
+    const float ajj_dn = __double2float_rd(ajj), ajj_up = __double2float_ru(ajj);
+    const float gam_up = __double2float_ru(gam), lam_up = fmaxf(lamf, 0.0f);
+    if (!forced && ajj_dn > tiny_up && ajj_dn >= __fmul_ru(u_up, fmaxf(lam_up, gam_up)) && ajj_dn >= __fmul_ru(alpha_up, lam_up)) {
+      apply1(a0, pa0, rinv0, g0, pr0);                 // proven: |pivot| > tiny, >= u * column max, >= alpha * lam
+      if (prof) { pf_fast += (1ull << 40) + (unsigned long long)(clock64() - pf_t0); pf_pending = false; }
       continue;
     }
     int r = -1;
+    if (lamf >= 0.0f) r = __ffs(__ballot_sync(0xffffffffu, lam_in == lamf)) - 1;
+    const float lam_lo = (lamf > 0.0f) ? nextafterf(lamf, 0.0f) : 0.0f;      // lam > lam_lo (lamf is lam rounded up)
+    // can the exact 1x1 test (ajj >= alpha * lam) still pass?  proven impossible when ajj_up < alpha_dn * lam_lo
+    const bool no_1x1 = !forced && r >= 0 && lam_lo > 0.0f && ajj_up < __fmul_rd(alpha_dn, lam_lo);
     double lam = 0.0;
-    if (lamf >= 0.0f) {
-      r = __ffs(__ballot_sync(0xffffffffu, lam_in == lamf)) - 1;
-      lam = fabs(cA[r]);                               // exact magnitude of the selected entry
+    bool ok1 = false;
+    if (!no_1x1) {
+      if (r >= 0) lam = fabs(cA[r]);                   // exact magnitude of the selected entry
+      ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
+      const double colmax_f = fmax(lam, gam);
+      if (forced) {
+        double dd = pa0;
+        const bool noise = !(fmax(ajj, colmax_f) > 1e-12);
+        if (noise || !(fabs(dd) > tiny)) { dd = (dd < 0.0) ? -1.5e-8 : 1.5e-8; ++c_tiny; }
+        else { dd = copysign(fmax(fabs(dd), 1e-8 * colmax_f), dd); ++c_forced; }
+        apply1(a0, dd, 1.0 / dd, g0, pr0);
+        continue;
+      }
+      if (lam == 0.0 || r < 0) {
+        if (ok1) apply1(a0, pa0, rinv0, g0, pr0);
+        else parked |= 1u << g0;
+        continue;
+      }
+      if (ok1 && ajj >= BK_ALPHA * lam) { apply1(a0, pa0, rinv0, g0, pr0); continue; }
     }
-    const bool ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam));
-    const double colmax_f = fmax(lam, gam);
-    if (forced) {
-      double dd = pa0;
-      const bool noise = !(fmax(ajj, colmax_f) > 1e-12);
-      if (noise || !(fabs(dd) > tiny)) { dd = (dd < 0.0) ? -1.5e-8 : 1.5e-8; ++c_tiny; }
-      else { dd = copysign(fmax(fabs(dd), 1e-8 * colmax_f), dd); ++c_forced; }
-      apply1(a0, dd, 1.0 / dd, g0, pr0);
-      continue;
-    }
-    if (lam == 0.0 || r < 0) {
-      if (ok1) apply1(a0, pa0, rinv0, g0, pr0);
-      else parked |= 1u << g0;
-      continue;
-    }
-    if (ok1 && ajj >= BK_ALPHA * lam) { apply1(a0, pa0, rinv0, g0, pr0); continue; }
     // ---- second column: the arg-max partner r ----
     const double* __restrict__ cB = As + r * 33;
     const double a1 = cB[lane];                        // A[lane][r]
     const double crr = cB[r];
     const double ge_r = gext_s[r];
+    const double pb = cA[r];                           // A[r][g0]  (|pb| = lam)
     double pr1[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) pr1[q] = cB[8 * w + q];   // A[8w+q][r]
+    const double det = pa0 * crr - pb * pb, adet = fabs(det);
+    const double idet = fast_rcp(det);                 // (started before the tests that decide whether it is used)
+    const double n1 = crr * a0 - pb * a1, n2 = pa0 * a1 - pb * a0;   // numerators of the two multipliers
     const float v1f = __double2float_ru(fabs(a1));
     const bool other = me_cand && lane != g0 && lane != r;
-    const double sig = (double)wredux_max((me_cand && lane != r) ? v1f : 0.0f);
-    double cjm = (double)wredux_max(other ? v0f : 0.0f), cr = (double)wredux_max(other ? v1f : 0.0f);
-    cr = fmax(cr, ge_r); cjm = fmax(cjm, gam);
+    const float sigf = wredux_max((me_cand && lane != r) ? v1f : 0.0f);
+    const float cjf = fmaxf(wredux_max(other ? v0f : 0.0f), gam_up);
+    const float crf = fmaxf(wredux_max(other ? v1f : 0.0f), __double2float_ru(ge_r));
     const double arr = fabs(crr);
-    const double pb = cA[r];                           // A[r][g0]
-    // Of the two columns read in this step one may stay alive (1x1 on g0 or on r) and is then rewritten by its owner:
-    // every warp must have finished reading before any store.  (The paths above only read column g0, which dies.)
-    __syncthreads();
-    const double det = pa0 * crr - pb * pb, adet = fabs(det);
-    const double idet = 1.0 / det;                     // (started before the tests that decide whether it is used)
-    if (ok1 && ajj * sig >= BK_ALPHA * lam * lam) { apply1(a0, pa0, rinv0, g0, pr0); continue; }
-    if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, ge_r)) { apply1(a1, crr, 1.0 / crr, r, pr1); continue; }   // 1x1 on r
-    if (lam > tiny && adet > 0.0 && isfinite(adet) &&
-        (arr * cjm + fabs(pb) * cr) * u <= adet && (ajj * cr + fabs(pb) * cjm) * u <= adet) {
-      const double l1 = other ? (crr * a0 - pb * a1) * idet : 0.0;
-      const double l2 = other ? (pa0 * a1 - pb * a0) * idet : 0.0;
+    bool take22 = false;
+    {
+      // float proof of the common outcome: the two 1x1 alternatives of the 2x2 branch fail and the 2x2 threshold test passes
+      const float arr_up = __double2float_ru(arr), pb_up = __double2float_ru(fabs(pb)), adet_dn = __double2float_rd(adet);
+      const float sig_lo = (sigf > 0.0f) ? nextafterf(sigf, 0.0f) : 0.0f;
+      const bool sig_fails = no_1x1 ? (__fmul_ru(ajj_up, sigf) < __fmul_rd(alpha_dn, __fmul_rd(lam_lo, lam_lo))) : false;
+      const bool r_fails = arr_up < __fmul_rd(alpha_dn, sig_lo) || arr_up <= 0.0f;
+      const float lhs1 = __fmul_ru(__fmaf_ru(arr_up, cjf, __fmul_ru(pb_up, crf)), u_up);
+      const float lhs2 = __fmul_ru(__fmaf_ru(ajj_up, crf, __fmul_ru(pb_up, cjf)), u_up);
+      take22 = sig_fails && r_fails && lam_lo > tiny_up && adet_dn > 0.0f && isfinite(adet) && lhs1 <= adet_dn && lhs2 <= adet_dn;
+    }
+    if (!take22) {
+      // exact sequence (identical decisions; reached when a float bound was inconclusive)
+      if (no_1x1) { lam = fabs(pb); ok1 = (ajj > tiny) && (ajj >= u * fmax(lam, gam)); }
+      const double sig = (double)sigf;
+      const double cjm = (double)cjf, cr = (double)crf;
+      // Of the two columns read in this step one stays alive when the pivot is 1x1 (on g0 or on r) and is then rewritten
+      // by its owner: in those two branches every warp must have finished reading before any store.
+      if (ok1 && ajj * sig >= BK_ALPHA * lam * lam) { __syncthreads(); apply1(a0, pa0, rinv0, g0, pr0); continue; }
+      if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, ge_r)) { __syncthreads(); apply1(a1, crr, 1.0 / crr, r, pr1); continue; }   // 1x1 on r
+      take22 = lam > tiny && adet > 0.0 && isfinite(adet) &&
+               (arr * cjm + fabs(pb) * cr) * u <= adet && (ajj * cr + fabs(pb) * cjm) * u <= adet;
+    }
+    if (take22) {
+      const double l1 = other ? n1 * idet : 0.0;
+      const double l2 = other ? n2 * idet : 0.0;
       cand &= ~((1u << g0) | (1u << r));
 #pragma unroll
       for (int q = 0; q < 8; ++q) a[q] = fma(-l2, pr1[q], fma(-l1, pr0[q], a[q]));
@@ -924,6 +968,10 @@ __device__ void cta_ldlt32s(double (&a)[8], const int f, const double u, const d
       continue;
     }
     parked |= 1u << g0;                                // nothing acceptable now: retry after the other candidates
+  }
+  if (prof) {
+    if (pf_pending) pf_slow += (1ull << 40) + (unsigned long long)(clock64() - pf_t0);
+    prof[0] = pf_fast; prof[1] = pf_slow;
   }
   if (w == 0) {
     if (lane < f) { order[lane] = my_order; pt[lane] = my_pt; dinv_s[lane] = my_dinv; doff_s[lane] = my_doff; }
@@ -1009,7 +1057,7 @@ __device__ void chain_role(const DevSym& S, const DevNum& N, const int s, const 
   double* __restrict__ P = N.L + S.L_off[s];
   double* __restrict__ Wp = N.W + S.L_off[s];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  unsigned long long ts[6];
+  unsigned long long ts[8];
   const bool tlog = N.flog != nullptr && tid == 0;
   if (tlog) ts[0] = flog_now();
   // ---- all global loads in flight at once (asynchronous copies straight into the tiles, zero-filled where masked) ----
@@ -1105,7 +1153,8 @@ __device__ void chain_role(const DevSym& S, const DevNum& N, const int s, const 
   __syncthreads();   // A2 becomes the full symmetric working copy of cta_ldlt32s: A2[c * 33 + i] = A[i][c]
 #pragma unroll
   for (int q = 0; q < 8; ++q) A2[(8 * w + q) * 33 + lane] = a[q];
-  cta_ldlt32s(a, nbn, N.u, N.tiny, A2, Ln, order, pt, dinv_s, doff_s, gext_s, N.counters);
+  __shared__ unsigned long long prof_s[2];
+  cta_ldlt32s(a, nbn, N.u, N.tiny, A2, Ln, order, pt, dinv_s, doff_s, gext_s, N.counters, tlog ? prof_s : nullptr);
   if (tlog) ts[4] = flog_now();
   const int mine = (lane < nbn) ? order[lane] : 0;
 #pragma unroll
@@ -1126,7 +1175,7 @@ __device__ void chain_role(const DevSym& S, const DevNum& N, const int s, const 
     N.doff[c0 + o + lane] = doff_s[lane];
     N.ptype[c0 + o + lane] = pt[lane];
   }
-  if (tlog) { ts[5] = flog_now(); flog_put(N, 1, s, jbp, ts, 6); }
+  if (tlog) { ts[5] = flog_now(); ts[6] = prof_s[0]; ts[7] = prof_s[1]; flog_put(N, 1, s, jbp, ts, 8); }
 }
 
 // --------------------------------------------------------------------------------------------

@@ -904,7 +904,12 @@ __device__ void big_bx(const DevSym& S, const DevNum& N, const DevSolve& V, cons
 //             columns, as two batched 64x64-tile GEMM passes (k_linv_gemm<1>: T = B A^-1 into the W scratch of the
 //             factorisation, k_linv_gemm<2>: -C^-1 T into Linv).  Work items are enumerated on the host at analysis.
 // ------------------------------------------------------------------------------------------------
-struct LinvItem { int s, ib, jb, m0, m1; };   // front, tile row / column (64-blocks), k-range of tiles [m0, m1)
+// front, tile row / column (64-blocks), k-range of tiles [m0, m1).  Long k-ranges are cut into nch chunks (this item is
+// chunk ci): the chunks write their partial tiles to scratch slot `slot` and the last one to arrive adds them up in chunk
+// order (deterministic) -- the launch then ends with a chunk, not with its longest dot product.  slot = first scratch tile
+// of the item (= index of its arrival counter).
+struct LinvItem { int s, ib, jb, m0, m1, nch, ci, slot; };
+#define LINV_KCHUNK 2     // tiles (of 64) per chunk
 
 #define LI_LD 66
 __global__ void __launch_bounds__(64) k_linv_diag(DevSym S, DevNum N, const int* __restrict__ pairs,
@@ -955,9 +960,11 @@ __global__ void __launch_bounds__(64) k_linv_diag(DevSym S, DevNum N, const int*
 // into registers while the current slab is consumed.
 template <int PHASE>
 __global__ void __launch_bounds__(128) k_linv_gemm(DevSym S, DevNum N, const LinvItem* __restrict__ items,
-                                                   const long long* __restrict__ linv_off, double* __restrict__ linv) {
+                                                   const long long* __restrict__ linv_off, double* __restrict__ linv,
+                                                   double* __restrict__ part, int* __restrict__ part_cnt) {
   __shared__ double As[16][65];
   __shared__ double Bs[16][65];
+  __shared__ int s_last;
   const LinvItem it = items[blockIdx.x];
   const int s = it.s;
   FlogScope fs(N, 10 + PHASE, s, it.ib);
@@ -1013,6 +1020,30 @@ __global__ void __launch_bounds__(128) k_linv_gemm(DevSym S, DevNum N, const Lin
         for (int p = 0; p < 4; ++p) acc[q][p] = fma(a[q], c[p], acc[q][p]);
     }
     __syncthreads();
+  }
+  if (it.nch > 1) {
+    // partial tile -> scratch; the last chunk to arrive sums all of them in chunk order
+    double* __restrict__ mine = part + ((size_t)it.slot + it.ci) * 4096;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) mine[(tx + 8 * q) + 64 * (ty + 16 * p)] = acc[q][p];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(part_cnt + it.slot, 1) == it.nch - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) { fs.done(); return; }
+    __threadfence();
+    if (tid == 0) part_cnt[it.slot] = 0;          // ready for the next factorisation
+    const double* __restrict__ base = part + (size_t)it.slot * 4096;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        double v = 0.0;
+        for (int c = 0; c < it.nch; ++c) v += __ldcg(base + (size_t)c * 4096 + (tx + 8 * q) + 64 * (ty + 16 * p));
+        acc[q][p] = v;
+      }
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q)

@@ -133,6 +133,7 @@ ESymSolverStatus B200LdltSolverInterface::InitializeStructure(Index dim, Index n
          return SYMSOLVER_FATAL_ERROR;
       }
       have_factors_ = false;
+      ++stats_.n_analyse;
       stats_.dim = dim;
       stats_.nonzeros = nonzeros;
    }

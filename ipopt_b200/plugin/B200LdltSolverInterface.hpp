@@ -58,6 +58,7 @@ public:
    struct Stats
    {
       int n_factor, n_solve, n_rhs, n_singular, n_wrong_inertia;
+      int n_analyse;   // InitializeStructure calls that handed a structure to the backend (not the kept ones of a warm start)
       double t_factor, t_solve, t_first_factor;
       int dim, nonzeros;
    };

@@ -27,7 +27,7 @@ pass
 names = {1: "chain", 2: "rows", 3: "update", 4: "front_smem", 5: "front_warp", 6: "schur", 7: "extend", 8: "cb_update", 10: "linv_diag", 11: "linv_g1", 12: "linv_g2"}
 # chain records carry the packed pivot-path statistics of the diagonal-block factorisation as a 7th word: not a time
 for r in recs:
-    if r[0] == 1 and len(r) > 12: r.append(("stats", r.pop(12)))
+    if r[0] == 1 and len(r) > 13: r.append(("prof", r.pop(12), r.pop(12)))
 def times(r): return [x for x in r[6:] if not isinstance(x, tuple)]
 t0 = min(min(times(r)) for r in recs)
 print("records", len(recs), " span %.1f us" % ((max(max(times(r)) for r in recs) - t0) / 1e3))
@@ -68,12 +68,11 @@ if ch:
             " ".join("%.1f..%.1f" % ((x[6] - t0) / 1e3, (x[7] - t0) / 1e3) for x in rr),
             " ".join("%.1f..%.1f" % ((x[6] - t0) / 1e3, (x[7] - t0) / 1e3) for x in uu)))
 if ch:
-    tot = np.zeros(8, int)
+    nf = cf = ns = cs = 0
     for r in ch:
         if isinstance(r[-1], tuple):
-            v = r[-1][1]
-            tot += np.array([(v >> (8 * i)) & 255 for i in range(8)])
-    print("pivot paths over %d chain steps: groups %d  fast1x1 %d  exact1x1 %d  sig1x1 %d  1x1-on-partner %d  2x2-adjacent %d  parked %d  generic steps %d" % ((len(ch),) + tuple(tot)))
+            nf += r[-1][1] >> 40; cf += r[-1][1] & ((1 << 40) - 1); ns += r[-1][2] >> 40; cs += r[-1][2] & ((1 << 40) - 1)
+    if nf + ns: print("diagonal LDL^T steps: fast 1x1 %d at %.0f cycles, other %d at %.0f cycles" % (nf, cf / max(nf, 1), ns, cs / max(ns, 1)))
 for kind in (2, 3, 4, 5, 6, 7, 8):
     d = [times(r)[-1] - r[6] for r in recs if r[0] == kind]
     if d: print("%-12s n=%5d mean %.2f us max %.2f us" % (names[kind], len(d), np.mean(d) / 1e3, np.max(d) / 1e3))

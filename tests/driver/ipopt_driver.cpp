@@ -123,6 +123,7 @@ int main(int argc, char** argv)
       openblas_set_num_threads(e ? atoi(e) : 1);
    }
    std::string backend = "b200", problem = "hs071", json_path, final_path, dump_prefix;
+   bool reopt = false;   // second solve of the same NLP with warm_start_same_structure=yes (ReOptimizeNLP)
    int N = 0, print_level = 5;
    std::vector<std::pair<std::string, std::string> > opts;
    std::vector<int> dump_which;
@@ -136,6 +137,7 @@ int main(int argc, char** argv)
       else if( s == "--final" && a + 1 < argc ) final_path = argv[++a];
       else if( s == "--print-level" && a + 1 < argc ) print_level = atoi(argv[++a]);
       else if( s == "--dump" && a + 1 < argc ) dump_prefix = argv[++a];
+      else if( s == "--reopt" ) reopt = true;
       else if( s == "--dump-iters" && a + 1 < argc )
       {
          char* p = argv[++a];
@@ -214,6 +216,16 @@ int main(int argc, char** argv)
    if( via_hsllib ) st = app->OptimizeTNLP(GetRawPtr(tnlp));
    else st = app->OptimizeNLP(nlp, builder);
    double total = wall_now() - t0;
+   int reopt_status = -99, reopt_iters = -1, n_factor_first = iface->GetStats().n_factor;
+   if( reopt && !via_hsllib )
+   {
+      // the reference's warm-start contract (IpMumpsSolverInterface.cpp:227-236): same structure => the adapter keeps its
+      // handle and symbolic analysis, InitializeStructure is answered without re-analysing
+      app->Options()->SetStringValue("warm_start_same_structure", "yes");
+      ApplicationReturnStatus st2 = app->ReOptimizeNLP(nlp);
+      reopt_status = (int) st2;
+      if( IsValid(app->Statistics()) ) reopt_iters = app->Statistics()->IterationCount();
+   }
 
    int iters = -1;
    double obj = 0;
@@ -223,9 +235,11 @@ int main(int argc, char** argv)
    snprintf(buf, sizeof(buf),
             "{\"backend\": \"%s\", \"problem\": \"%s\", \"N\": %d, \"status\": %d, \"iterations\": %d, \"objective\": %.17g, "
             "\"kkt_dim\": %d, \"kkt_nnz\": %d, \"n_factor\": %d, \"n_solve\": %d, \"n_rhs\": %d, \"n_singular\": %d, "
-            "\"n_wrong_inertia\": %d, \"t_first_factor_s\": %.6f, \"t_factor_s\": %.6f, \"t_solve_s\": %.6f, \"t_total_s\": %.6f, \"host_threads\": %d}",
+            "\"n_wrong_inertia\": %d, \"t_first_factor_s\": %.6f, \"t_factor_s\": %.6f, \"t_solve_s\": %.6f, \"t_total_s\": %.6f, \"host_threads\": %d, "
+            "\"n_analyse\": %d, \"reopt_status\": %d, \"reopt_iterations\": %d, \"n_factor_first\": %d}",
             via_hsllib ? "ma97-shim(b200-ldlt)" : be->name, problem.c_str(), N, (int) st, iters, obj, S.dim, S.nonzeros, S.n_factor, S.n_solve, S.n_rhs,
-            S.n_singular, S.n_wrong_inertia, S.t_first_factor, S.t_factor, S.t_solve, total, omp_get_max_threads());
+            S.n_singular, S.n_wrong_inertia, S.t_first_factor, S.t_factor, S.t_solve, total, omp_get_max_threads(),
+            S.n_analyse, reopt_status, reopt_iters, n_factor_first);
    printf("DRIVER_JSON %s\n", buf);
    if( !json_path.empty() ) { FILE* fp = fopen(json_path.c_str(), "w"); if( fp ) { fprintf(fp, "%s\n", buf); fclose(fp); } }
    if( !final_path.empty() )

@@ -249,7 +249,7 @@ def test_full_size_lukvle1():
 
 
 # ---- end-to-end through the reference's own IP loop (driver binary built where /root/reference exists) -------
-def _run_driver(backend, problem, N, tmp_path, opts=None):
+def _run_driver(backend, problem, N, tmp_path, opts=None, extra=()):
     if not os.path.exists(DRIVER):
         pytest.skip("tests/driver/ipopt_driver not built (needs /root/reference at build time)")
     js, fin = str(tmp_path / "r.json"), str(tmp_path / "f.bin")
@@ -258,6 +258,7 @@ def _run_driver(backend, problem, N, tmp_path, opts=None):
     cmd = [DRIVER, "--backend", backend, "--problem", problem, "--N", str(N), "--print-level", "0", "--json", js, "--final", fin]
     for k, v in (opts or {}).items():
         cmd += ["--opt", "%s=%s" % (k, v)]
+    cmd += list(extra)
     p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     with open(fin, "rb") as f:
@@ -418,3 +419,14 @@ def test_sharded_factor_solve_matches_single_gpu(world):
     assert st == SYMSOLVER_SUCCESS and neg == nc
     assert scaled_residual(dim, irn, jcn, val2, sh.solve(b), b) < 1e-13
     sh.close(); s.close()
+
+
+@pytest.mark.parametrize("problem,N", [("hs071", 0), ("MBndryCntrl1", 30)])
+def test_warm_start_same_structure_keeps_the_analysis(problem, N, tmp_path):
+    """Second solve of the same NLP with warm_start_same_structure=yes (ReOptimizeNLP): the adapter keeps its handle and
+    symbolic analysis (reference contract: IpMumpsSolverInterface.cpp:227-236), and the second solve converges like the first."""
+    summ, _ = _run_driver("b200", problem, N, tmp_path, extra=["--reopt"])
+    assert summ["status"] == 0 and summ["reopt_status"] == 0
+    assert summ["n_analyse"] == 1                                  # one InitializeStructure reached the backend, not two
+    assert summ["reopt_iterations"] == summ["iterations"]
+    assert summ["n_factor"] == 2 * summ["n_factor_first"]
