@@ -12,7 +12,7 @@ the single-GPU time of the same N=800 step measured in the same run and printed 
           b200ldlt_solve_device), CUDA events on the launching stream, max over ranks.
   e2e   : the same through the reference-facing C-ABI calls with HOST buffers (b200ldlt_factor reads the pinned
           values array Ipopt fills, b200ldlt_solve takes/returns host rhs) -- H2D/D2H inside the timed region.
-  roofline : the HBM-bound triangular-solve sweeps (k_solve<fwd> + k_solve<bwd>): algorithmic bytes 2*8*nnz(L) +
+  roofline : the HBM-bound triangular solve (bottom-level kernels + the two persistent sweeps): algorithmic bytes 2*8*nnz(L) +
           vector traffic (SURVEY.md 8d) / their measured duration, against MEASURED_PEAKS.json's hbm_gbs;
           roofline_schur: the Schur-complement GEMM's pipe utilisation from the committed ncu export.
   cpu_baseline : the CPU oracle (oracle/cpu_ldlt.cpp, "port") on the host cores on the same matrix.  The reference's own
@@ -322,6 +322,26 @@ def main():
             ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_metrics.json")))
         except Exception:
             pass
+        # DRAM bytes of ONE solve (all its launches) and the pipe utilisation of the Schur-complement kernels, from the committed
+        # `ncu --set full` exports of this workload (profiles/r2_final_*_raw.csv, summarised in r2_ncu_metrics.json)
+        kern = ncu.get("kernels", {})
+        solve_traffic, solve_traffic_src, schur_entry = None, None, None
+        if dim == 321600 and kern.get("r2final_solve"):
+            solve_traffic = sum((r.get("dram_read_bytes") or 0) + (r.get("dram_write_bytes") or 0) for r in kern["r2final_solve"])
+            solve_traffic_src = "profiles/r2_r2final_solve_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum over the %d launches of one solve" % len(kern["r2final_solve"])
+        if kern.get("r2final_schur") or kern.get("r2e_tc"):
+            def pick(rows, name):
+                rows = [r for r in rows if name in r["kernel"]]
+                if not rows:
+                    return None
+                return {"launches": len(rows), "fp64_pipe_pct": float(np.mean([r.get("fp64_pipe_pct") or 0 for r in rows])),
+                        "tensor_pipe_pct": float(np.mean([r.get("tensor_pipe_pct") or 0 for r in rows])),
+                        "mean_us": float(np.mean([r.get("duration_s") or 0 for r in rows]))}
+            schur_entry = {"default_path": "k_big_update_cb: FP64 DFMA rank-32 updates of the contribution block, one per panel, behind the pivot chain",
+                           "k_big_update_cb": pick(kern.get("r2final_schur", []), "k_big_update_cb"),
+                           "tensor_core_path_opt_in": "k_tc_schur: tcgen05.mma kind::i8 Ozaki split (tc_schur_min_r), MBndryCntrl1 N=800",
+                           "k_tc_schur": pick(kern.get("r2e_tc", []), "k_tc_schur"),
+                           "source": "profiles/r2_r2final_schur_raw.csv, profiles/r2_r2e_tc_raw.csv (sm__pipe_fp64_cycles_active / sm__pipe_tensor_cycles_active, % of peak)"}
         nnzL = info["nnz_L"]
         tri_bytes = 2 * 8 * nnzL + 8 * 4 * dim   # L streamed twice + 2 reads/2 writes of the vector
         ach = tri_bytes / (tri_ms * 1e-3) / 1e9
@@ -351,13 +371,12 @@ def main():
             "gpu_launches": launches_timed,
             "kkt_factor_solve_ms_per_iter": {"device_resident": step_ms, "e2e_host_buffers": ms_e2e / K,
                                              "factor_ms": fac_ms, "solve_ms_per_rhs": tri_ms},
-            "roofline": {"kernel": "supernodal triangular solve sweeps (k_solve<fwd> + k_solve<bwd>: shared-memory subtree tasks + chunked big-front GEMV tasks, one persistent kernel per sweep)",
+            "roofline": {"kernel": "supernodal triangular solve, all launches of one right-hand side (k_rhs_in, k_solve_direct x2 levels, k_solve<fwd>, k_solve<bwd>, k_solve_direct x2, k_sol_out)",
                          "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": ncu.get("solve_dram_bytes_per_solve") if dim == ncu.get("dim") else None,
-                         "traffic_source": ncu.get("solve_source"),
+                         "traffic": solve_traffic, "traffic_source": solve_traffic_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_solve": tri_bytes},
-            "roofline_schur": ncu.get("schur"),
+            "roofline_schur": schur_entry,
             "factor": {"flops_panel": info["flops_panel"], "flops_schur": info["flops_schur"],
                        "gflops_achieved": (info["flops_panel"] + info["flops_schur"]) / (fac_ms * 1e-3) / 1e9,
                        "nnz_L": nnzL, "supernodes": info["nsupernodes"], "levels": info["nlevels"], "max_front": info["max_front"]},
@@ -467,7 +486,7 @@ def run_sharded(args, snaps, src, config, rank, local_rank, world, K, W, host_co
                 "vs_baseline": None, "dtype": "f64", "data": src, "config": cfg,
                 "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "iter/s", "ms_per_step": ms_e2e / K,
                         "h2d_bytes_per_step": world * 8 * nnz + 2 * world * 8 * dim, "d2h_bytes_per_step": 2 * 8 * dim + 32 * world},
-                "gpu_launches": K * (sh.ranks[0].s.info()["launches_factor"] + 2 * 4), "analysis_once_s": {"wall": t_analyse},
+                "gpu_launches": K * (sh.ranks[0].s.info()["launches_factor"] + 2 * 8), "analysis_once_s": {"wall": t_analyse},
                 "single_gpu": single, "speedup_vs_single_gpu": (single["ms_per_step"] / (ms_dev / K)) if single else None,
                 "parity": {"scaled_residual": r / (xi + bi)}, "clocks": sampler.summary(), "host_cores": host_cores}
         print(json.dumps(line))

@@ -60,9 +60,13 @@ struct SolvePlan {
   DevBuf<SolveTask> d_tf, d_tb;
   DevBuf<int> d_bundle, d_sub_meta, d_ccnt, d_subrow;
   DevBuf<SubDesc> d_subs;
+  DevBuf<int2> d_subpair;
+  DevBuf<int> d_sub_Loff;
+  std::vector<std::unique_ptr<DevBuf<int>>> d_direct;   // per bottom level: the fronts k_solve_direct owns
+  std::vector<int> direct_cnt;
   DevBuf<double> d_part;
   DevSolve V;
-  int nsub = 0, ntf = 0, ntb = 0;
+  int nsub = 0, npair = 0, ntf = 0, ntb = 0;
   long long sub_bytes = 0;
 };
 
@@ -70,7 +74,7 @@ struct LevelPlan {
   // big fronts of the level: [big_off, big_off+big_cnt) in front_list
   int big_off = 0, big_cnt = 0, big_kmax = 0, big_fmax = 0, big_rmax = 0, big_chmax = 0;
   long long big_entmax = 0, big_zero_max = 0;
-  struct Bucket { int off, cnt, fmax, kmax, threads; size_t smem; };
+  struct Bucket { int off, cnt, fmax, kmax, threads; size_t smem; int kind = 0; };   // kind 2: k_front_warp2 (order 33..64, <= 32 pivots)
   std::vector<Bucket> small;
   int all_off = 0, all_cnt = 0, fmax = 0;  // whole level (solve)
   // Schur complements of the level's big fronts: tensor-core (Ozaki int8, schur_tc.cu) for r >= tc_min_r, DFMA tiles else
@@ -95,6 +99,10 @@ struct DebugSwitches {
   bool one_stream = false;        // B200_ONE_STREAM=1: big-front pipeline on a single stream
   bool solve_timeline = false;    // B200_SOLVE_TIMELINE=1: per-task %globaltimer log of the top solve kernel
   bool cb_at_end = false;         // B200_CB_AT_END=1: Schur complements as one GEMM per level (k_big_schur84) instead of per-panel updates
+  int solve_direct = 2;           // B200_SOLVE_DIRECT=D: the D lowest tree levels are solved by k_solve_direct (0 = all inside the subtrees)
+  bool solve_nopair = false;      // B200_SOLVE_NOPAIR=1: one subtree per CTA in the solve sweeps (no side-by-side pairs)
+  bool no_warp2 = false;          // B200_NO_WARP2=1: fronts of order 33..64 by the shared-memory kernel (one CTA each) instead of k_front_warp2
+  bool no_pdl = false;            // B200_NO_PDL=1: chain kernels launched without programmatic dependent launch
   bool factor_timeline = false;   // B200_FACTOR_TIMELINE=1: %globaltimer records of the factorisation kernels (b200ldlt_dump_factor_timeline)
   std::vector<int> buckets;       // B200_BUCKETS=a,b,c: soft split points of the shared-memory front classes
   void read() {
@@ -103,6 +111,10 @@ struct DebugSwitches {
     solve_timeline = getenv("B200_SOLVE_TIMELINE") != nullptr;
     factor_timeline = getenv("B200_FACTOR_TIMELINE") != nullptr;
     cb_at_end = getenv("B200_CB_AT_END") != nullptr;
+    solve_nopair = getenv("B200_SOLVE_NOPAIR") != nullptr;
+    if (const char* e = getenv("B200_SOLVE_DIRECT")) solve_direct = atoi(e);
+    no_pdl = getenv("B200_NO_PDL") != nullptr;
+    no_warp2 = getenv("B200_NO_WARP2") != nullptr;
     if (const char* e = getenv("B200_BUCKETS")) {
       for (const char* p = e; *p;) { buckets.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
     } else {
@@ -124,6 +136,7 @@ struct Solver {
   size_t ev_next = 0;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_zero = nullptr;
+  cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};   // D2H chunks of the host solve path
 
   int n = 0, nnz = 0;
   std::vector<int> irn, jcn;
@@ -176,6 +189,7 @@ struct Solver {
   std::vector<std::unique_ptr<LinvPlan>> linv_level;   // the same work, split by tree level (issued behind each level's chain)
   std::vector<SolveTask> h_tasks;   // fwd then bwd (debug timeline)
   SolvePlan splan;                  // all fronts
+  std::vector<char> solve_direct_front;   // per supernode: solved by k_solve_direct (see build_solve_tables)
   int solve_epoch = 0, df_grid = 0;
   unsigned long long ticket_f = 0, ticket_b = 0;
   int num_sms = 148;
@@ -202,6 +216,7 @@ struct Solver {
     if (h_counters) cudaFreeHost(h_counters);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (cudaEvent_t e : ev_chunk) if (e) cudaEventDestroy(e);
     if (fgraph_exec) cudaGraphExecDestroy(fgraph_exec);
     if (fgraph) cudaGraphDestroy(fgraph);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
@@ -244,7 +259,8 @@ struct Solver {
 
 // per level: big fronts first, then the shared-memory classes by descending front order; only fronts with take[s]
 static void build_level_plans(const Symbolic& S, int smax, const std::vector<char>& take, std::vector<int>& fl,
-                              std::vector<LevelPlan>& plan, const std::vector<int>& soft, SchurLists& SL, int tc_min_r) {
+                              std::vector<LevelPlan>& plan, const std::vector<int>& soft, SchurLists& SL, int tc_min_r,
+                              bool use_warp2) {
   SL.f.clear(); SL.t.clear(); SL.dfl.clear(); SL.dig_bytes = 0; SL.exp_ints = 0;
   fl.clear();
   fl.reserve(S.nsn);
@@ -306,16 +322,19 @@ static void build_level_plans(const Symbolic& S, int smax, const std::vector<cha
     auto threads_of = [](int f) { return f > 64 ? 256 : (f > 32 ? 128 : 64); };
     LevelPlan::Bucket cur{(int)fl.size(), 0, 0, 0, 256, 0};
     int cur_lo = 1 << 30;   // the current bucket accepts f > cur_lo ... (set when the bucket gets its first front)
+    std::vector<int> w2;    // order 33..64 with <= 32 pivot columns: register kernel, two rows per lane
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
       int s = S.level_sn[q];
       int f = S.f(s);
       if (!take[s] || f > smax) continue;
+      if (use_warp2 && f > 32 && f <= 64 && S.k(s) <= 32) { w2.push_back(s); continue; }
       bool split = false;
       if (cur.cnt) {
         if (threads_of(f) != cur.threads) split = true;
         else if (cur.cnt >= kMinBucket && f <= cur_lo) split = true;
       }
       if (split) { P.small.push_back(cur); cur = LevelPlan::Bucket{(int)fl.size(), 0, 0, 0, 256, 0}; }
+      if (cur.cnt == 0) cur.off = (int)fl.size();
       if (cur.cnt == 0) {
         cur.threads = threads_of(f);
         cur_lo = 0;
@@ -330,6 +349,12 @@ static void build_level_plans(const Symbolic& S, int smax, const std::vector<cha
     for (auto& bk : P.small) {
       size_t ld = (size_t)(bk.fmax | 1);
       bk.smem = (ld * bk.fmax + 2 * (size_t)bk.fmax) * sizeof(double) + (2 * (size_t)bk.kmax + 8) * sizeof(int);
+    }
+    if (!w2.empty()) {
+      LevelPlan::Bucket bk{(int)fl.size(), (int)w2.size(), 64, 32, 128, 4 * (size_t)S2_SMEM_PER_WARP};
+      bk.kind = 2;
+      for (int s : w2) fl.push_back(s);
+      P.small.insert(P.small.begin(), bk);     // the most numerous class first (it gets the main stream when there are no big fronts)
     }
     P.all_cnt = (int)fl.size() - P.all_off;
   }
@@ -410,10 +435,18 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
     const int p = S.sn_parent[s];
     if (p >= 0) { size[p] += size[s]; ntaken[p] += ntaken[s]; subF[p] = std::max(subF[p], subF[s]); }
   }
+  const std::vector<char>& direct = sv->solve_direct_front;
+  // compact panel bytes of the fronts of [s0, s] that are walked inside a subtree (not owned by the direct kernel)
+  std::vector<long long> ownL(nsn + 1, 0);   // prefix sums over supernodes
+  std::vector<int> ownN(nsn + 1, 0);
+  for (int q = 0; q < nsn; ++q) {
+    ownL[q + 1] = ownL[q] + (direct[q] ? 0 : S.L_off[q + 1] - S.L_off[q]);
+    ownN[q + 1] = ownN[q] + (direct[q] ? 0 : 1);
+  }
   auto layout_of = [&](int s) {
     const int s0 = s - size[s] + 1;
     SubLayout L;
-    L.nL = S.L_off[s + 1] - S.L_off[s0];
+    L.nL = ownL[s + 1] - ownL[s0];
     L.ncol = S.sn_start[s + 1] - S.sn_start[s0];
     L.nrt = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s0]);
     L.rroot = S.r(s);
@@ -425,6 +458,7 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
   auto ok = [&](int s) {
     if (!take[s] || ntaken[s] != size[s] || subF[s] > DF_MIDMAX || size[s] > 4096) return false;
     if (s - size[s] + 1 < 0) return false;
+    if (direct[s]) return false;        // (then the whole subtree is direct: nothing to walk)
     return layout_of(s).bytes() <= (long long)DF_DYN_SMEM;
   };
   std::vector<char> okv(nsn);
@@ -440,17 +474,21 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
   }
   // largest subtree (bytes of L) first
   std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) {
-    return S.L_off[a + 1] - S.L_off[a - size[a] + 1] > S.L_off[b + 1] - S.L_off[b - size[b] + 1];
+    return ownL[a + 1] - ownL[a - size[a] + 1] > ownL[b + 1] - ownL[b - size[b] + 1];
   });
+  std::vector<int> subLoff(std::max(nsn, 1), 0);
   const int nsub = (int)roots.size();
   std::vector<SubDesc> subs(std::max(nsub, 1), SubDesc{});
   std::vector<int> meta;
   SP.sub_bytes = 0;
   for (int u = 0; u < nsub; ++u) {
     const int sR = roots[u], s0 = sR - size[sR] + 1;
-    SP.sub_bytes += (S.L_off[sR + 1] - S.L_off[s0]) * 8;
-    std::vector<int> M(size[sR]);
-    for (int q = 0; q < size[sR]; ++q) M[q] = s0 + q;
+    SP.sub_bytes += (ownL[sR + 1] - ownL[s0]) * 8;
+    std::vector<int> M;
+    for (int q = s0; q <= sR; ++q) {
+      subLoff[q] = (int)(ownL[q] - ownL[s0]);
+      if (!direct[q]) M.push_back(q);
+    }
     // by (level, small first, larger first)
     std::stable_sort(M.begin(), M.end(), [&](int a, int b) {
       if (S.sn_level[a] != S.sn_level[b]) return S.sn_level[a] < S.sn_level[b];
@@ -472,13 +510,37 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
       d.nrt = (int)(S.rows_ptr[sR + 1] - S.rows_ptr[s0]); d.rroot = S.r(sR);
       d.ch00 = S.child_ptr[s0]; d.nchi = S.child_ptr[sR + 1] - S.child_ptr[s0];
       d.parent = S.sn_parent[sR];
-      d.L0 = S.L_off[s0]; d.nL = S.L_off[sR + 1] - S.L_off[s0]; d.ro0 = S.rows_ptr[s0];
+      d.nL = ownL[sR + 1] - ownL[s0]; d.ro0 = S.rows_ptr[s0]; d.nown = (int)M.size();
+      d.sbytes = (int)((layout_of(sR).bytes() + 127) / 128 * 128);
       subs[u] = d;
     }
     meta.insert(meta.end(), lvl.begin(), lvl.end());
     meta.insert(meta.end(), nsm.begin(), nsm.end());
     meta.insert(meta.end(), M.begin(), M.end());
   }
+  // Work items of the subtree phase.  The walk of one subtree is latency-bound (a few fronts per level, dependent
+  // shuffle chains) and most subtrees need less than half of the shared memory, so two of them share a CTA whenever their
+  // layouts fit together: the largest unpaired subtree takes the smallest one that still fits (both halves of the CTA
+  // work independently).  Items are issued by decreasing panel bytes (the hardware scheduler then does LPT).
+  std::vector<int2> pairs;
+  {
+    int lo = 0, hi = nsub - 1;      // subs[] is sorted by decreasing panel size
+    const bool pairing = !sv->dbg.solve_nopair;
+    while (lo <= hi) {
+      if (pairing && lo < hi && (long long)subs[lo].sbytes + subs[hi].sbytes <= (long long)DF_DYN_SMEM) {
+        pairs.push_back(make_int2(lo, hi)); ++lo; --hi;
+      } else {
+        pairs.push_back(make_int2(lo, -1)); ++lo;
+      }
+    }
+    std::stable_sort(pairs.begin(), pairs.end(), [&](const int2& a, const int2& b) {
+      const long long wa = subs[a.x].nL + (a.y >= 0 ? subs[a.y].nL : 0), wb = subs[b.x].nL + (b.y >= 0 ? subs[b.y].nL : 0);
+      return wa > wb;
+    });
+  }
+  SP.npair = (int)pairs.size();
+  if (pairs.empty()) pairs.push_back(make_int2(0, -1));
+  CU(SP.d_subpair.upload(pairs, st));
   // backward addresses of the contribution rows of the subtree fronts: a row inside the subtree's column range is a local
   // index into its x slice (>= 0); a row above it is one of the ROOT's contribution rows (every row of a descendant
   // beyond the root's columns is in the root's row list): -(1 + position there)
@@ -522,7 +584,7 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
       for (int phase = 0; phase < 2; ++phase)
         for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
           const int s = S.level_sn[q];
-          if (!take[s] || insub[s] || S.f(s) <= DF_MIDMAX) continue;
+          if (!take[s] || insub[s] || direct[s] || S.f(s) <= DF_MIDMAX) continue;
           const int nkb = (S.k(s) + DF_BLK - 1) / DF_BLK, ncb = (S.r(s) + DF_BLK - 1) / DF_BLK;
           if (pass == 0 && phase == 0) for (int b = nkb - 1; b >= 0; --b) chunked(T, ST_FP, s, b, 0, b + 1);
           if (pass == 0 && phase == 1) for (int j = 0; j < ncb; ++j) chunked(T, ST_FC, s, j, 0, nkb);
@@ -531,7 +593,7 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
         }
       for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
         const int s = S.level_sn[q];
-        if (!take[s] || insub[s] || S.f(s) > DF_MIDMAX) continue;
+        if (!take[s] || insub[s] || direct[s] || S.f(s) > DF_MIDMAX) continue;
         if (S.f(s) > 64) T.push_back(SolveTask{ST_MID, s, 0, 0, 0, 0, 1, 0, 0, 0});
         else smalls.push_back(s);
       }
@@ -542,10 +604,29 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
       }
     }
   }
+  // the bottom levels owned by k_solve_direct, one list per level
+  SP.d_direct.clear(); SP.direct_cnt.clear();
+  long long ndirect = 0, direct_nnz = 0;
+  for (int l = 0; l < S.nlevels && l < sv->dbg.solve_direct; ++l) {
+    std::vector<int> lst;
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      const int s = S.level_sn[q];
+      if (take[s] && direct[s]) { lst.push_back(s); direct_nnz += S.L_off[s + 1] - S.L_off[s]; }
+    }
+    ndirect += (long long)lst.size();
+    SP.direct_cnt.push_back((int)lst.size());
+    SP.d_direct.emplace_back(new DevBuf<int>());
+    if (lst.empty()) lst.push_back(0);
+    CU(SP.d_direct.back()->upload(lst, st));
+  }
+  CU(SP.d_sub_Loff.upload(subLoff, st));
+  if (sv->opt.verbose)
+    fprintf(stderr, "[b200ldlt] solve plan: %lld fronts (%.1f MB of L) on %d bottom levels by the direct kernel\n", ndirect,
+            direct_nnz * 8 / 1e6, (int)SP.direct_cnt.size());
   SP.nsub = nsub; SP.ntf = (int)tf.size(); SP.ntb = (int)tb.size();
   if (sv->opt.verbose)
-    fprintf(stderr, "[b200ldlt] solve plan: %d subtrees (%.1f MB of L, largest %.0f KB), top: %d fwd / %d bwd tasks, %lld partial slots\n",
-            nsub, SP.sub_bytes / 1e6, nsub ? (S.L_off[roots[0] + 1] - S.L_off[roots[0] - size[roots[0]] + 1]) * 8 / 1e3 : 0.0, SP.ntf, SP.ntb, npart);
+    fprintf(stderr, "[b200ldlt] solve plan: %d subtrees in %d work items (%.1f MB of L, largest %.0f KB), top: %d fwd / %d bwd tasks, %lld partial slots\n",
+            nsub, SP.npair, SP.sub_bytes / 1e6, nsub ? (ownL[roots[0] + 1] - ownL[roots[0] - size[roots[0]] + 1]) * 8 / 1e3 : 0.0, SP.ntf, SP.ntb, npart);
   if (sv->dbg.solve_timeline) { sv->h_tasks = tf; sv->h_tasks.insert(sv->h_tasks.end(), tb.begin(), tb.end()); }
   if (tf.empty()) tf.push_back(SolveTask{ST_SMALL, 0, 0, 0, 0, 0, 1, 0, 0, 0});
   if (tb.empty()) tb.push_back(SolveTask{ST_SMALL, 0, 0, 0, 0, 0, 1, 0, 0, 0});
@@ -568,6 +649,7 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
   V.linv = sv->d_linv.p; V.linv_off = sv->d_linv_off.p;
   V.fdesc = sv->d_fdesc.p; V.gmap = sv->d_gmap.p; V.gmap_off = sv->d_gmap_off.p;
   V.subs = SP.d_subs.p; V.sub_meta = SP.d_sub_meta.p; V.subrow = SP.d_subrow.p; V.nsub = nsub;
+  V.subpair = SP.d_subpair.p; V.npair = SP.npair; V.sub_Loff = SP.d_sub_Loff.p;
   V.upper_max = sv->opt.smem_front_max;
   V.tlog = nullptr;
   return B200LDLT_SUCCESS;
@@ -576,6 +658,14 @@ static int build_solve_plan(Solver* sv, const Symbolic& S, const std::vector<cha
 // per-front records shared by every solve plan: descriptors, gather maps of the big fronts, backward row addresses
 static int build_solve_tables(Solver* sv, const Symbolic& S, cudaStream_t st) {
   const int nsn = S.nsn;
+  // fronts owned by k_solve_direct: on the lowest levels, order <= 64, all children of the same kind (children precede parents)
+  sv->solve_direct_front.assign(nsn, 0);
+  for (int s = 0; s < nsn; ++s) {
+    if (S.sn_level[s] >= sv->dbg.solve_direct || S.f(s) > 64) continue;
+    bool all = true;
+    for (int q = S.child_ptr[s]; q < S.child_ptr[s + 1]; ++q) all = all && sv->solve_direct_front[S.child_idx[q]];
+    sv->solve_direct_front[s] = all ? 1 : 0;
+  }
   std::vector<FrontDesc> fd(nsn);
   for (int s = 0; s < nsn; ++s) {
     FrontDesc& d = fd[s];
@@ -583,7 +673,7 @@ static int build_solve_tables(Solver* sv, const Symbolic& S, cudaStream_t st) {
     d.ch0 = S.child_ptr[s];
     const int nch = S.child_ptr[s + 1] - S.child_ptr[s];
     if (nch > 65535) { sv->err = "front with more than 65535 children"; return B200LDLT_FATAL_ERROR; }
-    d.nch = (unsigned short)nch; d.pad = 0;
+    d.nch = (unsigned short)nch; d.direct = (unsigned short)sv->solve_direct_front[s];
     d.L_off = S.L_off[s]; d.ro = S.rows_ptr[s];
   }
   CU(sv->d_fdesc.upload(fd, st));
@@ -719,12 +809,13 @@ static int run_analysis(Solver* sv, const double* vals) {
   std::vector<int> fl;
   {
     std::vector<char> take(S.nsn, 1);
-    build_level_plans(S, sv->opt.smem_front_max, take, fl, sv->plan, sv->dbg.buckets, sv->schur, sv->tc_min_r);
+    build_level_plans(S, sv->opt.smem_front_max, take, fl, sv->plan, sv->dbg.buckets, sv->schur, sv->tc_min_r, !sv->dbg.no_warp2);
   }
   CU(sv->d_front_list.upload(fl, st));
   { int rc2 = upload_schur_lists(sv, sv->schur, st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
   CU(cudaFuncSetAttribute(k_tc_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CU(cudaFuncSetAttribute(k_big_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
+  CU(cudaFuncSetAttribute(k_front_warp2, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * S2_SMEM_PER_WARP));
   CU(cudaFuncSetAttribute(k_front_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   CU(cudaFuncSetAttribute(k_front_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CU(cudaFuncSetAttribute(k_fwd_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -827,6 +918,19 @@ static int run_analysis(Solver* sv, const double* vals) {
 
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
+// kernel launch with the programmatic-stream-serialisation attribute (PDL): the kernel may become resident while its
+// predecessor on the stream is still running; it synchronises itself with griddepcontrol.wait
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // enqueue the whole numeric factorisation of the values in d_vals
 static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nullptr, const int* fl_p = nullptr,
                           bool prologue = true, const LinvPlan* linv_p = nullptr, const SchurLists* sl_p = nullptr) {
@@ -904,7 +1008,9 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         }
         ++slot;
         if (fork && slot > 4) slot = 0;
-        if (bk.fmax <= 32) {  // one warp per front (registers), 4 fronts per CTA
+        if (bk.kind == 2) {   // order 33..64, <= 32 pivots: one warp per front, two rows per lane
+          k_front_warp2<<<cdiv(bk.cnt, 4), 128, bk.smem, sq>>>(D, N, fl + bk.off, bk.cnt); ++L;
+        } else if (bk.fmax <= 32) {  // one warp per front (registers), 4 fronts per CTA
           k_front_warp<<<cdiv(bk.cnt, 4), 128, 4 * XS_SMEM_PER_WARP, sq>>>(D, N, fl + bk.off, bk.cnt); ++L;
         } else {
           k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, sq>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
@@ -946,7 +1052,8 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
         if (p >= 2 && eUB[p - 2]) CU(cudaStreamWaitEvent(st, eUB[p - 2], 0));
         const int rows_below = P.big_fmax - jb;  // upper bound
         const int nrowblk = std::max(1u, cdiv(rows_below, 128));
-        k_big_panel<<<dim3(1 + nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), 128, CHAIN_SMEM, st>>>(D, N, bl, jb, nrowblk); ++L;
+        CU(launch_pdl(!sv->dbg.no_pdl, k_big_panel, dim3(1 + nrowblk + cdiv(jb, TRSM_SWAP_COLS), P.big_cnt), dim3(128), CHAIN_SMEM, st,
+                      D, N, bl, jb, nrowblk)); ++L;
         const int rem_k = P.big_kmax - jb - 2 * NB;
         if (rem_k > 0 || cb_panel) {
           cudaEvent_t en = sv->next_event();
@@ -1117,17 +1224,31 @@ __global__ void k_mark_flags(int* flags, const int* __restrict__ list, int n, in
 static int launch_sweep(Solver* sv, const SolvePlan& SP, bool fwd) {
   cudaStream_t st = sv->stream;
   const DevSolve& V = SP.V;
-  const long long nt = (long long)(fwd ? SP.ntf : SP.ntb) + SP.nsub;
-  if (nt <= 0) return B200LDLT_SUCCESS;
+  const long long nt = (long long)(fwd ? SP.ntf : SP.ntb) + SP.npair;
   const int grid = (int)std::min<long long>(sv->df_grid, nt);
+  const int nd = (int)SP.direct_cnt.size();
+  auto direct = [&](int l) {
+    if (SP.direct_cnt[l] <= 0) return;
+    const unsigned g = cdiv(SP.direct_cnt[l], DF_THREADS / 32);
+    if (fwd) k_solve_direct<true><<<g, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, SP.d_direct[l]->p, SP.direct_cnt[l], sv->solve_epoch, sv->d_x.p, sv->d_cbv.p);
+    else k_solve_direct<false><<<g, DF_THREADS, 0, st>>>(sv->DS, sv->DN, V, SP.d_direct[l]->p, SP.direct_cnt[l], sv->solve_epoch, sv->d_x.p, sv->d_cbv.p);
+    ++sv->launches;
+  };
   if (fwd) {
-    k_solve<true><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p);
-    sv->ticket_f += (unsigned long long)nt + grid;
+    for (int l = 0; l < nd; ++l) direct(l);      // bottom levels first, one launch per level
+    if (nt > 0) {
+      k_solve<true><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_f, sv->d_x.p, sv->d_cbv.p);
+      sv->ticket_f += (unsigned long long)nt + grid;
+      ++sv->launches;
+    }
   } else {
-    k_solve<false><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p);
-    sv->ticket_b += (unsigned long long)nt + grid;
+    if (nt > 0) {
+      k_solve<false><<<grid, DF_THREADS, DF_DYN_SMEM, st>>>(sv->DS, sv->DN, V, sv->solve_epoch, sv->ticket_b, sv->d_x.p, sv->d_cbv.p);
+      sv->ticket_b += (unsigned long long)nt + grid;
+      ++sv->launches;
+    }
+    for (int l = nd - 1; l >= 0; --l) direct(l);
   }
-  ++sv->launches;
   CU(cudaGetLastError());
   return B200LDLT_SUCCESS;
 }
@@ -1183,7 +1304,7 @@ static int shard_setup(Solver* sv, int rank, int world) {
   }
   for (int ph = 0; ph < 2; ++ph) {
     std::vector<int> fl;
-    build_level_plans(S, sv->opt.smem_front_max, take[ph], fl, H.plan[ph], sv->dbg.buckets, H.schur[ph], sv->tc_min_r);
+    build_level_plans(S, sv->opt.smem_front_max, take[ph], fl, H.plan[ph], sv->dbg.buckets, H.schur[ph], sv->tc_min_r, !sv->dbg.no_warp2);
     { int rc2 = upload_schur_lists(sv, H.schur[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
     { int rc2 = build_linv_plan(sv, S, take[ph], H.linv_plan[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
     { int rc2 = build_solve_plan(sv, S, take[ph], H.splan[ph], st); if (rc2 != B200LDLT_SUCCESS) return rc2; }
@@ -1221,7 +1342,7 @@ void b200ldlt_default_options(b200ldlt_options* o) {
   o->ordering = 0;
   o->pair_saddle = 1;
   o->leaf_k = 32;
-  o->relax_frac = 0.15;
+  o->relax_frac = 0.05;   // measured on the B200 (profiles/r2_summary.md): 0.05 gives the shortest factorisation at N=400 and N=800 (0.15: +5..8 %)
   o->scaling = 2;
   o->pivtol = 1e-8;
   o->pivtolmax = 1e-4;
@@ -1266,6 +1387,7 @@ b200ldlt_handle b200ldlt_create(const b200ldlt_options* opt) {
   for (auto& q : sv->side) cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, prio_lo);
   cudaEventCreate(&sv->ev0);
   cudaEventCreate(&sv->ev1);
+  for (auto& e : sv->ev_chunk) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaHostAlloc((void**)&sv->h_counters, CNT_N * sizeof(int), cudaHostAllocDefault);
   return (b200ldlt_handle)sv;
 }
@@ -1360,21 +1482,38 @@ int b200ldlt_solve(b200ldlt_handle h, int nrhs, double* rhs) {
     CU(sv->d_rhs.alloc(n * nrhs));
     sv->rhs_cap = nrhs;
   }
-  memcpy(sv->h_rhs, rhs, n * nrhs * sizeof(double));
+  // Host rhs -> pinned staging -> device in chunks, so that the DMA of one chunk runs under the host copy of the next (the
+  // caller's array is pageable: Ipopt allocates it per call, IpTSymLinearSolver.cpp:222-241); same on the way back.
+  const size_t total = n * (size_t)nrhs;
+  const size_t chunk = std::max<size_t>((total + 3) / 4, 32768);
   sv->launches = 0;
   CU(cudaEventRecord(sv->ev0, st));
-  CU(cudaMemcpyAsync(sv->d_rhs.p, sv->h_rhs, n * nrhs * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (size_t o = 0; o < total; o += chunk) {
+    const size_t m = std::min(chunk, total - o);
+    memcpy(sv->h_rhs + o, rhs + o, m * sizeof(double));
+    CU(cudaMemcpyAsync(sv->d_rhs.p + o, sv->h_rhs + o, m * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   for (int c = 0; c < nrhs; ++c) {
     double* col = sv->d_rhs.p + (size_t)c * n;
     int rc = enqueue_solve(sv, col, col);
     if (rc != B200LDLT_SUCCESS) return rc;
   }
-  CU(cudaMemcpyAsync(sv->h_rhs, sv->d_rhs.p, n * nrhs * sizeof(double), cudaMemcpyDeviceToHost, st));
+  int nchunk = 0;
+  for (size_t o = 0; o < total; o += chunk, ++nchunk) {
+    const size_t m = std::min(chunk, total - o);
+    CU(cudaMemcpyAsync(sv->h_rhs + o, sv->d_rhs.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (nchunk < 4) CU(cudaEventRecord(sv->ev_chunk[nchunk], st));
+  }
   CU(cudaEventRecord(sv->ev1, st));
+  nchunk = 0;
+  for (size_t o = 0; o < total; o += chunk, ++nchunk) {
+    const size_t m = std::min(chunk, total - o);
+    if (nchunk < 4) CU(cudaEventSynchronize(sv->ev_chunk[nchunk])); else CU(cudaStreamSynchronize(st));
+    memcpy(rhs + o, sv->h_rhs + o, m * sizeof(double));
+  }
   CU(cudaStreamSynchronize(st));
   cudaEventElapsedTime(&sv->info.ms_solve_gpu, sv->ev0, sv->ev1);
   sv->info.launches_solve = sv->launches;
-  memcpy(rhs, sv->h_rhs, n * nrhs * sizeof(double));
   return B200LDLT_SUCCESS;
 }
 

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) k_front_mid(DevSym S, DevNum N, const int
 #pragma unroll
       for (int c = 0; c < 32; ++c) a[c] = (lane < nb && c < nb) ? F[(jb + lane) + (jb + c) * ld] : 0.0;
       const double gext = (lane < nb) ? gmax[lane] : 0.0;
-      warp_ldlt32(a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colbuf, gext, N.counters);
+      warp_ldlt32<false>(a, a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colbuf, gext, N.counters);
       if (lane < nb) {
         N.lperm[c0 + jb + lane] = jb + order[lane];
         N.dinv[c0 + jb + lane] = dinv_s[lane];
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(32) k_big_diag(DevSym S, DevNum N, const int* 
   for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? T[lane * 33 + c] : T[c * 33 + lane];
   __syncwarp();
   const double gext = (lane < nb) ? N.colmax[c0 + jb + lane] : 0.0;
-  warp_ldlt32(a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colbuf, gext, N.counters);
+  warp_ldlt32<false>(a, a, nb, nb, N.u, N.tiny, T, order, pt, dinv_s, doff_s, colbuf, gext, N.counters);
   // write the block back in pivot order: L[t2][t] = Lraw[order[t2]][t]
   const int mine = (lane < nb) ? order[lane] : 0;
 #pragma unroll

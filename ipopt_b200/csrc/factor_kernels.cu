@@ -257,8 +257,9 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       const double* __restrict__ cj = F + j * ld;
       for (int i = j + 1 + lane; i < f; i += 32) {
         const double li = cj[i] * rdv;
+        const int mend = min(i, k - 1);                 // pivot columns only: the contribution block is updated once, at the end
         int m = j + 1 + warp;
-        for (; m + 3 * nwarp <= i; m += 4 * nwarp) {   // lower triangle only: columns m <= i
+        for (; m + 3 * nwarp <= mend; m += 4 * nwarp) {   // lower triangle only: columns m <= i
           const double c0 = cj[m], c1 = cj[m + nwarp], c2 = cj[m + 2 * nwarp], c3 = cj[m + 3 * nwarp];
           double* q0 = F + i + m * ld;
           double* q1 = q0 + nwarp * ld;
@@ -267,7 +268,7 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
           const double f0 = *q0, f1 = *q1, f2 = *q2, f3 = *q3;
           *q0 = fma(-li, c0, f0); *q1 = fma(-li, c1, f1); *q2 = fma(-li, c2, f2); *q3 = fma(-li, c3, f3);
         }
-        for (; m <= i; m += nwarp) F[i + m * ld] = fma(-li, cj[m], F[i + m * ld]);
+        for (; m <= mend; m += nwarp) F[i + m * ld] = fma(-li, cj[m], F[i + m * ld]);
       }
       gsync<WARP>();
       j += 1;
@@ -290,8 +291,9 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
       for (int i = j + 2 + lane; i < f; i += 32) {
         const double r1 = cj[i], r2 = cj1[i];
         const double l1 = fma(r1, da, r2 * dof), l2 = fma(r1, dof, r2 * db);
+        const int mend = min(i, k - 1);
         int m = j + 2 + warp;
-        for (; m + 3 * nwarp <= i; m += 4 * nwarp) {
+        for (; m + 3 * nwarp <= mend; m += 4 * nwarp) {
           const double a0 = cj[m], a1 = cj[m + nwarp], a2 = cj[m + 2 * nwarp], a3 = cj[m + 3 * nwarp];
           const double b0 = cj1[m], b1 = cj1[m + nwarp], b2 = cj1[m + 2 * nwarp], b3 = cj1[m + 3 * nwarp];
           double* q0 = F + i + m * ld;
@@ -302,12 +304,43 @@ __device__ void factor_front_smem(double* F, int ld, int f, int k, int* lp, int*
           *q0 = fma(-l2, b0, fma(-l1, a0, f0)); *q1 = fma(-l2, b1, fma(-l1, a1, f1));
           *q2 = fma(-l2, b2, fma(-l1, a2, f2)); *q3 = fma(-l2, b3, fma(-l1, a3, f3));
         }
-        for (; m <= i; m += nwarp) F[i + m * ld] = fma(-l2, cj1[m], fma(-l1, cj[m], F[i + m * ld]));
+        for (; m <= mend; m += nwarp) F[i + m * ld] = fma(-l2, cj1[m], fma(-l1, cj[m], F[i + m * ld]));
       }
       gsync<WARP>();
       j += 2;
     }
     ++progress;
+  }
+  // ---------------- deferred Schur complement of the contribution block ----------------
+  // CB[i][m] -= sum_t L[i][t] W[m][t] (i >= m >= k), W = L D = the unscaled pivot columns.  Entry (i, m) belongs to one thread
+  // (lane <- row, warp <- column), so there is no barrier inside; the L entries of a row are formed once per chunk of 8
+  // pivots and reused for all its columns.  (During the pivot loop only the k pivot columns were updated: the pivot search
+  // and the interchanges never look at the contribution block.)
+  if (f > k) {
+    for (int i = k + lane; i < f; i += 32) {
+      for (int t0 = 0; t0 < k; t0 += 8) {
+        double l[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int t = t0 + q;
+          double v = 0.0;
+          if (t < k) {
+            const int ty = pt[t];
+            if (ty == 1) v = F[i + t * ld] * cv1[t];
+            else if (ty == 2) v = fma(F[i + t * ld], cv1[t], F[i + (t + 1) * ld] * cv2[t]);
+            else v = fma(F[i + (t - 1) * ld], cv2[t - 1], F[i + t * ld] * cv1[t]);
+          }
+          l[q] = v;
+        }
+        for (int m = k + warp; m <= i; m += nwarp) {
+          double acc = F[i + m * ld];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (t0 + q < k) acc = fma(-l[q], F[m + (t0 + q) * ld], acc);
+          F[i + m * ld] = acc;
+        }
+      }
+    }
   }
   if (tid == 0) {
     if (c_neg) atomicAdd(counters + CNT_NEG, c_neg);
@@ -339,17 +372,24 @@ __device__ __forceinline__ void wred_max_idx(double& v, int& idx) {
   }
 }
 
-__device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const double u, const double tiny,
+// TWO = true: fronts of order 33..64 with k <= 32.  The warp also carries rows 32..f-1 (lane -> row 32 + lane) of the
+// first 32 columns in b[]: they are never pivot candidates (all candidates are among rows 0..k-1 < 32), but they take part
+// in every threshold test, receive every update (so b[c], c < 32-k, ends as the Schur complement column k+c of row
+// 32+lane) and their L entries go to Lraw[(32+lane)*33 + t].  The block rows >= 32 x columns >= 32 of the Schur
+// complement is formed afterwards from L and D (dpiv/dpb: the pivots themselves, see k_front_warp2).
+template <bool TWO>
+__device__ void warp_ldlt32(double (&a)[32], double (&b)[32], const int f, const int k, const double u, const double tiny,
                             double* __restrict__ Lraw, int* __restrict__ order, int* __restrict__ pt,
                             double* __restrict__ dinv_s, double* __restrict__ doff_s,
                             double* __restrict__ colbuf /* 64 doubles of shared memory, 16-byte aligned */,
                             const double gext /* lane c: max |entry| of column c in rows OUTSIDE the block (0 if none) */,
-                            int* counters) {
+                            int* counters, double* __restrict__ dpiv = nullptr, double* __restrict__ dpb = nullptr) {
   const int lane = threadIdx.x & 31;
   // mypos = current POSITION of the column whose original index is this lane (columns stay compacted)
   int mypos = lane;
   colbuf[lane] = 0.0; colbuf[32 + lane] = 0.0;
   __syncwarp();
+  const bool me2 = TWO && (lane + 32 < f);          // this lane carries a second row
   unsigned alive = (f >= 32) ? 0xffffffffu : ((1u << f) - 1u);
   unsigned cand = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   int nc = k, npass = k, t = 0, progress = 0;
@@ -370,7 +410,10 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
     const float v0f = __double2float_ru(v0);
     const float lam_in = (me_cand && lane != g0) ? v0f : -1.0f;
     const float lamf = wredux_max(lam_in);
-    const float gamf = wredux_max((me_alive && !me_cand) ? v0f : 0.0f);
+    float gam_in = (me_alive && !me_cand) ? v0f : 0.0f;
+    float w0f = 0.0f;
+    if (TWO) { w0f = me2 ? __double2float_ru(fabs(b[0])) : 0.0f; gam_in = fmaxf(gam_in, w0f); }
+    const float gamf = wredux_max(gam_in);
     int r = __ffs(__ballot_sync(0xffffffffu, lam_in == lamf)) - 1;   // lowest lane holding the maximum
     double lam = 0.0;
     if (lamf < 0.0f) r = -1;
@@ -393,14 +436,22 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
         for (int c = 2; c < 32; ++c)
           if (c == p) { double x = a[c]; a[c] = ta; ta = x; }
         a[1] = ta;
+        if (TWO) {
+          double tb = b[1];
+#pragma unroll
+          for (int c = 2; c < 32; ++c)
+            if (c == p) { double x = b[c]; b[c] = tb; tb = x; }
+          b[1] = tb;
+        }
         if (mypos == 1) mypos = p; else if (mypos == p) mypos = 1;
       }
       const double v1 = fabs(a[1]);
       const float v1f = __double2float_ru(v1);
       const bool other = me_alive && lane != g0 && lane != r;
+      const float w1f = (TWO && me2) ? __double2float_ru(fabs(b[1])) : 0.0f;   // the second rows are always "other" rows
       double sig = (double)wredux_max((me_cand && lane != r) ? v1f : 0.0f);
-      double gamr = (double)wredux_max((me_alive && !me_cand) ? v1f : 0.0f);
-      double cj = (double)wredux_max(other ? v0f : 0.0f), cr = (double)wredux_max(other ? v1f : 0.0f);
+      double gamr = (double)wredux_max(fmaxf((me_alive && !me_cand) ? v1f : 0.0f, w1f));
+      double cj = (double)wredux_max(fmaxf(other ? v0f : 0.0f, w0f)), cr = (double)wredux_max(fmaxf(other ? v1f : 0.0f, w1f));
       {
         const double ge_r = __shfl_sync(0xffffffffu, gext, r), ge_j = __shfl_sync(0xffffffffu, gext, g0);
         gamr = fmax(gamr, ge_r); cr = fmax(cr, ge_r); cj = fmax(cj, ge_j);
@@ -411,6 +462,7 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       else if (arr > tiny && arr >= BK_ALPHA * sig && arr >= u * fmax(sig, gamr)) {
         // 1x1 on r: swap positions 0 and 1
         double x = a[0]; a[0] = a[1]; a[1] = x;
+        if (TWO) { double y = b[0]; b[0] = b[1]; b[1] = y; }
         if (mypos == 0) mypos = 1; else if (mypos == 1) mypos = 0;
         g0 = r;
         type = 1;
@@ -431,6 +483,15 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
         else if (c == nc - 1) a[c] = ta;
       }
       if (nc == 32) a[31] = ta;
+      if (TWO) {
+        const double tb = b[0];
+#pragma unroll
+        for (int c = 0; c < 31; ++c) {
+          if (c < nc - 1) b[c] = b[c + 1];
+          else if (c == nc - 1) b[c] = tb;
+        }
+        if (nc == 32) b[31] = tb;
+      }
       if (mypos == 0) mypos = nc - 1; else if (mypos < nc) mypos -= 1;
       --npass;
       continue;
@@ -450,6 +511,7 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       const double c0v = a[0];
       const double rinv = 1.0 / dd;
       const double l = (me_alive && lane != g0) ? c0v * rinv : 0.0;
+      const double lb = (TWO && me2) ? b[0] * rinv : 0.0;
       // pivot row by position: F[g0][col at position c] = F[that col's row][g0] = that lane's a[0]
       if (me_alive) colbuf[mypos] = c0v;
       __syncwarp();
@@ -459,15 +521,25 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
         const double2 pp = cb2[c2];
         if (c2 > 0) a[2 * c2] = fma(-l, pp.x, a[2 * c2]);
         a[2 * c2 + 1] = fma(-l, pp.y, a[2 * c2 + 1]);
+        if (TWO) {
+          if (c2 > 0) b[2 * c2] = fma(-lb, pp.x, b[2 * c2]);
+          b[2 * c2 + 1] = fma(-lb, pp.y, b[2 * c2 + 1]);
+        }
       }
       __syncwarp();
       Lraw[lane * 33 + t] = l;
+      if (TWO) { Lraw[(32 + lane) * 33 + t] = lb; if (lane == 0) { dpiv[t] = dd; dpb[t] = 0.0; } }
       if (lane == t) { my_order = g0; my_pt = 1; my_dinv = rinv; my_doff = 0.0; }   // lane t keeps pivot t's record
       if (dd < 0.0) ++c_neg;
       alive &= ~(1u << g0); cand &= ~(1u << g0);
 #pragma unroll
       for (int c = 0; c < 31; ++c) a[c] = a[c + 1];
       a[31] = 0.0;
+      if (TWO) {
+#pragma unroll
+        for (int c = 0; c < 31; ++c) b[c] = b[c + 1];
+        b[31] = 0.0;
+      }
       mypos -= 1;
       nc -= 1; npass = max(npass - 1, 0); t += 1;
     } else {
@@ -479,6 +551,9 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
       const double idet = 1.0 / det;
       const double l1 = other ? (pc2 * c1 - pb * c2v) * idet : 0.0;
       const double l2 = other ? (pa * c2v - pb * c1) * idet : 0.0;
+      const double e1 = TWO ? b[0] : 0.0, e2 = TWO ? b[1] : 0.0;
+      const double m1 = (TWO && me2) ? (pc2 * e1 - pb * e2) * idet : 0.0;
+      const double m2 = (TWO && me2) ? (pa * e2 - pb * e1) * idet : 0.0;
       if (me_alive) { colbuf[mypos] = c1; colbuf[32 + mypos] = c2v; }
       __syncwarp();
       const double2* cb1 = reinterpret_cast<const double2*>(colbuf);
@@ -488,10 +563,19 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
         const double2 p1 = cb1[q], p2 = cb2[q];
         a[2 * q] = fma(-l2, p2.x, fma(-l1, p1.x, a[2 * q]));
         a[2 * q + 1] = fma(-l2, p2.y, fma(-l1, p1.y, a[2 * q + 1]));
+        if (TWO) {
+          b[2 * q] = fma(-m2, p2.x, fma(-m1, p1.x, b[2 * q]));
+          b[2 * q + 1] = fma(-m2, p2.y, fma(-m1, p1.y, b[2 * q + 1]));
+        }
       }
       __syncwarp();
       Lraw[lane * 33 + t] = l1;
       Lraw[lane * 33 + t + 1] = l2;
+      if (TWO) {
+        Lraw[(32 + lane) * 33 + t] = m1;
+        Lraw[(32 + lane) * 33 + t + 1] = m2;
+        if (lane == 0) { dpiv[t] = pa; dpb[t] = pb; dpiv[t + 1] = pc2; dpb[t + 1] = 0.0; }
+      }
       if (lane == t) { my_order = g0; my_pt = 2; my_dinv = pc2 * idet; my_doff = -pb * idet; }
       if (lane == t + 1) { my_order = r; my_pt = 3; my_dinv = pa * idet; my_doff = 0.0; }
       ++c_2x2;
@@ -500,6 +584,11 @@ __device__ void warp_ldlt32(double (&a)[32], const int f, const int k, const dou
 #pragma unroll
       for (int c = 0; c < 30; ++c) a[c] = a[c + 2];
       a[30] = 0.0; a[31] = 0.0;
+      if (TWO) {
+#pragma unroll
+        for (int c = 0; c < 30; ++c) b[c] = b[c + 2];
+        b[30] = 0.0; b[31] = 0.0;
+      }
       mypos -= 2;
       nc -= 2; npass = max(npass - 2, 0); t += 2;
     }
@@ -650,7 +739,7 @@ __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const in
 #pragma unroll
   for (int c = 0; c < 32; ++c) a[c] = F[lane + c * ld];   // lanes >= f / columns >= f read zeros
   __syncwarp();
-  warp_ldlt32(a, f, k, N.u, N.tiny, F, order, pt, dinv_s, doff_s, colbuf, 0.0, N.counters);
+  warp_ldlt32<false>(a, a, f, k, N.u, N.tiny, F, order, pt, dinv_s, doff_s, colbuf, 0.0, N.counters);
   // L panel in pivot order
   double* __restrict__ P = N.L + S.L_off[s];
   const int orig = (lane < k) ? order[lane] : lane;
@@ -675,6 +764,156 @@ __global__ void __launch_bounds__(128) k_front_warp(DevSym S, DevNum N, const in
 #pragma unroll
   for (int c = 0; c < 32; ++c)
     if (lane >= k && lane < f && c <= lane - k) cbo[(lane - k) + (size_t)c * r] = a[c];
+  fs.done();
+}
+
+// --------------------------------------------------------------------------------------------
+// Class S2: fronts of order 33..64 with at most 32 pivot columns, ONE WARP per front (4 fronts per CTA), two rows per lane:
+// the first 32 columns of the front are factorised in registers (warp_ldlt32<true>: rows 0..31 in a[], rows 32..f-1 in
+// b[]); the trailing block rows >= 32 x columns >= 32 of the contribution block is  C22 - L2 D L2^T  formed afterwards
+// from the finished panel (lane = row, L rows of the partners broadcast from shared memory).
+// smem per warp: P0/Lraw[64*33] doubles (P0 = first 32 columns, column-major ld 66; aliased by Lraw once the columns are
+//   in registers) | C22[32*33] | colbuf[64] | dinv_s[32] | doff_s[32] | dpiv[32] | dpb[32] | order[32] | pt[32]
+// --------------------------------------------------------------------------------------------
+#define S2_LD 66
+#define S2_SMEM_PER_WARP ((64 * 33 + 32 * 33 + 64 + 4 * 32) * 8 + 64 * 4)
+__global__ void __launch_bounds__(128, 2) k_front_warp2(DevSym S, DevNum N, const int* __restrict__ front_list, int nfronts) {
+  extern __shared__ double smem[];
+  const int group = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (group >= nfronts) return;
+  const int s = front_list[group];
+  FlogScope fs(N, 5, s, 1);
+  const int c0 = S.sn_start[s], k = S.sn_start[s + 1] - c0;
+  const int r = (int)(S.rows_ptr[s + 1] - S.rows_ptr[s]);
+  const int f = k + r, f1 = f - 32;            // 32 < f <= 64, k <= 32 (guaranteed by the launch plan)
+  double* P0 = (double*)((char*)smem + (size_t)(threadIdx.x >> 5) * S2_SMEM_PER_WARP);
+  double* C22 = P0 + 64 * 33;
+  double* colbuf = C22 + 32 * 33;        // offset (2112 + 1056) * 8 bytes: 16-byte aligned
+  double* dinv_s = colbuf + 64;
+  double* doff_s = dinv_s + 32;
+  double* dpiv = doff_s + 32;
+  double* dpb = dpiv + 32;
+  int* order = (int*)(dpb + 32);
+  int* pt = order + 32;
+  const int lane = threadIdx.x & 31;
+  for (int t = lane; t < 64 * 33 + 32 * 33; t += 32) P0[t] = 0.0;
+  __syncwarp();
+  // entry (li, lj), li >= lj, of the front: columns < 32 live in P0 (the top 32 x 32 block with both triangles), the rest in C22
+  auto put = [&](int li, int lj, double v, bool add) {
+    if (lj < 32) {
+      double* d1 = P0 + li + lj * S2_LD;
+      *d1 = add ? *d1 + v : v;
+      if (li < 32 && li != lj) { double* d2 = P0 + lj + li * S2_LD; *d2 = add ? *d2 + v : v; }
+    } else {
+      double* d1 = C22 + (li - 32) + (lj - 32) * 33;
+      *d1 = add ? *d1 + v : v;
+    }
+  };
+  for (long long uu = S.uent_ptr[s] + lane; uu < S.uent_ptr[s + 1]; uu += 32) {
+    const unsigned d = S.u_dst[uu];
+    put((int)(d & 0xffffu), (int)(d >> 16), N.uval[uu], false);     // unique entries: no write conflicts
+  }
+  __syncwarp();
+  const int ch0 = S.child_ptr[s], nch = S.child_ptr[s + 1] - ch0;
+  for (int q0 = 0; q0 < nch; q0 += 32) {
+   // the descriptors of up to 32 children lane-parallel (three dependent global loads each), then the children in order
+   long long m_cb = 0, m_ro = 0;
+   int m_rc = 0;
+   if (q0 + lane < nch) {
+     const int c = S.child_idx[ch0 + q0 + lane];
+     m_ro = S.rows_ptr[c]; m_rc = (int)(S.rows_ptr[c + 1] - m_ro); m_cb = S.cb_off[c];
+   }
+   for (int qq = 0; qq < min(32, nch - q0); ++qq) {
+    const int rc = __shfl_sync(0xffffffffu, m_rc, qq);              // <= 63: the child's rows are rows of this front
+    const double* __restrict__ cb = N.CB + __shfl_sync(0xffffffffu, m_cb, qq);
+    const int* __restrict__ rl = S.rel + __shfl_sync(0xffffffffu, m_ro, qq);
+    const int li0 = (lane < rc) ? rl[lane] : 0, li1 = (lane + 32 < rc) ? rl[lane + 32] : 0;
+    // rel is strictly increasing inside a child, so the entries (ii, jj) of one child land on pairwise distinct addresses
+    // (the mirrored writes of the top block included): no synchronisation inside a child, and the loads of 8 columns are in
+    // flight together (the loop is latency-bound otherwise: one dependent global load per column)
+    for (int jj0 = 0; jj0 < rc; jj0 += 8) {
+      double v0[8], v1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = jj0 + u;
+        v0[u] = (jj < rc && lane >= jj && lane < rc) ? cb[lane + (size_t)jj * rc] : 0.0;
+        v1[u] = (jj < rc && lane + 32 >= jj && lane + 32 < rc) ? cb[lane + 32 + (size_t)jj * rc] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = jj0 + u;
+        if (jj < rc) {     // warp-uniform
+          const int lj = (jj < 32) ? __shfl_sync(0xffffffffu, li0, jj) : __shfl_sync(0xffffffffu, li1, jj - 32);
+          if (lane >= jj && lane < rc) put(li0, lj, v0[u], true);
+          if (lane + 32 >= jj && lane + 32 < rc) put(li1, lj, v1[u], true);
+        }
+      }
+    }
+    __syncwarp();
+   }
+  }
+  double a[32], b[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) { a[c] = P0[lane + c * S2_LD]; b[c] = P0[32 + lane + c * S2_LD]; }   // rows >= f read zeros
+  __syncwarp();     // every lane has its columns: the region becomes Lraw
+  double* Lraw = P0;
+  warp_ldlt32<true>(a, b, f, k, N.u, N.tiny, Lraw, order, pt, dinv_s, doff_s, colbuf, 0.0, N.counters, dpiv, dpb);
+  // L panel in pivot order (f x k, ld = f); L11^T in the upper triangle of the pivot block (see k_front_smem)
+  double* __restrict__ P = N.L + S.L_off[s];
+  const int orig = (lane < k) ? order[lane] : lane;
+#pragma unroll 4
+  for (int t = 0; t < 32; ++t) {
+    if (t < k) {
+      double v;
+      if (lane < t) v = Lraw[order[t] * 33 + lane];
+      else if (lane == t) v = 1.0;
+      else v = Lraw[orig * 33 + t];
+      P[lane + (size_t)t * f] = v;
+      if (lane < f1) P[32 + lane + (size_t)t * f] = Lraw[(32 + lane) * 33 + t];
+    }
+  }
+  if (lane < k) {
+    N.lperm[c0 + lane] = order[lane];
+    N.dinv[c0 + lane] = dinv_s[lane];
+    N.doff[c0 + lane] = doff_s[lane];
+    N.ptype[c0 + lane] = pt[lane];
+  }
+  // contribution block (lower part, r x r, ld = r).  Columns k..31 of the front: what is left in a[] / b[].
+  double* __restrict__ cbo = N.CB + S.cb_off[s];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (c < 32 - k) {
+      if (lane >= k && c <= lane - k) cbo[(lane - k) + (size_t)c * r] = a[c];
+      if (lane < f1) cbo[(32 - k + lane) + (size_t)c * r] = b[c];
+    }
+  }
+  // columns >= 32: C22[i][j] - sum_t (L D)[i][t] L[j][t], row i = 32 + lane, partners j <= lane
+  {
+    double wrow[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) wrow[t] = (t < k && lane < f1) ? Lraw[(32 + lane) * 33 + t] : 0.0;
+    // w = l D: 1x1 pivots w_t = l_t d_t; 2x2 pivots (t, t+1): w_t = l_t d_tt + l_t+1 d_o, w_t+1 = l_t d_o + l_t+1 d_t+1,t+1
+    double prevl = 0.0;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const double lt = wrow[t];
+      if (t < k) {
+        const int ty = pt[t];
+        double w = lt * dpiv[t];
+        if (ty == 2) w = fma(wrow[(t + 1) & 31], dpb[t], w);          // (still the L entry: ascending t)
+        else if (ty == 3) w = fma(prevl, dpb[(t + 31) & 31], w);
+        prevl = lt;
+        wrow[t] = w;
+      }
+    }
+    for (int j = 0; j < f1; ++j) {
+      const double* __restrict__ lj = Lraw + (32 + j) * 33;
+      double acc = 0.0;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) acc = fma(wrow[t], lj[t], acc);     // (entries t >= k of wrow are zero)
+      if (j <= lane && lane < f1) cbo[(32 - k + lane) + (size_t)(32 - k + j) * r] = C22[lane + j * 33] - acc;
+    }
+  }
   fs.done();
 }
 
@@ -1197,6 +1436,11 @@ __global__ void __launch_bounds__(128) k_big_panel(DevSym S, DevNum N, const int
                                                    int nrowblk) {
   extern __shared__ double csm[];
   const int s = front_list[blockIdx.y];
+  // Programmatic dependent launch (the launches of one front's panels follow each other on the chain stream): let the next
+  // panel's CTAs become resident now, and wait here until the previous panel kernel has completed and flushed.  Both are
+  // no-ops when the kernel was launched without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (blockIdx.x == 0) { chain_role(S, N, s, jb, csm); return; }
   if (jb < 0) return;
   __shared__ __align__(16) double Lb[NB * TRSM_LD];

@@ -51,7 +51,7 @@ struct __align__(16) FrontDesc {
   int c0;                  // first (permuted) column
   unsigned short k, r;     // pivot columns, contribution rows
   int ch0;                 // first entry in child_idx
-  unsigned short nch, pad;
+  unsigned short nch, direct;   // direct != 0: the front is solved by k_solve_direct (bottom levels), never inside a subtree / task
   long long L_off;         // panel offset in L
   long long ro;            // offset of the row list / update vector (rows_ptr)
 };
@@ -60,9 +60,10 @@ struct __align__(16) FrontDesc {
 //   meta[moff] = nlv ; then nlv+1 level offsets into the front list ; then nlv counts of small (order <= 64) fronts ;
 //   then the front list itself (nfront ids, by level, small fronts first)
 struct SubDesc {
-  int s0, sR, moff, nlv;
-  int col0, ncol, nrt, rroot, ch00, nchi, parent, pad;   // first column / #columns, #rows of all fronts / of the root, child list, parent of the root
-  long long L0, nL, ro0;                                 // panel range (doubles), first row-list offset
+  int s0, sR, moff, nlv;             // (meta: nlv+1 level offsets, nlv small counts, then the nown OWNED fronts by level)
+  int col0, ncol, nrt, rroot, ch00, nchi, parent, sbytes;   // first column / #columns, #rows of all fronts / of the root, child list, parent of the root, shared-memory bytes (SubLayout, rounded up to 128)
+  long long nL, ro0;                                     // doubles of the compact panel copy, first row-list offset
+  int nown, pad;                                         // fronts walked here (the others in [s0, sR] are direct fronts)
 };
 
 struct DevSolve {
@@ -93,6 +94,9 @@ struct DevSolve {
   const int* subrow;           // aligned with rows: backward address of a contribution row inside its subtree:
                                //   >= 0 : column (local index into the subtree's x slice) ; < 0 : -(1 + index into the root's rows)
   int nsub;
+  const int* sub_Loff;         // nsn : offset (doubles) of a front's panel inside its subtree's compact shared-memory copy
+  const int2* subpair;         // work items of the subtree phase: (u0, u1) two subtrees walked side by side by the two halves
+  int npair;                   //   of a CTA (their layouts fit the dynamic shared memory together), or (u0, -1) one subtree by the whole CTA
   int upper_max;               // fronts up to this order carry L11^T in the upper triangle of their pivot block
   unsigned long long* tlog;    // optional (debug): 2 timestamps per top task, fwd then bwd; nullptr = off
 };
@@ -107,6 +111,13 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 }
 __device__ __forceinline__ void wait_eq(const int* p, int epoch) {
   while (ld_acquire(p) != epoch) __nanosleep(20);
+}
+
+// A team = the threads that work on one front / subtree together: the whole CTA (hardware barrier 0, identical to
+// __syncthreads) or one half of it (barriers 1 / 2) when two subtrees share a CTA.
+struct Team { int tid, nt, bar; };
+__device__ __forceinline__ void team_sync(const Team& tm) {
+  asm volatile("bar.sync %0, %1;" ::"r"(tm.bar), "r"(tm.nt) : "memory");
 }
 
 // ---- TMA 1-D bulk copy global -> shared with mbarrier completion (sm_90+; PTX cp.async.bulk) ---------------------
@@ -165,7 +176,7 @@ __device__ __forceinline__ FrontDesc load_fd(const FrontDesc* p) {
   const int4 a = reinterpret_cast<const int4*>(p)[0], b = reinterpret_cast<const int4*>(p)[1];
   FrontDesc d;
   d.c0 = a.x; d.k = (unsigned short)(a.y & 0xffff); d.r = (unsigned short)((unsigned)a.y >> 16);
-  d.ch0 = a.z; d.nch = (unsigned short)(a.w & 0xffff); d.pad = 0;
+  d.ch0 = a.z; d.nch = (unsigned short)(a.w & 0xffff); d.direct = (unsigned short)((unsigned)a.w >> 16);
   d.L_off = ((long long)(unsigned)b.x) | ((long long)b.y << 32);
   d.ro = ((long long)(unsigned)b.z) | ((long long)b.w << 32);
   return d;
@@ -222,6 +233,7 @@ __device__ void w64_fwd(const FrontIO& io, const DevSolve& V, int s, int epoch, 
       const int c = io.chi[fd.ch0 - io.ch00 + q0 + lane];
       inq = (!SUB) || (c >= io.s0 && c <= io.sR);
       const FrontDesc cd = load_fd(inq ? io.fd + (c - io.s0) : io.gfd + c);
+      if (SUB && cd.direct) inq = 0;      // solved by the direct kernel before this sweep: its update vector is in global memory
       oq = cd.ro; rq = cd.r;
       if (!SUB) wait_eq(V.done_f + c, epoch);
     }
@@ -419,21 +431,22 @@ __device__ void w64_bwd(const FrontIO& io, const DevSolve& V, int s, int epoch, 
 // ------------------------------------------------------------------------------------------------
 template <bool SUB>
 __device__ void mid_fwd(const FrontIO& io, const DevSolve& V, int s, int epoch, double* scr, const double* Lp_override,
-                        unsigned long long* mbar, unsigned mphase) {
+                        unsigned long long* mbar, unsigned mphase, const Team tm) {
   const FrontDesc fd = load_fd(io.fd + (s - io.s0));
   const int k = fd.k, r = fd.r, f = k + r, nch = fd.nch;
   const int cl = fd.c0 - io.col0;
   const long long rol = fd.ro - io.ro0;
   double* v = scr;
   double* w = scr + f;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = tm.tid, nt = tm.nt, lane = tid & 31, warp = tid >> 5;
   if (!SUB) for (int q = tid; q < nch; q += nt) wait_eq(V.done_f + io.chi[fd.ch0 - io.ch00 + q], epoch);
   for (int i = tid; i < f; i += nt) w[i] = (i < k) ? io.xs[cl + i] : 0.0;
-  __syncthreads();
+  team_sync(tm);
   for (int q = 0; q < nch; ++q) {
     const int c = io.chi[fd.ch0 - io.ch00 + q];
-    const bool in = (!SUB) || (c >= io.s0 && c <= io.sR);
-    const FrontDesc cd = load_fd(in ? io.fd + (c - io.s0) : io.gfd + c);
+    const bool inr = (!SUB) || (c >= io.s0 && c <= io.sR);
+    const FrontDesc cd = load_fd(inr ? io.fd + (c - io.s0) : io.gfd + c);
+    const bool in = inr && !cd.direct;
     const int rc = cd.r;
     if (SUB && in) {
       const int* __restrict__ rl = io.rel + (cd.ro - io.ro0);
@@ -444,11 +457,11 @@ __device__ void mid_fwd(const FrontIO& io, const DevSolve& V, int s, int epoch, 
       const double* __restrict__ src = io.gcbv + cd.ro;
       for (int t = tid; t < rc; t += nt) w[rl[t]] += __ldcg(src + t);
     }
-    __syncthreads();
+    team_sync(tm);
   }
   const int* __restrict__ lp = io.lperm + cl;
   for (int i = tid; i < f; i += nt) v[i] = (i < k) ? w[lp[i]] : w[i];
-  __syncthreads();
+  team_sync(tm);
   const double* __restrict__ P = Lp_override ? Lp_override : io.Lbase + (fd.L_off - io.L0);
   if (mbar) mbar_wait(mbar, mphase);   // the staged panel (bulk copy issued by the caller) has landed
   for (int t0 = 0; t0 < k; t0 += 32) {
@@ -470,14 +483,14 @@ __device__ void mid_fwd(const FrontIO& io, const DevSolve& V, int s, int epoch, 
       }
       if (lane < nb) v[t0 + lane] = yi;
     }
-    __syncthreads();
+    team_sync(tm);
     for (int i = t0 + nb + tid; i < f; i += nt) {
       double acc = 0.0;
 #pragma unroll 8
       for (int q = 0; q < nb; ++q) acc = fma(P[i + (size_t)(t0 + q) * f], v[t0 + q], acc);
       v[i] -= acc;
     }
-    __syncthreads();
+    team_sync(tm);
   }
   for (int t = tid; t < k; t += nt) {
     const int ty = io.ptype[cl + t];
@@ -489,25 +502,25 @@ __device__ void mid_fwd(const FrontIO& io, const DevSolve& V, int s, int epoch, 
   }
   double* __restrict__ out = io.uv + rol;
   for (int i = tid; i < r; i += nt) out[i] = v[k + i];
-  __syncthreads();
+  team_sync(tm);
   if (!SUB && tid == 0) st_release(V.done_f + s, epoch);
 }
 
 template <bool SUB>
 __device__ void mid_bwd(const FrontIO& io, const DevSolve& V, int s, int epoch, int parent, double* scr,
-                        const double* Lp_override, unsigned long long* mbar, unsigned mphase, int upper_max) {
+                        const double* Lp_override, unsigned long long* mbar, unsigned mphase, int upper_max, const Team tm) {
   const FrontDesc fd = load_fd(io.fd + (s - io.s0));
   const int k = fd.k, r = fd.r, f = k + r;
   const int cl = fd.c0 - io.col0;
   const long long rol = fd.ro - io.ro0;
   double* v = scr;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int tid = tm.tid, nt = tm.nt, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   if (!SUB) {
     if (parent >= 0 && tid == 0) wait_eq(V.done_b + parent, epoch);
-    __syncthreads();
+    team_sync(tm);
   }
   for (int i = tid; i < f; i += nt) v[i] = (i < k) ? io.xs[cl + i] : cb_row_x<SUB>(io, rol, fd.ro, i - k);
-  __syncthreads();
+  team_sync(tm);
   const double* __restrict__ P = Lp_override ? Lp_override : io.Lbase + (fd.L_off - io.L0);
   if (mbar) mbar_wait(mbar, mphase);
   const int nblk = (k + 31) / 32;
@@ -521,7 +534,7 @@ __device__ void mid_bwd(const FrontIO& io, const DevSolve& V, int s, int epoch, 
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) v[t0 + q] -= acc;
     }
-    __syncthreads();
+    team_sync(tm);
     if (warp == 0) {
       // triangle of this block: lane t owns column t; row q of the block comes from L11^T in the upper triangle when the
       // factorisation stored it (fronts up to order 128), else from the lower triangle (stride-f gather)
@@ -545,11 +558,11 @@ __device__ void mid_bwd(const FrontIO& io, const DevSolve& V, int s, int epoch, 
       }
       if (lane < nb) v[t0 + lane] = zi;
     }
-    __syncthreads();
+    team_sync(tm);
   }
   const int* __restrict__ lp = io.lperm + cl;
   for (int t = tid; t < k; t += nt) io.xs[cl + lp[t]] = v[t];
-  __syncthreads();
+  team_sync(tm);
   if (!SUB && tid == 0) st_release(V.done_b + s, epoch);
 }
 
@@ -1077,15 +1090,16 @@ struct SubLayout {
 // one subtree, by the whole CTA (see the file header).  `mbar` / `mphase`: the CTA's transaction barrier and its phase.
 template <bool FWD>
 __device__ void solve_subtree(const DevSym& S, const DevNum& N, const DevSolve& V, int u, int epoch, unsigned char* smraw,
-                              unsigned long long* mbar, unsigned mphase, double* __restrict__ x, double* __restrict__ cbv) {
-  const int tid = threadIdx.x, warp = tid >> 5;
+                              unsigned long long* mbar, unsigned mphase, double* __restrict__ x, double* __restrict__ cbv,
+                              const Team tm) {
+  const int tid = tm.tid, warp = tid >> 5, NT = tm.nt;
   unsigned long long t_a = 0, t_b = 0;
   if (V.tlog && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
   const SubDesc sd = V.subs[u];
   const int s0 = sd.s0, sR = sd.sR, nfront = sR - s0 + 1, nlv = sd.nlv;
   const int col0 = sd.col0, ncol = sd.ncol, nrt = sd.nrt, rroot = sd.rroot, ch00 = sd.ch00, nchi = sd.nchi;
-  const long long L0 = sd.L0, nL = sd.nL, ro0 = sd.ro0, roR = sd.ro0 + (sd.nrt - sd.rroot);
-  const int nmeta = 2 * nlv + 1 + nfront;
+  const long long nL = sd.nL, ro0 = sd.ro0, roR = sd.ro0 + (sd.nrt - sd.rroot);
+  const int nmeta = 2 * nlv + 1 + sd.nown;
   // carve
   double* Ls = reinterpret_cast<double*>(smraw);
   double* xs = Ls + nL;
@@ -1104,42 +1118,58 @@ __device__ void solve_subtree(const DevSym& S, const DevNum& N, const DevSolve& 
   int* meta = chi + nchi;
   FrontDesc* fds = reinterpret_cast<FrontDesc*>(smraw + lay.fd_off());
 
-  if (tid == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this shared memory before the async write
-    mbar_expect_tx(mbar, (unsigned)(nL * 8));
-    bulk_g2s(Ls, N.L + L0, (unsigned long long)nL * 8, mbar);      // the whole subtree's panels: contiguous (postorder)
+  // The panels of the subtree's fronts (those the direct kernel does not own) -> compact shared-memory copy, one bulk copy
+  // per front, issued by as many threads as there are fronts; thread 0 announces the total byte count.
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this shared memory before the async writes
+  if (tid == 0) mbar_expect_tx(mbar, (unsigned)(nL * 8));
+  {
+    const int nown = sd.nown;
+    const int* __restrict__ gfl = V.sub_meta + sd.moff + 2 * nlv + 1;
+    for (int i = tid; i < nown; i += NT) {
+      const int s = gfl[i];
+      const FrontDesc gd = load_fd(V.fdesc + s);
+      const long long pn = ((long long)(gd.k + gd.r) * gd.k + 1) & ~1LL;
+      bulk_g2s(Ls + V.sub_Loff[s], N.L + gd.L_off, (unsigned long long)pn * 8, mbar);
+    }
   }
   // everything else: plain coalesced loads, all in flight together with the bulk copy
-  for (int i = tid; i < ncol; i += DF_THREADS) {
+  for (int i = tid; i < ncol; i += NT) {
     xs[i] = x[col0 + i];
     dinv[i] = N.dinv[col0 + i];
     doff[i] = N.doff[col0 + i];
     lperm[i] = N.lperm[col0 + i];
     ptype[i] = N.ptype[col0 + i];
   }
-  for (int i = tid; i < nrt; i += DF_THREADS) relsub[i] = FWD ? S.rel[ro0 + i] : V.subrow[ro0 + i];
-  for (int i = tid; i < nchi; i += DF_THREADS) chi[i] = S.child_idx[ch00 + i];
-  for (int i = tid; i < nmeta; i += DF_THREADS) meta[i] = V.sub_meta[sd.moff + i];
+  for (int i = tid; i < nrt; i += NT) relsub[i] = FWD ? S.rel[ro0 + i] : V.subrow[ro0 + i];
+  for (int i = tid; i < nchi; i += NT) chi[i] = S.child_idx[ch00 + i];
+  for (int i = tid; i < nmeta; i += NT) meta[i] = V.sub_meta[sd.moff + i];
   {
     const int4* src = reinterpret_cast<const int4*>(V.fdesc + s0);
     int4* dst = reinterpret_cast<int4*>(fds);
-    for (int i = tid; i < 2 * nfront; i += DF_THREADS) dst[i] = src[i];
+    for (int i = tid; i < 2 * nfront; i += NT) {
+      int4 v = src[i];
+      if (i & 1) {                       // second half of descriptor i/2: (L_off, ro) -> L_off = offset in the compact copy
+        const long long lo = (long long)V.sub_Loff[s0 + (i >> 1)];
+        v.x = (int)(unsigned)(lo & 0xffffffffll); v.y = (int)(lo >> 32);
+      }
+      dst[i] = v;
+    }
   }
   if (!FWD) {
     // the root's contribution rows are columns of ancestors: final once the parent front is done
     const int grow = (tid < rroot) ? S.rows[roR + tid] : 0;   // (first chunk's row ids in flight before the wait)
     if (sd.parent >= 0 && tid == 0) wait_eq(V.done_b + sd.parent, epoch);
-    __syncthreads();
+    team_sync(tm);
     if (tid < rroot) rootx[tid] = __ldcg(x + grow);
-    for (int i = tid + DF_THREADS; i < rroot; i += DF_THREADS) rootx[i] = __ldcg(x + S.rows[roR + i]);
+    for (int i = tid + NT; i < rroot; i += NT) rootx[i] = __ldcg(x + S.rows[roR + i]);
   }
   FrontIO io;
-  io.Lbase = Ls; io.L0 = L0; io.xs = xs; io.col0 = col0; io.uv = uv; io.ro0 = ro0;
+  io.Lbase = Ls; io.L0 = 0; io.xs = xs; io.col0 = col0; io.uv = uv; io.ro0 = ro0;
   io.dinv = dinv; io.doff = doff; io.ptype = ptype; io.lperm = lperm;
   io.rel = relsub; io.subrow = relsub; io.rootx = rootx;
   io.fd = fds; io.s0 = s0; io.sR = sR; io.chi = chi; io.ch00 = ch00;
   io.gfd = V.fdesc; io.gcbv = cbv; io.grel = S.rel; io.grows = S.rows; io.gx = x;
-  __syncthreads();
+  team_sync(tm);
   mbar_wait(mbar, mphase);
   if (V.tlog && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
   const int* lvl = meta;              // nlv + 1 offsets into the front list
@@ -1148,28 +1178,28 @@ __device__ void solve_subtree(const DevSym& S, const DevNum& N, const DevSolve& 
   for (int li = 0; li < nlv; ++li) {
     const int e = FWD ? li : nlv - 1 - li;
     const int b = lvl[e], en = lvl[e + 1], ns = nsm[e];
-    for (int q = b + warp; q < b + ns; q += DF_THREADS / 32) {
+    for (int q = b + warp; q < b + ns; q += NT / 32) {
       const int s = fl[q];
       if (FWD) w64_fwd<true>(io, V, s, epoch, wscr + warp * DF_WSCR);
       else w64_bwd<true>(io, V, s, epoch, -1, V.upper_max);
     }
     for (int q = b + ns; q < en; ++q) {   // (mid fronts use their own scratch: no barrier needed before them)
       const int s = fl[q];
-      if (FWD) mid_fwd<true>(io, V, s, epoch, midscr, nullptr, nullptr, 0);
-      else mid_bwd<true>(io, V, s, epoch, -1, midscr, nullptr, nullptr, 0, V.upper_max);
+      if (FWD) mid_fwd<true>(io, V, s, epoch, midscr, nullptr, nullptr, 0, tm);
+      else mid_bwd<true>(io, V, s, epoch, -1, midscr, nullptr, nullptr, 0, V.upper_max, tm);
     }
-    __syncthreads();
+    team_sync(tm);
   }
   // results back to global memory: the x slice (forward: z = D^-1 y in pivot order; backward: the solution), the
   // root's update vector (forward), and the done flags (the root's with release semantics: the parent waits for it)
-  for (int i = tid; i < ncol; i += DF_THREADS) x[col0 + i] = xs[i];
+  for (int i = tid; i < ncol; i += NT) x[col0 + i] = xs[i];
   if (FWD) {
-    for (int i = tid; i < rroot; i += DF_THREADS) cbv[roR + i] = uv[(roR - ro0) + i];
-    for (int i = tid; i < nfront - 1; i += DF_THREADS) V.done_f[s0 + i] = epoch;
+    for (int i = tid; i < rroot; i += NT) cbv[roR + i] = uv[(roR - ro0) + i];
+    for (int i = tid; i < sd.nown; i += NT) { const int s = fl[i]; if (s != sR) V.done_f[s] = epoch; }
   } else {
-    for (int i = tid; i < nfront; i += DF_THREADS) V.done_b[s0 + i] = epoch;
+    for (int i = tid; i < sd.nown; i += NT) V.done_b[fl[i]] = epoch;
   }
-  __syncthreads();
+  team_sync(tm);
   if (FWD && tid == 0) st_release(V.done_f + sR, epoch);
   if (V.tlog && tid == 0) {   // debug: 4 records per subtree after the task records
     unsigned long long t_c;
@@ -1190,6 +1220,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve(DevSym S, DevNum N, Dev
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ unsigned long long s_ticket;
   __shared__ unsigned long long s_mbar;
+  __shared__ unsigned long long s_mbar1;    // second subtree of a pair
   __shared__ int s_flag;
   double* sm = reinterpret_cast<double*>(smraw);                // [0, 8*DF_WSCR + DF_MIDSCR) scratch, then the panel stage
   double* midscr = sm + (DF_THREADS / 32) * DF_WSCR;
@@ -1197,15 +1228,16 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve(DevSym S, DevNum N, Dev
   const long long stage_doubles = (DF_DYN_SMEM / 8) - ((DF_THREADS / 32) * DF_WSCR + DF_MIDSCR);
   const SolveTask* tasks = FWD ? V.tasks : V.tasks_bwd;
   const int ntasks = FWD ? V.ntasks_fwd : V.ntasks_bwd;
-  const unsigned long long total = (unsigned long long)ntasks + V.nsub;
+  const unsigned long long total = (unsigned long long)ntasks + V.npair;
   FrontIO io;
   io.Lbase = N.L; io.L0 = 0; io.xs = x; io.col0 = 0; io.uv = cbv; io.ro0 = 0;
   io.dinv = N.dinv; io.doff = N.doff; io.ptype = N.ptype; io.lperm = N.lperm;
   io.rel = S.rel; io.subrow = nullptr; io.rootx = nullptr;
   io.fd = V.fdesc; io.s0 = 0; io.sR = S.nsn - 1; io.chi = S.child_idx; io.ch00 = 0;
   io.gfd = V.fdesc; io.gcbv = cbv; io.grel = S.rel; io.grows = S.rows; io.gx = x;
-  unsigned mphase = 0;
-  if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+  unsigned mphase = 0, mphase1 = 0;
+  const Team cta{(int)threadIdx.x, DF_THREADS, 0};
+  if (threadIdx.x == 0) { mbar_init(&s_mbar, 1); mbar_init(&s_mbar1, 1); }
   __syncthreads();
   while (true) {
     if (threadIdx.x == 0) s_ticket = atomicAdd(V.ticket + (FWD ? 0 : 1), 1ull) - ticket_base;
@@ -1213,14 +1245,21 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve(DevSym S, DevNum N, Dev
     const unsigned long long tk = s_ticket;
     __syncthreads();
     if (tk >= total) return;
-    const bool is_sub = FWD ? (tk < (unsigned long long)V.nsub) : (tk >= (unsigned long long)ntasks);
+    const bool is_sub = FWD ? (tk < (unsigned long long)V.npair) : (tk >= (unsigned long long)ntasks);
     if (is_sub) {
-      solve_subtree<FWD>(S, N, V, (int)(FWD ? tk : tk - ntasks), epoch, smraw, &s_mbar, mphase, x, cbv);
+      const int2 pr = V.subpair[FWD ? tk : tk - ntasks];
+      // (u0, -1): one subtree by the whole CTA.  (u0, u1): two subtrees side by side -- threads 0..127 walk u0 in the lower
+      // part of the shared memory, threads 128..255 walk u1 above it (own transaction barrier, own hardware barrier).
+      const bool second = pr.y >= 0 && threadIdx.x >= DF_THREADS / 2;
+      const Team tm = pr.y < 0 ? cta : Team{(int)threadIdx.x - (second ? DF_THREADS / 2 : 0), DF_THREADS / 2, second ? 2 : 1};
+      solve_subtree<FWD>(S, N, V, second ? pr.y : pr.x, epoch, second ? smraw + V.subs[pr.x].sbytes : smraw,
+                         second ? &s_mbar1 : &s_mbar, second ? mphase1 : mphase, x, cbv, tm);
       mphase ^= 1;
+      if (pr.y >= 0) mphase1 ^= 1;
       __syncthreads();
       continue;
     }
-    const unsigned long long ti = FWD ? tk - V.nsub : tk;
+    const unsigned long long ti = FWD ? tk - V.npair : tk;
     const SolveTask T = tasks[ti];
     unsigned long long t_start = 0;
     if (V.tlog && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -1248,8 +1287,8 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve(DevSym S, DevNum N, Dev
         Lp = stage; mb = &s_mbar; ph = mphase;
         mphase ^= 1;
       }
-      if (FWD) mid_fwd<false>(io, V, T.s, epoch, midscr, Lp, mb, ph);
-      else mid_bwd<false>(io, V, T.s, epoch, S.sn_parent[T.s], midscr, Lp, mb, ph, V.upper_max);
+      if (FWD) mid_fwd<false>(io, V, T.s, epoch, midscr, Lp, mb, ph, cta);
+      else mid_bwd<false>(io, V, T.s, epoch, S.sn_parent[T.s], midscr, Lp, mb, ph, V.upper_max, cta);
     } else if (T.type == ST_FP) {
       big_fp(S, N, V, T, epoch, sm, &s_flag, x, cbv);
     } else if (T.type == ST_FC) {
@@ -1267,6 +1306,33 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_solve(DevSym S, DevNum N, Dev
       rec[0] = t_start; rec[1] = t_end;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The bottom levels of the tree (fronts of order <= 64 whose descendants are of the same kind: 70 % of all fronts, a third
+// of nnz(L) at level 0 alone) need no task machinery at all: a level has no internal dependencies, so ONE launch per level
+// gives every front its own warp straight from global memory (column loads issued ahead of the shuffle chain) with every
+// warp slot of the GPU busy -- instead of walking them inside the shared-memory subtrees, where they are serialised behind
+// each other on a handful of warps.  Forward: these launches precede k_solve<fwd>; backward: they follow k_solve<bwd>.
+// Their parents find the update vectors in global memory (FrontDesc::direct).
+// ------------------------------------------------------------------------------------------------
+template <bool FWD>
+__global__ void __launch_bounds__(DF_THREADS, 2) k_solve_direct(DevSym S, DevNum N, DevSolve V, const int* __restrict__ list,
+                                                                int cnt, int epoch, double* __restrict__ x,
+                                                                double* __restrict__ cbv) {
+  __shared__ double wscr[(DF_THREADS / 32) * DF_WSCR];
+  const int w = threadIdx.x >> 5;
+  const int g = blockIdx.x * (DF_THREADS / 32) + w;
+  if (g >= cnt) return;
+  FrontIO io;
+  io.Lbase = N.L; io.L0 = 0; io.xs = x; io.col0 = 0; io.uv = cbv; io.ro0 = 0;
+  io.dinv = N.dinv; io.doff = N.doff; io.ptype = N.ptype; io.lperm = N.lperm;
+  io.rel = S.rel; io.subrow = nullptr; io.rootx = nullptr;
+  io.fd = V.fdesc; io.s0 = 0; io.sR = S.nsn - 1; io.chi = S.child_idx; io.ch00 = 0;
+  io.gfd = V.fdesc; io.gcbv = cbv; io.grel = S.rel; io.grows = S.rows; io.gx = x;
+  const int s = list[g];
+  if (FWD) w64_fwd<false>(io, V, s, epoch, wscr + w * DF_WSCR);
+  else w64_bwd<false>(io, V, s, epoch, -1, V.upper_max);
 }
 
 }  // namespace b200

@@ -23,7 +23,7 @@ struct AnalyseOptions {
   int ordering = 0;            // 0 = METIS nested dissection, 1 = natural
   int pair_saddle = 1;         // match zero-diagonal rows with a neighbour (needs values)
   int leaf_k = 32;             // merge whole elimination subtrees of <= leaf_k columns
-  double relax_frac = 0.15;    // relaxed amalgamation: tolerated fraction of explicit zeros
+  double relax_frac = 0.05;    // relaxed amalgamation: tolerated fraction of explicit zeros
   int relax_small = 16;        // always merge a last child when merged k <= relax_small
   int dense_n = 48;            // n <= dense_n: a single dense front, natural order
 };

@@ -12,7 +12,11 @@ NF = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dim, irn, jcn, val, nc = mbndry_kkt(N, sigma_spread=3.0, seed=1)
 _, _, _, v0, _ = mbndry_kkt(N, w_zero=True)
 import os
-s = B200Ldlt(verbose=1, tc_schur_min_r=int(os.environ.get("B200_TC_MIN_R", "0")))
+kw = {}
+if os.environ.get("B200_LEAF_K"): kw["leaf_k"] = int(os.environ["B200_LEAF_K"])
+if os.environ.get("B200_RELAX"): kw["relax_frac"] = float(os.environ["B200_RELAX"])
+if os.environ.get("B200_SMEM_MAX"): kw["smem_front_max"] = int(os.environ["B200_SMEM_MAX"])
+s = B200Ldlt(verbose=1, tc_schur_min_r=int(os.environ.get("B200_TC_MIN_R", "0")), **kw)
 s.InitializeStructure(dim, len(irn), irn, jcn)
 a = s.GetValuesArrayPtr()
 a[:] = v0
