@@ -184,7 +184,8 @@ def main():
     wl_dim = wl_N * wl_N * 2 + 4 * wl_N
     config = {"workload": "MBndryCntrl1 N=%d KKT (dim %d): 1 numeric LDL^T + 2 back-solves per step" % (wl_N, wl_dim),
               "parallelism": ("elimination-tree sharding over %d GPUs" % world) if world > 1 else "single GPU",
-              "l2_policy": "working set (L + contribution blocks: hundreds of MB) exceeds the 126 MB L2; 3 different matrices cycled"}
+              "l2_policy": "working set (L + contribution blocks: hundreds of MB) exceeds the 126 MB L2; 3 different matrices cycled",
+              "scaling_note": "one KKT system per step on all GPUs (strong scaling); --gpus 1 runs BASELINE config 3 (N=400, the metric's configuration), --gpus > 1 config 5 (N=800, the one north_star shards) with its single-GPU time in the same line"}
 
     if args.impl == "reference":
         # CPU path of the same workload (the reference's MUMPS is a third-party library absent from /root/reference and
@@ -195,7 +196,7 @@ def main():
         sec, st = time_oracle(snaps, K, W, cpu_threads)
         line = {"impl": "reference", "metric": "kkt_factor_solve_iters_per_sec", "value": 1.0 / sec, "unit": "iter/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True,
-                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": src, "config": config,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": src, "config": config,
                 "cpu_baseline": {"value": 1.0 / sec, "unit": "iter/s", "cores": cpu_threads, "kind": "port",
                                  "sample": "%d steps (1 factorisation + 2 solves each) of the same KKT snapshots; CPU oracle, NOT MUMPS" % K},
                 "mumps_probe": probe_mumps(),
@@ -365,7 +366,7 @@ def main():
         line = {
             "metric": "kkt_factor_solve_iters_per_sec", "value": world * K / (ms_dev * 1e-3), "unit": "iter/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": src, "config": config,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": src, "config": config,
             "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": "iter/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": 8 * nnz + 2 * 8 * dim, "d2h_bytes_per_step": 2 * 8 * dim + 32},
             "gpu_launches": launches_timed,

@@ -1347,7 +1347,7 @@ void b200ldlt_default_options(b200ldlt_options* o) {
   o->pivtol = 1e-8;
   o->pivtolmax = 1e-4;
   o->tiny = 1e-15;
-  o->smem_front_max = 128;
+  o->smem_front_max = 96;    // measured (profiles/r2_summary.md): 64: 4.84, 96: 4.77, 128: 4.89 ms per N=400 factorisation
   o->tc_schur_min_r = 0;
   o->use_graph = 1;   /* 1 = CUDA-graph replay of the factorisation + dataflow solve; 0 = plain launches; 2 = level-per-launch solve */
   o->verbose = 0;

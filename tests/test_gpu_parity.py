@@ -111,6 +111,33 @@ def test_synthetic_vs_oracle(gen, arg, kw):
     s.close()
 
 
+@pytest.mark.parametrize("env", [
+    {}, {"B200_SOLVE_DIRECT": "0"}, {"B200_SOLVE_DIRECT": "1"}, {"B200_SOLVE_DIRECT": "4"}, {"B200_SOLVE_NOPAIR": "1"},
+    {"B200_NO_WARP2": "1"}, {"B200_NO_PDL": "1"}, {"B200_CB_AT_END": "1"}, {"B200_ONE_STREAM": "1"},
+])
+def test_kernel_variants_agree_with_oracle(env, monkeypatch):
+    """Every A/B switch of the factor / solve pipelines (read once at b200ldlt_create: DESIGN.md section 2) selects another
+    set of kernels for the same mathematics: bottom levels inside the subtrees vs by the direct kernel, one vs two subtrees
+    per CTA, fronts 33..64 in registers vs shared memory, with / without programmatic dependent launch, Schur complement per
+    panel vs per level, one vs five streams.  All of them must reproduce the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for gen, arg, kw in ((mbndry_kkt, 70, dict(sigma_spread=3.0, seed=5)), (lukvle1_kkt, 2000, dict(sigma_spread=2.0, seed=6))):
+        dim, irn, jcn, val, nc = gen(arg, **kw)
+        b = np.random.default_rng(11).standard_normal(dim)
+        xo, nego = oracle_solution(dim, irn, jcn, val, b)
+        s = gpu_solver(dim, irn, jcn)
+        s.GetValuesArrayPtr()[:] = val
+        st, neg = s.factor(True, nego)
+        assert st == SYMSOLVER_SUCCESS and neg == nego, (env, s.info())
+        for _ in range(2):          # (twice: the solve flags are epoch-stamped, not cleared)
+            x = b.copy()
+            assert s.solve(x) == SYMSOLVER_SUCCESS
+            assert scaled_residual(dim, irn, jcn, val, x, b) < 1e-12, env
+            assert np.linalg.norm(x - xo) <= max(RTOL, 1e3 * scaled_residual(dim, irn, jcn, val, xo, b)) * np.linalg.norm(xo), env
+        s.close()
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_random_saddle_point_inertia_and_solution(seed):
     dim, irn, jcn, val, nc = random_kkt(150 + 40 * seed, 60 + 10 * seed, density=0.03, seed=seed)
