@@ -992,6 +992,7 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       }
     }
     if (P.big_cnt) sv->mark("big-assemble", l);
+    unsigned used_side = 0;
     {
       // the front classes of a level are independent: issue them side by side (forked from / joined to the main stream)
       const bool fork = !sv->dbg.one_stream && (P.small.size() + (P.big_cnt ? 1 : 0)) > 1;
@@ -1016,11 +1017,9 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
           k_front_smem<false><<<bk.cnt, bk.threads, bk.smem, sq>>>(D, N, fl + bk.off, bk.cnt, 0); ++L;
         }
       }
-      for (int q = 0; q < 4; ++q) if (used & (1u << q)) {
-        cudaEvent_t e = sv->next_event();
-        CU(cudaEventRecord(e, sv->side[q]));
-        CU(cudaStreamWaitEvent(st, e, 0));
-      }
+      used_side = used;
+      // (the side streams are joined at the END of the level: this level's big fronts do not depend on its small fronts,
+      //  so the panel chain below runs next to them)
     }
     sv->mark("small-fronts", l);
     if (P.big_cnt) {
@@ -1098,6 +1097,11 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       if (!cb_panel && P.df_cnt > 0) {
         k_big_schur84<<<dim3(cdiv(P.df_rmax, TM), cdiv(P.df_rmax, TM), P.df_cnt), 128, 0, st>>>(D, N, SL.d_dfl.p + P.df_off); ++L;
       }
+    }
+    for (int q = 0; q < 4; ++q) if (used_side & (1u << q)) {     // join the small-front streams of this level
+      cudaEvent_t e = sv->next_event();
+      CU(cudaEventRecord(e, sv->side[q]));
+      CU(cudaStreamWaitEvent(st, e, 0));
     }
   }
   sv->mark("big-schur(last)", S.nlevels);

@@ -1,24 +1,24 @@
-// Supernodal triangular solve (forward L, D^-1, backward L^T): TWO kernels per sweep.
+// Supernodal triangular solve (forward L, D^-1, backward L^T).  Per right-hand side and sweep:
 //
-//   k_solve_sub<FWD> : the BOTTOM of the elimination tree.  The tree below the big separator fronts is cut into
-//                      subtrees whose whole working set -- the L panels (contiguous in memory: supernodes are numbered in
-//                      postorder), right-hand side, D, permutations, row maps, front descriptors -- fits in shared memory.
-//                      ONE CTA owns one subtree: a single TMA bulk copy (cp.async.bulk + mbarrier) brings the L panels
-//                      in, then the CTA walks the subtree level by level out of shared memory -- fronts of order <= 64
-//                      one warp each, larger ones by the whole CTA -- with CTA barriers only: no global flags, no
-//                      tickets, no atomics, no dependent global loads on the critical path; update vectors between the
-//                      fronts of a subtree never leave shared memory.  Subtrees are launched largest first (the
-//                      hardware block scheduler then does LPT scheduling); two CTAs per SM overlap one subtree's bulk
-//                      load with the other's arithmetic.
-//   k_solve_top<FWD> : everything above the subtrees: a persistent task-queue kernel.  Fronts up to order 256 are one
-//                      task each (panel staged in shared memory by a bulk copy when it fits); a front larger than that
-//                      is cut into (64-row block) x (2-tile chunk) GEMV tasks on the EXPLICIT inverse of its pivot
-//                      block (k_linv_*), so a separator front of order 1000+ keeps ~100 CTAs busy instead of a chain of
-//                      block steps.  A task waits for its producers through ld.acquire/st.release flags; it only ever
-//                      waits for tasks EARLIER in the (topologically sorted) list and every ticket holder is resident,
-//                      so the scheme cannot deadlock.  Chunk partials are combined by the last-arriving CTA in chunk
-//                      order (fence + counter), so results do not depend on arrival order: bit-reproducible.
-// Forward: sub then top; backward: top then sub (the kernel boundary is the only synchronisation between the two).
+//   k_solve_direct<FWD> : the lowest tree levels (fronts of order <= 64 whose children are of the same kind).  A level has
+//                      no internal dependencies: one launch per level, one warp per front straight from global memory.
+//   k_solve<FWD>      : ONE persistent kernel for everything else; CTAs take work items with an atomic ticket.
+//     subtree items   : the tree below the big separator fronts is cut into subtrees whose whole working set -- the L
+//                      panels of the fronts walked here, right-hand side, D, permutations, row maps, front descriptors --
+//                      fits in shared memory.  TMA bulk copies (cp.async.bulk + mbarrier, one per front, compact layout)
+//                      bring the panels in, then the subtree is walked level by level out of shared memory -- fronts of
+//                      order <= 64 one warp each, larger ones by the team -- with hardware barriers only: no global flags,
+//                      no atomics, no dependent global loads on the critical path; update vectors between the fronts of a
+//                      subtree never leave shared memory.  A team is the whole CTA, or one half of it when two subtrees
+//                      fit the shared memory together (named barriers, one transaction barrier each).  Largest first.
+//     top tasks       : everything above the subtrees.  Fronts up to order 256 are one task each (panel staged in shared
+//                      memory by a bulk copy when it fits); a front larger than that is cut into (64-row block) x (2-tile
+//                      chunk) GEMV tasks on the EXPLICIT inverse of its pivot block (k_linv_*), so a separator front of
+//                      order 1000+ keeps ~100 CTAs busy instead of a chain of block steps.  A task waits for its producers
+//                      through ld.acquire/st.release flags; it only ever waits for tasks EARLIER in the (topologically
+//                      sorted) list and every ticket holder is resident, so the scheme cannot deadlock.  Chunk partials
+//                      are combined by the last-arriving CTA in chunk order (fence + counter): bit-reproducible.
+// Forward: direct levels, then subtrees before top tasks; backward: top tasks before subtrees, then the direct levels.
 // L is streamed exactly once per sweep (HBM-bound, SURVEY.md 8d: 2*8*nnz(L) bytes per right-hand side); children ->
 // parent data flows through per-front update vectors gathered by the parent (no atomics on the data path).
 // Replaces the vendor back-solve of the reference (MUMPS job=3,
