@@ -962,11 +962,13 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
     k_apply_scale<<<cdiv(nu, 256), 256, 0, st>>>(nu, sv->d_u_row.p, sv->d_u_col.p, sv->d_scale.p, sv->d_uval.p); ++L;
   }
   }  // prologue
-  // storage of all big fronts of this plan is cleared up front on the bulk stream (overlaps the leaf levels)
+  // storage of all big fronts of this plan is cleared up front on the third stream (idle until the first L11 inverse),
+  // level by level with one event per level: a level's big fronts wait for THEIR storage only, the leaf levels run next to it
   bool any_big = false;
   for (int l = 0; l < S.nlevels; ++l) any_big = any_big || plan[l].big_cnt > 0;
+  std::vector<cudaEvent_t> ev_zero_lvl(S.nlevels, nullptr);
   if (any_big) {
-    cudaStream_t sz = sv->dbg.one_stream ? st : sv->stream2;
+    cudaStream_t sz = sv->dbg.one_stream ? st : sv->stream3;
     cudaEvent_t e0 = sv->next_event();
     CU(cudaEventRecord(e0, st));
     CU(cudaStreamWaitEvent(sz, e0, 0));
@@ -976,17 +978,17 @@ static int enqueue_factor(Solver* sv, const std::vector<LevelPlan>* plan_p = nul
       k_big_zero<<<dim3(std::min<unsigned>(cdiv(P.big_zero_max, 1024), 592), P.big_cnt), 256, 0, sz>>>(D, N, fl + P.big_off); ++L;
       // ... and the original entries scattered in (they do not depend on the children either)
       k_big_assemble<<<dim3(std::max(1u, std::min<unsigned>(cdiv(P.big_entmax, 256), 64)), P.big_cnt), 256, 0, sz>>>(D, N, fl + P.big_off); ++L;
+      ev_zero_lvl[l] = sv->next_event();
+      CU(cudaEventRecord(ev_zero_lvl[l], sz));
     }
-    sv->ev_zero = sv->next_event();
-    CU(cudaEventRecord(sv->ev_zero, sz));
   }
-  bool zero_waited = false, linv_forked = false;
+  bool linv_forked = false;
   sv->mark("prologue", -1);
   for (int l = 0; l < S.nlevels; ++l) {
     const LevelPlan& P = plan[l];
     if (P.big_cnt) {
       const int* bl = fl + P.big_off;
-      if (!zero_waited) { CU(cudaStreamWaitEvent(st, sv->ev_zero, 0)); zero_waited = true; }
+      if (ev_zero_lvl[l]) CU(cudaStreamWaitEvent(st, ev_zero_lvl[l], 0));
       if (P.big_chmax > 0) {
         k_big_extend_all<<<dim3(cdiv(P.big_fmax, 8), P.big_cnt), 256, 0, st>>>(D, N, bl); ++L;
       }
