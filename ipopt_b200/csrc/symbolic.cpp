@@ -355,24 +355,61 @@ int analyse(int n, int64_t nnz, const int* irn, const int* jcn, const double* va
 
   lap("5 etree/postorder/relabel");
   // ---- 6. column counts (pass 1) --------------------------------------------------------------
+  // Skeleton-graph algorithm (Gilbert, Ng, Peyton 1994): entry (i, j), i > j, of the permuted matrix makes j a LEAF of the
+  // row subtree of i iff j's first descendant lies beyond every leaf seen so far; every new leaf adds one to the count of j
+  // and takes one from the least common ancestor with the previous leaf (found with a path-halving disjoint-set forest).
+  // O(nnz(A) alpha(n)) instead of walking the nnz(L) structure.  The columns are already numbered in postorder, so the
+  // first descendant of j is j - size(j) + 1.
   std::vector<int> cc(n, 1);
   {
-    std::vector<std::vector<int>> st(n);
-    std::vector<int> mark(n, -1);
-    for (int j = 0; j < n; ++j) {
-      std::vector<int>& out = st[j];
-      int old = perm[j];
-      for (int64_t p = xadj[old]; p < xadj[old + 1]; ++p) {
-        int i = iperm[adj[p]];
-        if (i > j && mark[i] != j) { mark[i] = j; out.push_back(i); }
-      }
-      for (int c = chead[j]; c >= 0; c = cnext[c]) {
-        for (int i : st[c]) if (i != j && mark[i] != j) { mark[i] = j; out.push_back(i); }
-        std::vector<int>().swap(st[c]);
-      }
-      cc[j] = (int)out.size() + 1;
-      S.nnzL_true += cc[j];
+    std::vector<int> first(n), delta(n), maxfirst(n, -1), prevleaf(n, -1), anc(n);
+    {
+      std::vector<int> sz(n, 1);
+      for (int j = 0; j < n; ++j) if (parent[j] >= 0) sz[parent[j]] += sz[j];
+      for (int j = 0; j < n; ++j) { first[j] = j - sz[j] + 1; delta[j] = (sz[j] == 1) ? 1 : 0; }
     }
+    std::iota(anc.begin(), anc.end(), 0);
+    auto find = [&](int v) {
+      while (anc[v] != v) { anc[v] = anc[anc[v]]; v = anc[v]; }
+      return v;
+    };
+    for (int j = 0; j < n; ++j) {
+      if (parent[j] >= 0) delta[parent[j]]--;        // j is not a root: its parent's count loses the overlap
+      const int old = perm[j];
+      for (int64_t p = xadj[old]; p < xadj[old + 1]; ++p) {
+        const int i = iperm[adj[p]];
+        if (i <= j || first[j] <= maxfirst[i]) continue;
+        maxfirst[i] = first[j];
+        const int jprev = prevleaf[i];
+        prevleaf[i] = j;
+        delta[j]++;                                   // j is a leaf of the row subtree of i
+        if (jprev >= 0) delta[find(jprev)]--;         // ... a subsequent one: the path above the lca was counted before
+      }
+      if (parent[j] >= 0) anc[j] = parent[j];
+    }
+    for (int j = 0; j < n; ++j) cc[j] = delta[j];
+    for (int j = 0; j < n; ++j) if (parent[j] >= 0) cc[parent[j]] += cc[j];
+    if (getenv("B200_SYMBOLIC_CHECK")) {              // debug: the explicit column structures, one column at a time
+      std::vector<std::vector<int>> st(n);
+      std::vector<int> mark(n, -1);
+      long long bad = 0;
+      for (int j = 0; j < n; ++j) {
+        std::vector<int>& out = st[j];
+        int old2 = perm[j];
+        for (int64_t p = xadj[old2]; p < xadj[old2 + 1]; ++p) {
+          int i = iperm[adj[p]];
+          if (i > j && mark[i] != j) { mark[i] = j; out.push_back(i); }
+        }
+        for (int c = chead[j]; c >= 0; c = cnext[c]) {
+          for (int i : st[c]) if (i != j && mark[i] != j) { mark[i] = j; out.push_back(i); }
+          std::vector<int>().swap(st[c]);
+        }
+        if (cc[j] != (int)out.size() + 1) ++bad;
+      }
+      fprintf(stderr, "[symbolic] column-count check: %lld of %d columns differ\n", bad, n);
+      if (bad) { err = "column count self-check failed"; return -6; }
+    }
+    for (int j = 0; j < n; ++j) S.nnzL_true += cc[j];
   }
 
   lap("6 column counts");

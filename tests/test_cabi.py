@@ -63,7 +63,7 @@ def test_options_struct_layout_roundtrip(built_lib):
     o = capi.Options()
     L.b200ldlt_default_options(ctypes.byref(o))
     assert o.device == -1 and o.pair_saddle == 1 and o.leaf_k == 32
-    assert o.pivtol == 1e-8 and o.pivtolmax == 1e-4 and o.smem_front_max == 128 and o.scaling == 2 and o.use_graph == 1
+    assert o.pivtol == 1e-8 and o.pivtolmax == 1e-4 and o.smem_front_max == 96 and o.scaling == 2 and o.use_graph == 1
 
 
 def test_product_does_not_link_the_oracle(built_lib):
