@@ -97,3 +97,15 @@ def test_stats_match_survey_sizes(built_lib):
     assert dim == 1920 and len(irn) == 7440
     dim, irn, jcn, val, nc = lukvle1_kkt(1000)
     assert dim == 1998 and len(irn) == 6991
+
+
+@pytest.mark.parametrize("gen,arg,kw", [(mbndry_kkt, 40, dict(w_zero=True)), (lukvle1_kkt, 5000, dict(w_zero=True)),
+                                        (random_kkt, (700, 250), dict(density=0.02, seed=4)), (mbndry_kkt, 9, dict(sigma_spread=2.0, seed=1))])
+def test_column_counts_match_the_explicit_structures(built_lib, gen, arg, kw, monkeypatch):
+    """The skeleton-graph column counts of the analysis (symbolic.cpp step 6) against the explicit column structures built
+    one column at a time (B200_SYMBOLIC_CHECK makes the analysis fail on any difference)."""
+    monkeypatch.setenv("B200_SYMBOLIC_CHECK", "1")
+    dim, irn, jcn, val, nc = gen(*arg, **kw) if isinstance(arg, tuple) else gen(arg, **kw)
+    S = SymbolicAnalysis(dim, irn, jcn, val)
+    assert S.stats()["nnzL_true"] > 0
+    _check_structure(S, dim)
